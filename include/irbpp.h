@@ -1,0 +1,160 @@
+/*
+ * irbpp.h -- C ABI of the B200-native IR-BPP packing-environment hot path.
+ *
+ * The reference (alexfrom0815/IR-BPP) has no FFI layer: its boundary is the Python VecEnv class
+ * contract of envs.py:67-165 / wrapper/vec_env.py:29-108 / wrapper/shmem_vec_env.py:20-157.
+ * Each entry point below states the reference interface it replaces (paths relative to the
+ * reference root).  Host code (Python `irbpp_b200.vec_env.GpuVecEnv`) binds these with ctypes;
+ * INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++ / torch types cross this boundary
+ *   - every function returns 0 on success or a negative IRBPP_E* code; the message is available
+ *     from irbpp_last_error(handle) (thread-unsafe per handle; one host thread per handle)
+ *   - "dev" pointers are CUDA device pointers owned by the caller (e.g. torch tensors);
+ *     "host" pointers are ordinary host memory owned by the caller
+ *   - all GPU work is ordered on the `stream` argument (a cudaStream_t passed as void*, NULL =
+ *     default stream); the library owns its internal state and result staging buffers
+ *   - there is no CPU fallback: without a CUDA device irbpp_create fails with IRBPP_ECUDA
+ */
+#ifndef IRBPP_H_
+#define IRBPP_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IRBPP_ABI_VERSION 1
+
+#define IRBPP_OK        0
+#define IRBPP_EINVAL   -1   /* bad argument / unsupported configuration */
+#define IRBPP_ECUDA    -2   /* CUDA runtime error */
+#define IRBPP_ESTATE   -3   /* call order violated (e.g. step_async twice; vec_env.py:7-26) */
+#define IRBPP_EDEVICE  -4   /* a kernel flagged an environment error (see irbpp_last_error) */
+
+typedef struct irbpp_env* irbpp_handle;
+
+/* PackingGame.__init__ / Space.__init__ settings that reach the hot path
+ * (environment/physics0/binPhy.py:25-49, space.py:15-24, arguments.py:11-96,115). */
+typedef struct irbpp_config {
+    int32_t num_envs;          /* N bins resident on this GPU (args.num_processes) */
+    int32_t num_rotations;     /* ZRotNum = --resolutionRot (arguments.py:85,117) */
+    int32_t selected_action;   /* --selectedAction, candidate rows per observation (default 500) */
+    int32_t buffer_size;       /* --bufferSize k; k > 1 selects the order->location protocol */
+    double  bin_dimension[3];  /* [0.32, 0.32, 0.30] (arguments.py:115) */
+    double  resolution_act;    /* --resolutionA 0.02 */
+    double  resolution_h;      /* --resolutionH 0.01 */
+    double  resolution_z;      /* --resolutionZ 0.01 (cvTools.py:77 heightResolution) */
+    int32_t device;            /* CUDA device ordinal */
+    int32_t approx_legacy;     /* 0: approxPolyDP as cv2 4.13 (segment distance); 1: legacy line distance */
+} irbpp_config;
+
+/* Host views of the per-env results of the last step (library-owned pinned memory, valid until the
+ * next irbpp_step_async on the handle).  Replaces the (rews, dones, infos) tuple of
+ * ShmemVecEnv.step_wait (wrapper/shmem_vec_env.py:76-81) and the Monitor episode info
+ * (wrapper/monitor.py:58-75). */
+typedef struct irbpp_step_result {
+    const float*   reward;      /* [N]  10*volume/bin_volume on success, 0 otherwise (binPhy.py:299-322) */
+    const uint8_t* done;        /* [N]  1 when the placement failed and the bin was auto-reset */
+    const uint8_t* valid;       /* [N]  info['Valid'] (always 1 without the PyBullet settle) */
+    const uint8_t* error;       /* [N]  non-zero: kernel-detected error for that env */
+    const int32_t* counter;     /* [N]  info['counter'] = items packed, meaningful where done */
+    const int32_t* ep_len;      /* [N]  info['episode']['l'], meaningful where done */
+    const double*  ratio;       /* [N]  info['ratio'] = packed volume / bin volume, where done */
+    const double*  ep_reward;   /* [N]  unrounded sum of episode rewards (Monitor rounds to 6 dp) */
+} irbpp_step_result;
+
+/* Device-resident copies of the same arrays (for callers that keep the loop on the GPU). */
+typedef struct irbpp_device_result {
+    const float*   reward;
+    const uint8_t* done;
+    const uint8_t* valid;
+    const uint8_t* error;
+    const int32_t* counter;
+    const int32_t* ep_len;
+    const double*  ratio;
+    const double*  ep_reward;
+} irbpp_device_result;
+
+int irbpp_abi_version(void);
+
+/* Replaces: make_vec_envs + N x PackingGame(args) construction (envs.py:67-99, binPhy.py:22-116). */
+int irbpp_create(const irbpp_config* cfg, irbpp_handle* out);
+int irbpp_destroy(irbpp_handle h);
+const char* irbpp_last_error(irbpp_handle h);   /* h may be NULL: error of the last failed create */
+
+/* Observation lengths: binPhy.py:87-98.  loc = selected_action*5 + 9 + Hx*Hy; order = k + Hx*Hy;
+ * obs_len = (k > 1) ? order : loc. */
+int irbpp_obs_len(irbpp_handle h, int32_t* obs_len, int32_t* loc_obs_len, int32_t* order_obs_len);
+
+/* Replaces: args.shotInfo / args.shapeDict / args.infoDict (tools.py:248-279, binPhy.py:31-33).
+ * Host arrays: dims[S,R,4] = (w, h, wA, hA) from space.py:104-106; ext[S,R,3] raw mesh extents;
+ * vol[S]; maps = float64 pool with the four [w,h] row-major tables T | B | maskT | maskB of (s,r)
+ * starting at offsets[s,r] (in doubles). */
+int irbpp_load_shapes(irbpp_handle h, int32_t num_shapes, int32_t num_rotations,
+                      const int32_t* dims, const double* ext, const double* vol,
+                      const double* maps, const int64_t* offsets, int64_t maps_len);
+
+/* Replaces: the item creators (environment/physics0/IRcreator.py:6-103).  ids[N,L] host int32; env e
+ * draws ids[e, cursor % L] on every generate_item; the cursor persists across episodes. */
+int irbpp_set_sequences(irbpp_handle h, const int32_t* ids, int32_t length);
+
+/* Replaces: envs.reset() (envs.py:149-152 -> ShmemVecEnv.reset, shmem_vec_env.py:60-66; and
+ * reset_specific, :113-118, when `which` (host uint8[N], 1 = reset) is not NULL).
+ * obs_out: dev float32 [N, obs_len]; rows of envs not reset are left untouched. */
+int irbpp_reset(irbpp_handle h, const uint8_t* which, float* obs_out, void* stream);
+
+/* Replaces: envs.step_async (envs.py:154-159 -> shmem_vec_env.py:70-74).  actions: int64[N], a host
+ * pointer (copied through pinned staging) or a device pointer when actions_on_device != 0.
+ * obs_out: dev float32 [N, obs_len], written in stream order.  Returns IRBPP_ESTATE if a step is
+ * already pending. */
+int irbpp_step_async(irbpp_handle h, const int64_t* actions, int32_t actions_on_device,
+                     float* obs_out, void* stream);
+
+/* Replaces: envs.step_wait (envs.py:161-165 -> shmem_vec_env.py:76-81).  Copies the per-env results to
+ * pinned host memory, synchronises the step's stream and fills *out.  out may be NULL (sync only). */
+int irbpp_step_wait(irbpp_handle h, irbpp_step_result* out);
+
+/* Device-side loop variant: marks the pending step as consumed without any host copy or sync and
+ * returns device views of the result arrays (valid in stream order). */
+int irbpp_step_wait_device(irbpp_handle h, irbpp_device_result* out);
+
+/* Replaces: envs.get_action_candidates(order_actions) (wrapper/shmem_vec_env.py:99-102 ->
+ * binPhy.py:161-169), buffer_size > 1 only.  order_actions: int64[N] host or device.
+ * loc_obs_out: dev float32 [N, loc_obs_len]. */
+int irbpp_get_action_candidates(irbpp_handle h, const int64_t* order_actions, int32_t on_device,
+                                float* loc_obs_out, void* stream);
+
+/* Replaces: PackingGame.get_all_possible_observation (binPhy.py:171-180), buffer_size > 1 only.
+ * out: dev float32 [N, k * loc_obs_len].  Leaves the candidate state of slot k-1 current. */
+int irbpp_get_all_possible_observation(irbpp_handle h, float* out, void* stream);
+
+/* ---- parity / debugging views (float64, host destinations; any pointer may be NULL) ---- */
+
+/* Current bin state: heightmap [N,Hx,Hy] row-major, the candidate table [N,selected_action,5]
+ * (rot, x, y decoded from the packed state; H and V columns are 0), next item ids [N, max(k,1)]. */
+int irbpp_debug_state(irbpp_handle h, double* heightmap, int32_t* queue, int32_t* cursor,
+                      int32_t* packed_count);
+int irbpp_debug_set_heightmap(irbpp_handle h, const double* heightmap /* host [N,Hx,Hy] */);
+
+/* Run the scan + candidate extraction of space.py:98-129 / cvTools.py:61-103 / binPhy.py:205-225 for
+ * item_ids[N] (host int32) on the CURRENT heightmaps without touching env state.  Host outputs:
+ * posZmap, posZValid, naiveMask float64 [N,R,Ax,Ay]; cand float64 [N,selected_action,5];
+ * num_hull int32 [N] = K before select/pad (0 = fallback path taken). */
+int irbpp_debug_scan(irbpp_handle h, const int32_t* item_ids, double* posZmap, double* posZValid,
+                     double* naiveMask, double* cand, int32_t* num_hull);
+
+/* Candidate extraction alone on caller-supplied maps: posZValid, mask host float64 [N,R,Ax,Ay] ->
+ * cand [N,selected_action,5], num_hull [N]  (cvTools.getConvexHullActions + binPhy.py:205-225). */
+int irbpp_debug_hulls(irbpp_handle h, const double* posZValid, const double* mask, double* cand,
+                      int32_t* num_hull);
+
+/* Kernel launches issued by this handle so far (bench.py's gpu_launches). */
+int64_t irbpp_launch_count(irbpp_handle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IRBPP_H_ */

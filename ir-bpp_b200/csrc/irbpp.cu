@@ -1,0 +1,492 @@
+// irbpp.cu -- C-ABI (include/irbpp.h) host side: state ownership, table preprocessing, launches.
+//
+// No CPU fallback lives here: every entry point that computes anything launches irbpp_env_kernel.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/irbpp.h"
+#include "irbpp_kernels.cuh"
+
+using namespace irbpp;
+
+static std::string g_create_error;
+
+struct irbpp_env {
+    irbpp_config cfg;
+    Params P;                      // device pointers + configuration (mode/inputs filled per launch)
+    SmemLayout SL;
+    std::string err;
+    bool shapes_loaded = false, sequences_set = false, was_reset = false, waiting_step = false;
+    cudaStream_t pending_stream = nullptr;
+    int64_t launches = 0;
+    // device allocations
+    std::vector<void*> dev_allocs;
+    void* results_dev = nullptr;   // one block: ratio | ep_reward | reward | counter | ep_len | done | valid | error
+    void* results_host = nullptr;  // pinned mirror
+    size_t results_bytes = 0;
+    int64_t* actions_dev = nullptr;
+    int64_t* actions_pinned = nullptr;
+    uint8_t* which_dev = nullptr;
+    // shape pools
+    ShapeRot* srot_dev = nullptr; double* Bs_dev = nullptr; double* Ts_dev = nullptr;
+    double* vol_dev = nullptr; double* rew_dev = nullptr; int32_t* seq_dev = nullptr;
+};
+
+static int fail(irbpp_env* h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (h) h->err = buf; else g_create_error = buf;
+    return code;
+}
+
+#define CUDA_TRY(h, expr)                                                                         \
+    do {                                                                                          \
+        cudaError_t e_ = (expr);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return fail(h, IRBPP_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(e_));          \
+    } while (0)
+
+template <class T>
+static cudaError_t dev_alloc(irbpp_env* h, T** p, size_t count, bool zero = true) {
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, count * sizeof(T) + 16);
+    if (e != cudaSuccess) return e;
+    if (zero) { e = cudaMemset(q, 0, count * sizeof(T) + 16); if (e != cudaSuccess) return e; }
+    h->dev_allocs.push_back(q);
+    *p = reinterpret_cast<T*>(q);
+    return cudaSuccess;
+}
+
+// np.round(x, 6): multiply, rint, divide
+static inline double np_round6(double x) { return rint(x * 1e6) / 1e6; }
+
+extern "C" {
+
+int irbpp_abi_version(void) { return IRBPP_ABI_VERSION; }
+
+const char* irbpp_last_error(irbpp_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int irbpp_create(const irbpp_config* cfg, irbpp_handle* out) {
+    if (!cfg || !out) return fail(nullptr, IRBPP_EINVAL, "null argument");
+    *out = nullptr;
+    if (cfg->num_envs <= 0) return fail(nullptr, IRBPP_EINVAL, "num_envs must be positive");
+    if (cfg->num_rotations < 1 || cfg->num_rotations > 32)
+        return fail(nullptr, IRBPP_EINVAL, "num_rotations must be in [1, 32]");
+    if (cfg->buffer_size < 1 || cfg->buffer_size > MAX_QUEUE)
+        return fail(nullptr, IRBPP_EINVAL, "buffer_size must be in [1, %d]", MAX_QUEUE);
+    if (cfg->selected_action < 1 || cfg->selected_action > 4096)
+        return fail(nullptr, IRBPP_EINVAL, "selected_action must be in [1, 4096]");
+    // grid sizes exactly as Space.__init__ computes them (space.py:19-24)
+    const double stepf = cfg->resolution_act / cfg->resolution_h;
+    const int step = (int)stepf;
+    const int hx = (int)ceil(cfg->bin_dimension[0] / cfg->resolution_h), hy = (int)ceil(cfg->bin_dimension[1] / cfg->resolution_h);
+    const int ax = (int)ceil(cfg->bin_dimension[0] / cfg->resolution_act), ay = (int)ceil(cfg->bin_dimension[1] / cfg->resolution_act);
+    if ((double)step != stepf || step != STEP || hx != HX || hy != HY || ax != AX || ay != AY)
+        return fail(nullptr, IRBPP_EINVAL,
+                    "unsupported grid: heightmap %dx%d, actions %dx%d, step %g (this build: %dx%d, %dx%d, %d)",
+                    hx, hy, ax, ay, stepf, HX, HY, AX, AY, STEP);
+    if (cfg->selected_action > cfg->num_rotations * NPOSE)
+        return fail(nullptr, IRBPP_EINVAL, "selected_action exceeds the number of poses (reference fallback "
+                                           "binPhy.py:217-225 would return a short table)");
+    if (!(cfg->resolution_z > 0) || ceil(cfg->bin_dimension[2] / cfg->resolution_z) + 1 >= LEVEL_OFFSET)
+        return fail(nullptr, IRBPP_EINVAL, "bin height / resolution_z must stay below %d levels", LEVEL_OFFSET - 1);
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, IRBPP_ECUDA, "no CUDA device (%s); this library has no CPU path",
+                    e == cudaSuccess ? "count 0" : cudaGetErrorString(e));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, IRBPP_EINVAL, "bad device ordinal %d", cfg->device);
+    e = cudaSetDevice(cfg->device);
+    if (e != cudaSuccess) return fail(nullptr, IRBPP_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+
+    irbpp_env* h = new irbpp_env();
+    h->cfg = *cfg;
+    Params& P = h->P;
+    memset(&P, 0, sizeof(P));
+    const int N = cfg->num_envs;
+    P.N = N; P.R = cfg->num_rotations; P.sel = cfg->selected_action; P.K = cfg->buffer_size;
+    P.loc_len = P.sel * 5 + 9 + HX * HY;
+    P.order_len = P.K + HX * HY;
+    P.obs_stride = (P.K > 1) ? P.order_len : P.loc_len;
+    P.legacy = cfg->approx_legacy;
+    P.binz = cfg->bin_dimension[2];
+    P.resZ = cfg->resolution_z;
+    P.binvol = (cfg->bin_dimension[0] * cfg->bin_dimension[1]) * cfg->bin_dimension[2];   // np.prod
+    h->SL = smem_layout(P.R, P.sel);
+
+#define TRY_ALLOC(expr)                                                                          \
+    do { cudaError_t e2_ = (expr); if (e2_ != cudaSuccess) {                                      \
+        fail(nullptr, IRBPP_ECUDA, "%s: %s", #expr, cudaGetErrorString(e2_)); irbpp_destroy(h); return IRBPP_ECUDA; } } while (0)
+    TRY_ALLOC(dev_alloc(h, &P.hm, (size_t)N * HX * HY));
+    TRY_ALLOC(dev_alloc(h, &P.cand, (size_t)N * P.sel));
+    TRY_ALLOC(dev_alloc(h, &P.queue, (size_t)N * MAX_QUEUE));
+    TRY_ALLOC(dev_alloc(h, &P.cursor, N)); TRY_ALLOC(dev_alloc(h, &P.cur_item, N));
+    TRY_ALLOC(dev_alloc(h, &P.order_act, N)); TRY_ALLOC(dev_alloc(h, &P.packed, N));
+    TRY_ALLOC(dev_alloc(h, &P.ep_len, N)); TRY_ALLOC(dev_alloc(h, &P.vol_sum, N));
+    TRY_ALLOC(dev_alloc(h, &P.ep_rew, N)); TRY_ALLOC(dev_alloc(h, &P.mask_any, N));
+    TRY_ALLOC(dev_alloc(h, &h->actions_dev, N)); TRY_ALLOC(dev_alloc(h, &h->which_dev, N));
+    // result block (8-byte fields first so every array stays aligned)
+    h->results_bytes = (size_t)N * (8 + 8 + 4 + 4 + 4 + 1 + 1 + 1);
+    TRY_ALLOC(cudaMalloc(&h->results_dev, h->results_bytes + 64));
+    TRY_ALLOC(cudaMemset(h->results_dev, 0, h->results_bytes + 64));
+    TRY_ALLOC(cudaMallocHost(&h->results_host, h->results_bytes + 64));
+    memset(h->results_host, 0, h->results_bytes + 64);
+    TRY_ALLOC(cudaMallocHost((void**)&h->actions_pinned, (size_t)N * sizeof(int64_t)));
+    {
+        char* b = reinterpret_cast<char*>(h->results_dev);
+        P.r_ratio = reinterpret_cast<double*>(b); b += (size_t)N * 8;
+        P.r_eprew = reinterpret_cast<double*>(b); b += (size_t)N * 8;
+        P.r_reward = reinterpret_cast<float*>(b); b += (size_t)N * 4;
+        P.r_counter = reinterpret_cast<int32_t*>(b); b += (size_t)N * 4;
+        P.r_eplen = reinterpret_cast<int32_t*>(b); b += (size_t)N * 4;
+        P.r_done = reinterpret_cast<uint8_t*>(b); b += N;
+        P.r_valid = reinterpret_cast<uint8_t*>(b); b += N;
+        P.r_error = reinterpret_cast<uint8_t*>(b);
+    }
+    TRY_ALLOC(cudaFuncSetAttribute(irbpp_env_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->SL.total));
+#undef TRY_ALLOC
+    *out = h;
+    return IRBPP_OK;
+}
+
+int irbpp_destroy(irbpp_handle h) {
+    if (!h) return IRBPP_OK;
+    cudaSetDevice(h->cfg.device);
+    cudaDeviceSynchronize();
+    for (void* p : h->dev_allocs) cudaFree(p);
+    if (h->results_dev) cudaFree(h->results_dev);
+    if (h->results_host) cudaFreeHost(h->results_host);
+    if (h->actions_pinned) cudaFreeHost(h->actions_pinned);
+    delete h;
+    return IRBPP_OK;
+}
+
+int irbpp_obs_len(irbpp_handle h, int32_t* obs_len, int32_t* loc_obs_len, int32_t* order_obs_len) {
+    if (!h) return IRBPP_EINVAL;
+    if (obs_len) *obs_len = h->P.obs_stride;
+    if (loc_obs_len) *loc_obs_len = h->P.loc_len;
+    if (order_obs_len) *order_obs_len = h->P.order_len;
+    return IRBPP_OK;
+}
+
+int irbpp_load_shapes(irbpp_handle h, int32_t S, int32_t R, const int32_t* dims, const double* ext,
+                      const double* vol, const double* maps, const int64_t* offsets, int64_t maps_len) {
+    if (!h || !dims || !ext || !vol || !maps || !offsets) return fail(h, IRBPP_EINVAL, "null argument");
+    if (R != h->P.R) return fail(h, IRBPP_EINVAL, "library has %d rotations, env configured for %d", R, h->P.R);
+    if (S <= 0) return fail(h, IRBPP_EINVAL, "empty shape library");
+    const irbpp_config& c = h->cfg;
+    std::vector<ShapeRot> srot((size_t)S * R);
+    std::vector<double> Bs, Ts;
+    std::vector<double> rew(S);
+    for (int s = 0; s < S; ++s) {
+        rew[s] = (vol[s] / h->P.binvol) * 10;                        // binPhy.py:155-156,321-322
+        for (int r = 0; r < R; ++r) {
+            const int32_t* d = dims + ((size_t)s * R + r) * 4;
+            const double* e = ext + ((size_t)s * R + r) * 3;
+            const int w = d[0], hh = d[1], wA = d[2], hA = d[3];
+            if (w <= 0 || hh <= 0 || w > HX || hh > HY || wA <= 0 || hA <= 0)
+                return fail(h, IRBPP_EINVAL, "shape %d rot %d: bad window %dx%d / %dx%d", s, r, w, hh, wA, hA);
+            // the reference's window slice would run off the heightmap (NumPy broadcast error, space.py:118)
+            if (w > STEP * wA || hh > STEP * hA)
+                return fail(h, IRBPP_EINVAL, "shape %d rot %d: window %dx%d exceeds action footprint %dx%d "
+                            "(the reference fails on this table)", s, r, w, hh, wA, hA);
+            const int64_t off = offsets[(size_t)s * R + r];
+            const int64_t n = (int64_t)w * hh;
+            if (off < 0 || off + 4 * n > maps_len) return fail(h, IRBPP_EINVAL, "shape %d rot %d: table out of range", s, r);
+            ShapeRot& q = srot[(size_t)s * R + r];
+            q.w = w; q.h = hh;
+            q.nX = AX - wA + 1; q.nY = AY - hA + 1;                  // range(rangeX_A - rangeX_OA + 1)
+            if (q.nX < 0) q.nX = 0; if (q.nY < 0) q.nY = 0;
+            q.ez = np_round6(e[2]);
+            q.pad = 0;
+            // prejudge (binPhy.py:236,240-241): round(round(l*resA, 6) + extent - bin, 6) > 0 fails
+            q.okx = 0; q.oky = 0;
+            for (int l = 0; l < AX; ++l) {
+                const double tx = np_round6((double)l * c.resolution_act);
+                if (!(np_round6(tx + e[0] - c.bin_dimension[0]) > 0)) q.okx |= 1u << l;
+            }
+            for (int l = 0; l < AY; ++l) {
+                const double ty = np_round6((double)l * c.resolution_act);
+                if (!(np_round6(ty + e[1] - c.bin_dimension[1]) > 0)) q.oky |= 1u << l;
+            }
+            q.off = (int64_t)Bs.size();
+            const double* T = maps + off; const double* B = T + n; const double* mT = B + n; const double* mB = mT + n;
+            int any_zero = 0;
+            for (int64_t i = 0; i < n; ++i) {
+                if ((mB[i] != 0.0 && mB[i] != 1.0) || (mT[i] != 0.0 && mT[i] != 1.0))
+                    return fail(h, IRBPP_EINVAL, "shape %d rot %d: masks must be 0/1", s, r);
+                if (!isfinite(B[i]) || !isfinite(T[i])) return fail(h, IRBPP_EINVAL, "shape %d rot %d: non-finite height", s, r);
+                if (mB[i] == 0.0) any_zero = 1;
+                Bs.push_back(mB[i] != 0.0 ? B[i] : INFINITY);
+                Ts.push_back(mT[i] != 0.0 ? T[i] : -INFINITY);
+            }
+            q.any_zero = any_zero;
+        }
+    }
+    cudaSetDevice(c.device);
+    CUDA_TRY(h, dev_alloc(h, &h->srot_dev, srot.size(), false));
+    CUDA_TRY(h, dev_alloc(h, &h->Bs_dev, Bs.size() + 1, false));
+    CUDA_TRY(h, dev_alloc(h, &h->Ts_dev, Ts.size() + 1, false));
+    CUDA_TRY(h, dev_alloc(h, &h->vol_dev, (size_t)S, false));
+    CUDA_TRY(h, dev_alloc(h, &h->rew_dev, (size_t)S, false));
+    CUDA_TRY(h, cudaMemcpy(h->srot_dev, srot.data(), srot.size() * sizeof(ShapeRot), cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(h->Bs_dev, Bs.data(), Bs.size() * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(h->Ts_dev, Ts.data(), Ts.size() * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(h->vol_dev, vol, (size_t)S * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(h->rew_dev, rew.data(), (size_t)S * 8, cudaMemcpyHostToDevice));
+    h->P.S = S; h->P.srot = h->srot_dev; h->P.Bs = h->Bs_dev; h->P.Ts = h->Ts_dev;
+    h->P.vol = h->vol_dev; h->P.reward_tab = h->rew_dev;
+    h->shapes_loaded = true;
+    return IRBPP_OK;
+}
+
+int irbpp_set_sequences(irbpp_handle h, const int32_t* ids, int32_t length) {
+    if (!h || !ids || length <= 0) return fail(h, IRBPP_EINVAL, "bad sequences");
+    if (!h->shapes_loaded) return fail(h, IRBPP_ESTATE, "load shapes before sequences");
+    const size_t n = (size_t)h->P.N * length;
+    for (size_t i = 0; i < n; ++i)
+        if (ids[i] < 0 || ids[i] >= h->P.S) return fail(h, IRBPP_EINVAL, "item id %d out of range at %zu", ids[i], i);
+    cudaSetDevice(h->cfg.device);
+    CUDA_TRY(h, dev_alloc(h, &h->seq_dev, n, false));
+    CUDA_TRY(h, cudaMemcpy(h->seq_dev, ids, n * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemset(h->P.cursor, 0, (size_t)h->P.N * 4));
+    h->P.seq = h->seq_dev; h->P.L = length;
+    h->sequences_set = true;
+    return IRBPP_OK;
+}
+
+static int launch(irbpp_env* h, Params& P, cudaStream_t s, int grid_y = 1) {
+    dim3 grid(P.N, grid_y);
+    irbpp_env_kernel<<<grid, CTA_THREADS, h->SL.total, s>>>(P);
+    h->launches += 1;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(h, IRBPP_ECUDA, "kernel launch: %s", cudaGetErrorString(e));
+    return IRBPP_OK;
+}
+
+static int ready(irbpp_env* h) {
+    if (!h) return IRBPP_EINVAL;
+    if (!h->shapes_loaded || !h->sequences_set) return fail(h, IRBPP_ESTATE, "shapes / sequences not loaded");
+    cudaError_t e = cudaSetDevice(h->cfg.device);
+    if (e != cudaSuccess) return fail(h, IRBPP_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    return IRBPP_OK;
+}
+
+int irbpp_reset(irbpp_handle h, const uint8_t* which, float* obs_out, void* stream) {
+    int rc = ready(h); if (rc) return rc;
+    if (!obs_out) return fail(h, IRBPP_EINVAL, "obs_out is null");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (h->waiting_step) {         // "Called reset() while waiting for the step to complete" (shmem_vec_env.py:61-63)
+        cudaStreamSynchronize(h->pending_stream);
+        h->waiting_step = false;
+    }
+    Params P = h->P;
+    P.mode = MODE_RESET; P.obs = obs_out; P.which = nullptr;
+    if (which) {
+        CUDA_TRY(h, cudaMemcpyAsync(h->which_dev, which, (size_t)P.N, cudaMemcpyHostToDevice, s));
+        P.which = h->which_dev;
+    }
+    rc = launch(h, P, s); if (rc) return rc;
+    h->was_reset = true;
+    return IRBPP_OK;
+}
+
+int irbpp_step_async(irbpp_handle h, const int64_t* actions, int32_t on_device, float* obs_out, void* stream) {
+    int rc = ready(h); if (rc) return rc;
+    if (!actions || !obs_out) return fail(h, IRBPP_EINVAL, "null argument");
+    if (!h->was_reset) return fail(h, IRBPP_ESTATE, "step before reset");
+    if (h->waiting_step) return fail(h, IRBPP_ESTATE, "already running an async step");   // vec_env.py:7-16
+    cudaStream_t s = (cudaStream_t)stream;
+    Params P = h->P;
+    P.mode = MODE_STEP; P.obs = obs_out;
+    if (on_device) P.actions = actions;
+    else {
+        memcpy(h->actions_pinned, actions, (size_t)P.N * sizeof(int64_t));
+        CUDA_TRY(h, cudaMemcpyAsync(h->actions_dev, h->actions_pinned, (size_t)P.N * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+        P.actions = h->actions_dev;
+    }
+    rc = launch(h, P, s); if (rc) return rc;
+    h->waiting_step = true; h->pending_stream = s;
+    return IRBPP_OK;
+}
+
+static void host_views(irbpp_env* h, char* b, irbpp_step_result* out) {
+    const size_t N = h->P.N;
+    out->ratio = reinterpret_cast<double*>(b); b += N * 8;
+    out->ep_reward = reinterpret_cast<double*>(b); b += N * 8;
+    out->reward = reinterpret_cast<float*>(b); b += N * 4;
+    out->counter = reinterpret_cast<int32_t*>(b); b += N * 4;
+    out->ep_len = reinterpret_cast<int32_t*>(b); b += N * 4;
+    out->done = reinterpret_cast<uint8_t*>(b); b += N;
+    out->valid = reinterpret_cast<uint8_t*>(b); b += N;
+    out->error = reinterpret_cast<uint8_t*>(b);
+}
+
+int irbpp_step_wait(irbpp_handle h, irbpp_step_result* out) {
+    int rc = ready(h); if (rc) return rc;
+    if (!h->waiting_step) return fail(h, IRBPP_ESTATE, "not running an async step");   // vec_env.py:18-26
+    cudaStream_t s = h->pending_stream;
+    h->waiting_step = false;
+    if (out) CUDA_TRY(h, cudaMemcpyAsync(h->results_host, h->results_dev, h->results_bytes, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(h, cudaStreamSynchronize(s));
+    if (out) {
+        host_views(h, reinterpret_cast<char*>(h->results_host), out);
+        for (int i = 0; i < h->P.N; ++i)
+            if (out->error[i]) return fail(h, IRBPP_EDEVICE, "env %d reported device error code %d", i, (int)out->error[i]);
+    }
+    return IRBPP_OK;
+}
+
+int irbpp_step_wait_device(irbpp_handle h, irbpp_device_result* out) {
+    int rc = ready(h); if (rc) return rc;
+    if (!h->waiting_step) return fail(h, IRBPP_ESTATE, "not running an async step");
+    h->waiting_step = false;
+    if (out) {
+        out->ratio = h->P.r_ratio; out->ep_reward = h->P.r_eprew; out->reward = h->P.r_reward;
+        out->counter = h->P.r_counter; out->ep_len = h->P.r_eplen; out->done = h->P.r_done;
+        out->valid = h->P.r_valid; out->error = h->P.r_error;
+    }
+    return IRBPP_OK;
+}
+
+int irbpp_get_action_candidates(irbpp_handle h, const int64_t* order_actions, int32_t on_device,
+                                float* loc_obs_out, void* stream) {
+    int rc = ready(h); if (rc) return rc;
+    if (!order_actions || !loc_obs_out) return fail(h, IRBPP_EINVAL, "null argument");
+    if (h->P.K <= 1) return fail(h, IRBPP_ESTATE, "get_action_candidates needs buffer_size > 1");
+    if (!h->was_reset) return fail(h, IRBPP_ESTATE, "get_action_candidates before reset");
+    cudaStream_t s = (cudaStream_t)stream;
+    Params P = h->P;
+    P.mode = MODE_CANDIDATES; P.obs = loc_obs_out; P.obs_stride = P.loc_len;
+    if (on_device) P.actions = order_actions;
+    else {
+        memcpy(h->actions_pinned, order_actions, (size_t)P.N * sizeof(int64_t));
+        CUDA_TRY(h, cudaMemcpyAsync(h->actions_dev, h->actions_pinned, (size_t)P.N * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+        P.actions = h->actions_dev;
+    }
+    return launch(h, P, s);
+}
+
+int irbpp_get_all_possible_observation(irbpp_handle h, float* out, void* stream) {
+    int rc = ready(h); if (rc) return rc;
+    if (!out) return fail(h, IRBPP_EINVAL, "null argument");
+    if (h->P.K <= 1) return fail(h, IRBPP_ESTATE, "get_all_possible_observation needs buffer_size > 1");
+    if (!h->was_reset) return fail(h, IRBPP_ESTATE, "called before reset");
+    Params P = h->P;
+    P.mode = MODE_ALL_OBS; P.obs = out; P.obs_stride = P.K * P.loc_len;
+    return launch(h, P, (cudaStream_t)stream, P.K);
+}
+
+int irbpp_debug_state(irbpp_handle h, double* heightmap, int32_t* queue, int32_t* cursor, int32_t* packed_count) {
+    int rc = ready(h); if (rc) return rc;
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    const int N = h->P.N;
+    if (heightmap) {
+        std::vector<double> raw((size_t)N * HX * HY);
+        CUDA_TRY(h, cudaMemcpy(raw.data(), h->P.hm, raw.size() * 8, cudaMemcpyDeviceToHost));
+        for (int e = 0; e < N; ++e)
+            for (int x = 0; x < HX; ++x)
+                for (int y = 0; y < HY; ++y)
+                    heightmap[((size_t)e * HX + x) * HY + y] =
+                        raw[(size_t)e * HX * HY + ((y & 1) * HX + x) * (HY / 2) + (y >> 1)];
+    }
+    if (queue) {
+        std::vector<int32_t> q((size_t)N * MAX_QUEUE);
+        CUDA_TRY(h, cudaMemcpy(q.data(), h->P.queue, q.size() * 4, cudaMemcpyDeviceToHost));
+        const int k = h->P.K > 1 ? h->P.K : 1;
+        for (int e = 0; e < N; ++e) for (int i = 0; i < k; ++i) queue[(size_t)e * k + i] = q[(size_t)e * MAX_QUEUE + i];
+    }
+    if (cursor) CUDA_TRY(h, cudaMemcpy(cursor, h->P.cursor, (size_t)N * 4, cudaMemcpyDeviceToHost));
+    if (packed_count) CUDA_TRY(h, cudaMemcpy(packed_count, h->P.packed, (size_t)N * 4, cudaMemcpyDeviceToHost));
+    return IRBPP_OK;
+}
+
+int irbpp_debug_set_heightmap(irbpp_handle h, const double* heightmap) {
+    int rc = ready(h); if (rc) return rc;
+    if (!heightmap) return fail(h, IRBPP_EINVAL, "null argument");
+    const int N = h->P.N;
+    std::vector<double> raw((size_t)N * HX * HY);
+    for (int e = 0; e < N; ++e)
+        for (int x = 0; x < HX; ++x)
+            for (int y = 0; y < HY; ++y)
+                raw[(size_t)e * HX * HY + ((y & 1) * HX + x) * (HY / 2) + (y >> 1)] = heightmap[((size_t)e * HX + x) * HY + y];
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    CUDA_TRY(h, cudaMemcpy(h->P.hm, raw.data(), raw.size() * 8, cudaMemcpyHostToDevice));
+    return IRBPP_OK;
+}
+
+static int debug_run(irbpp_env* h, Params& P, double* posZmap, double* posZValid, double* naiveMask,
+                     double* cand, int32_t* num_hull) {
+    const size_t N = P.N, nm = N * P.R * NPOSE, nc = N * P.sel * 5;
+    double *d_pz = nullptr, *d_pv = nullptr, *d_mk = nullptr, *d_cd = nullptr; int32_t* d_nh = nullptr; float* d_obs = nullptr;
+    auto cleanup = [&]() { cudaFree(d_pz); cudaFree(d_pv); cudaFree(d_mk); cudaFree(d_cd); cudaFree(d_nh); cudaFree(d_obs); };
+#define DBG_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { cleanup(); return fail(h, IRBPP_ECUDA, "%s: %s", #expr, cudaGetErrorString(e_)); } } while (0)
+    if (P.mode == MODE_DEBUG_SCAN) {
+        DBG_TRY(cudaMalloc(&d_pz, nm * 8)); DBG_TRY(cudaMalloc(&d_pv, nm * 8)); DBG_TRY(cudaMalloc(&d_mk, nm * 8));
+        P.dbg_posz = d_pz; P.dbg_poszv = d_pv; P.dbg_mask = d_mk;
+    }
+    DBG_TRY(cudaMalloc(&d_cd, nc * 8)); DBG_TRY(cudaMalloc(&d_nh, N * 4));
+    DBG_TRY(cudaMalloc(&d_obs, N * (size_t)P.loc_len * 4));
+    P.dbg_cand = d_cd; P.dbg_nhull = d_nh; P.obs = d_obs; P.obs_stride = P.loc_len;
+    int rc = launch(h, P, nullptr);
+    if (rc) { cleanup(); return rc; }
+    DBG_TRY(cudaDeviceSynchronize());
+    if (posZmap && d_pz) DBG_TRY(cudaMemcpy(posZmap, d_pz, nm * 8, cudaMemcpyDeviceToHost));
+    if (posZValid && d_pv) DBG_TRY(cudaMemcpy(posZValid, d_pv, nm * 8, cudaMemcpyDeviceToHost));
+    if (naiveMask && d_mk) DBG_TRY(cudaMemcpy(naiveMask, d_mk, nm * 8, cudaMemcpyDeviceToHost));
+    if (cand) DBG_TRY(cudaMemcpy(cand, d_cd, nc * 8, cudaMemcpyDeviceToHost));
+    if (num_hull) DBG_TRY(cudaMemcpy(num_hull, d_nh, N * 4, cudaMemcpyDeviceToHost));
+    std::vector<uint8_t> errs(N);
+    DBG_TRY(cudaMemcpy(errs.data(), P.r_error, N, cudaMemcpyDeviceToHost));
+    cleanup();
+#undef DBG_TRY
+    for (size_t i = 0; i < N; ++i) if (errs[i]) return fail(h, IRBPP_EDEVICE, "env %zu reported device error code %d", i, (int)errs[i]);
+    return IRBPP_OK;
+}
+
+int irbpp_debug_scan(irbpp_handle h, const int32_t* item_ids, double* posZmap, double* posZValid,
+                     double* naiveMask, double* cand, int32_t* num_hull) {
+    int rc = ready(h); if (rc) return rc;
+    if (!item_ids) return fail(h, IRBPP_EINVAL, "null argument");
+    for (int i = 0; i < h->P.N; ++i)
+        if (item_ids[i] < 0 || item_ids[i] >= h->P.S) return fail(h, IRBPP_EINVAL, "item id out of range");
+    int32_t* d_items = nullptr;
+    CUDA_TRY(h, cudaMalloc(&d_items, (size_t)h->P.N * 4));
+    CUDA_TRY(h, cudaMemcpy(d_items, item_ids, (size_t)h->P.N * 4, cudaMemcpyHostToDevice));
+    Params P = h->P;
+    P.mode = MODE_DEBUG_SCAN; P.dbg_items = d_items;
+    rc = debug_run(h, P, posZmap, posZValid, naiveMask, cand, num_hull);
+    cudaFree(d_items);
+    return rc;
+}
+
+int irbpp_debug_hulls(irbpp_handle h, const double* posZValid, const double* mask, double* cand, int32_t* num_hull) {
+    int rc = ready(h); if (rc) return rc;
+    if (!posZValid || !mask) return fail(h, IRBPP_EINVAL, "null argument");
+    const size_t nm = (size_t)h->P.N * h->P.R * NPOSE;
+    double *d_pz = nullptr, *d_mk = nullptr;
+    CUDA_TRY(h, cudaMalloc(&d_pz, nm * 8));
+    CUDA_TRY(h, cudaMalloc(&d_mk, nm * 8));
+    CUDA_TRY(h, cudaMemcpy(d_pz, posZValid, nm * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(d_mk, mask, nm * 8, cudaMemcpyHostToDevice));
+    Params P = h->P;
+    P.mode = MODE_DEBUG_HULLS; P.dbg_in_posz = d_pz; P.dbg_in_mask = d_mk;
+    rc = debug_run(h, P, nullptr, nullptr, nullptr, cand, num_hull);
+    cudaFree(d_pz); cudaFree(d_mk);
+    return rc;
+}
+
+int64_t irbpp_launch_count(irbpp_handle h) { return h ? h->launches : 0; }
+
+}  // extern "C"

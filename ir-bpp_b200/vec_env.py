@@ -1,0 +1,353 @@
+"""The reference's vectorised-environment surface, served by the CUDA library.
+
+Mirrors (paths relative to the reference root):
+
+* ``wrapper/vec_env.py:7-26``   ``AlreadySteppingError`` / ``NotSteppingError``
+* ``wrapper/vec_env.py:29-108`` ``VecEnv``: ``reset / step_async / step_wait / step / close``
+* ``wrapper/shmem_vec_env.py:20-118`` ``ShmemVecEnv``: ``waiting_step``, ``get_action_candidates``,
+  ``reset_specific``; auto-reset on done (``:140-144``)
+* ``envs.py:142-165`` ``VecPyTorch``: observations as ``torch.float32`` on ``device``, reward as a
+  CPU ``float32 [N, 1]`` tensor, ``done`` a NumPy bool array, ``infos`` a sequence of dicts
+* ``wrapper/monitor.py:58-75`` episode info ``info['episode'] = {'r', 'l', 't'}`` on done
+
+so ``agent.py`` / ``trainer.py`` can drive ``GpuVecEnv`` where they drove
+``VecPyTorch(ShmemVecEnv([...PackingGame...]))``.  All N bins live on one GPU; ``step`` is one kernel
+launch (see ``csrc/irbpp_kernels.cuh``).  PyTorch is used for device memory and streams only.
+"""
+import ctypes
+import time
+from abc import ABC, abstractmethod
+from collections.abc import Sequence
+
+import numpy as np
+
+from . import _lib
+
+
+class AlreadySteppingError(Exception):
+    """step_async() called while a step is pending (reference wrapper/vec_env.py:7-16)."""
+
+    def __init__(self):
+        Exception.__init__(self, "already running an async step")
+
+
+class NotSteppingError(Exception):
+    """step_wait() called without a pending step (reference wrapper/vec_env.py:18-26)."""
+
+    def __init__(self):
+        Exception.__init__(self, "not running an async step")
+
+
+class VecEnv(ABC):
+    """Abstract asynchronous vectorised environment (reference wrapper/vec_env.py:29-108)."""
+    closed = False
+
+    def __init__(self, num_envs, observation_space, action_space):
+        self.num_envs = num_envs
+        self.observation_space = observation_space
+        self.action_space = action_space
+
+    @abstractmethod
+    def reset(self):
+        pass
+
+    @abstractmethod
+    def step_async(self, actions):
+        pass
+
+    @abstractmethod
+    def step_wait(self):
+        pass
+
+    def close_extras(self):
+        pass
+
+    def close(self):
+        if self.closed:
+            return
+        self.close_extras()
+        self.closed = True
+
+    def step(self, actions):
+        self.step_async(actions)
+        return self.step_wait()
+
+    @property
+    def unwrapped(self):
+        return self
+
+
+class Box(object):
+    """Minimal stand-in for ``gym.spaces.Box`` (gym is not a dependency of this package): the
+    attributes the reference's callers read (``shape``, ``low``, ``high``, ``dtype``;
+    binPhy.py:100-101)."""
+
+    def __init__(self, low, high, shape, dtype=np.float32):
+        self.low = np.full(shape, low, dtype=dtype)
+        self.high = np.full(shape, high, dtype=dtype)
+        self.shape = tuple(shape)
+        self.dtype = np.dtype(dtype)
+
+    def __repr__(self):
+        return "Box(%s, %s, %s, %s)" % (self.low.min(), self.high.max(), self.shape, self.dtype)
+
+
+class Discrete(object):
+    """Stand-in for ``gym.spaces.Discrete`` (binPhy.py:102)."""
+
+    def __init__(self, n):
+        self.n = int(n)
+        self.shape = ()
+        self.dtype = np.dtype(np.int64)
+
+    def __repr__(self):
+        return "Discrete(%d)" % self.n
+
+
+class LazyInfos(Sequence):
+    """``infos`` of one step: behaves like the reference's tuple of N dicts but builds a dict only
+    when indexed (at N = 4096 eagerly building them would dominate the step)."""
+
+    def __init__(self, valid, done, counter, ratio, ep_reward, ep_len, t_rel):
+        self._valid, self._done = valid, done
+        self._counter, self._ratio, self._ep_reward, self._ep_len = counter, ratio, ep_reward, ep_len
+        self._t = t_rel
+
+    def __len__(self):
+        return len(self._valid)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(len(self)))]
+        if i < 0:
+            i += len(self)
+        if not 0 <= i < len(self):
+            raise IndexError(i)
+        info = {"Valid": bool(self._valid[i])}
+        if self._done[i]:
+            # binPhy.py:306-309 and monitor.py:58-75 (round(eprew, 6) is Python's round, as there)
+            info["counter"] = int(self._counter[i])
+            info["ratio"] = float(self._ratio[i])
+            info["episode"] = {"r": round(float(self._ep_reward[i]), 6), "l": int(self._ep_len[i]), "t": self._t}
+        return info
+
+
+def _as_host_i64(a, n, what):
+    arr = np.ascontiguousarray(np.asarray(a).reshape(-1), dtype=np.int64)
+    if arr.shape[0] != n:
+        raise ValueError("%s: expected %d entries, got %d" % (what, n, arr.shape[0]))
+    return arr
+
+
+class GpuVecEnv(VecEnv):
+    """N packing bins resident on one B200 behind the VecEnv contract.
+
+    Parameters mirror what ``PackingGame.__init__`` reads from ``args`` (binPhy.py:25-49):
+    ``library`` is a ``shapes.ShapeLibrary`` (the ``shotInfo`` / ``shapeDict`` / ``infoDict`` data),
+    ``sequences`` the per-env item ids (stand-in for the item creators, IRcreator.py)."""
+
+    def __init__(self, library, sequences, num_envs=None, device="cuda:0", selected_action=500, buffer_size=1,
+                 bin_dimension=(0.32, 0.32, 0.30), resolution_act=0.02, resolution_h=0.01, resolution_z=0.01,
+                 approx_legacy=False):
+        import torch
+        self._torch = torch
+        self._lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("GpuVecEnv needs a CUDA device; there is no CPU path")
+        sequences = np.ascontiguousarray(sequences, dtype=np.int32)
+        if num_envs is None:
+            num_envs = sequences.shape[0]
+        if sequences.shape[0] != num_envs:
+            raise ValueError("sequences has %d rows for %d envs" % (sequences.shape[0], num_envs))
+        idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        cfg = _lib.IrbppConfig()
+        cfg.num_envs = num_envs
+        cfg.num_rotations = library.num_rotations
+        cfg.selected_action = selected_action
+        cfg.buffer_size = buffer_size
+        for i in range(3):
+            cfg.bin_dimension[i] = float(bin_dimension[i])
+        cfg.resolution_act, cfg.resolution_h, cfg.resolution_z = resolution_act, resolution_h, resolution_z
+        cfg.device = idx
+        cfg.approx_legacy = 1 if approx_legacy else 0
+        handle = ctypes.c_void_p()
+        rc = self._lib.irbpp_create(ctypes.byref(cfg), ctypes.byref(handle))
+        _lib.check(self._lib, None, rc)
+        self._h = handle
+        self._cfg = cfg
+        self.buffer_size = buffer_size
+        self.selected_action = selected_action
+        self.library = library
+        dims, ext, vol, maps, offsets = library.flat()
+        self._keep = (dims, ext, vol, maps, offsets, sequences)
+        rc = self._lib.irbpp_load_shapes(self._h, library.num_shapes, library.num_rotations,
+                                         dims.ctypes.data, ext.ctypes.data, vol.ctypes.data, maps.ctypes.data,
+                                         offsets.ctypes.data, maps.size)
+        self._check(rc)
+        rc = self._lib.irbpp_set_sequences(self._h, sequences.ctypes.data, sequences.shape[1])
+        self._check(rc)
+        o, l, k = _lib.c_i32(), _lib.c_i32(), _lib.c_i32()
+        self._check(self._lib.irbpp_obs_len(self._h, ctypes.byref(o), ctypes.byref(l), ctypes.byref(k)))
+        self.obs_len, self.loc_obs_len, self.order_obs_len = o.value, l.value, k.value
+        obs_space = Box(0.0, float(bin_dimension[2]), (self.obs_len,))                 # binPhy.py:100-101
+        act_space = Discrete(buffer_size if buffer_size > 1 else selected_action)     # binPhy.py:81-85,102
+        VecEnv.__init__(self, num_envs, obs_space, act_space)
+        self.waiting_step = False
+        self._obs_pending = None
+        self._tstart = time.time()
+        self._result = _lib.IrbppStepResult()
+
+    # -- helpers --
+    def _check(self, rc):
+        _lib.check(self._lib, self._h, rc)
+
+    def _stream(self):
+        return self._torch.cuda.current_stream(self.device).cuda_stream
+
+    def _new_obs(self, width):
+        return self._torch.empty((self.num_envs, width), dtype=self._torch.float32, device=self.device)
+
+    def _actions_arg(self, actions, what):
+        """Host array / list (copied through pinned staging) or a CUDA int64 tensor (used in place)."""
+        torch = self._torch
+        if isinstance(actions, torch.Tensor):
+            if actions.is_cuda:
+                a = actions.reshape(-1).to(torch.int64).contiguous()
+                if a.numel() != self.num_envs:
+                    raise ValueError("%s: expected %d entries" % (what, self.num_envs))
+                return a, a.data_ptr(), 1
+            actions = actions.cpu().numpy()
+        a = _as_host_i64(actions, self.num_envs, what)
+        return a, a.ctypes.data, 0
+
+    # -- VecEnv surface --
+    def reset(self):
+        """``envs.reset()`` -> float32 [N, obs_len] on device (envs.py:149-152)."""
+        if self.waiting_step:                     # shmem_vec_env.py:61-63
+            self.step_wait()
+        obs = self._new_obs(self.obs_len)
+        self._check(self._lib.irbpp_reset(self._h, None, obs.data_ptr(), self._stream()))
+        self._tstart = time.time()
+        return obs
+
+    def reset_specific(self, indexs, obs):
+        """``ShmemVecEnv.reset_specific`` (shmem_vec_env.py:113-118): reset the listed envs, writing
+        their rows of ``obs`` (a [N, obs_len] device tensor) in place."""
+        which = np.zeros(self.num_envs, dtype=np.uint8)
+        which[np.asarray(indexs, dtype=np.int64)] = 1
+        self._check(self._lib.irbpp_reset(self._h, which.ctypes.data, obs.data_ptr(), self._stream()))
+        self._torch.cuda.current_stream(self.device).synchronize()   # `which` is read asynchronously
+        return obs
+
+    def step_async(self, actions):
+        if self.waiting_step:
+            raise AlreadySteppingError()
+        keep, ptr, on_dev = self._actions_arg(actions, "actions")
+        obs = self._new_obs(self.obs_len)
+        self._check(self._lib.irbpp_step_async(self._h, ptr, on_dev, obs.data_ptr(), self._stream()))
+        self._obs_pending = (obs, keep)
+        self.waiting_step = True
+
+    def step_wait(self):
+        """-> (obs float32 [N, obs_len] on device, reward float32 [N, 1] on CPU, done bool [N], infos)
+        exactly as ``VecPyTorch.step_wait`` (envs.py:161-165)."""
+        if not self.waiting_step:
+            raise NotSteppingError()
+        torch = self._torch
+        self.waiting_step = False
+        obs, _ = self._obs_pending
+        self._obs_pending = None
+        res = self._result
+        self._check(self._lib.irbpp_step_wait(self._h, ctypes.byref(res)))
+        n = self.num_envs
+
+        def view(ptr, ctype, dtype):
+            return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctype)), shape=(n,)).astype(dtype, copy=True)
+
+        reward = view(res.reward, ctypes.c_float, np.float32)
+        done = view(res.done, ctypes.c_uint8, np.bool_)
+        valid = view(res.valid, ctypes.c_uint8, np.bool_)
+        infos = LazyInfos(valid, done, view(res.counter, ctypes.c_int32, np.int32),
+                          view(res.ratio, ctypes.c_double, np.float64),
+                          view(res.ep_reward, ctypes.c_double, np.float64),
+                          view(res.ep_len, ctypes.c_int32, np.int32), round(time.time() - self._tstart, 6))
+        return obs, torch.from_numpy(reward).unsqueeze(dim=1), done, infos
+
+    def step_device(self, actions):
+        """Device-resident loop: ``actions`` is a CUDA int64 tensor; nothing is copied to the host and
+        nothing is synchronised.  Returns (obs, reward, done) device views valid in stream order."""
+        if self.waiting_step:
+            raise AlreadySteppingError()
+        keep, ptr, on_dev = self._actions_arg(actions, "actions")
+        if not on_dev:
+            raise ValueError("step_device needs a CUDA tensor")
+        obs = self._new_obs(self.obs_len)
+        self._check(self._lib.irbpp_step_async(self._h, ptr, 1, obs.data_ptr(), self._stream()))
+        res = self._result
+        self._check(self._lib.irbpp_step_wait_device(self._h, ctypes.byref(res)))
+        return obs, res
+
+    def get_action_candidates(self, order_actions, as_tensor=False):
+        """``envs.get_action_candidates(orderAction)`` (shmem_vec_env.py:99-102 -> binPhy.py:161-169).
+        Default return matches the reference (list of N float64 host arrays of length 3533, what
+        ``trainer.py:267-268`` feeds to ``np.array``); ``as_tensor=True`` returns the float32 device
+        tensor and skips the host copy."""
+        keep, ptr, on_dev = self._actions_arg(order_actions, "order_actions")
+        out = self._new_obs(self.loc_obs_len)
+        self._check(self._lib.irbpp_get_action_candidates(self._h, ptr, on_dev, out.data_ptr(), self._stream()))
+        if as_tensor:
+            return out
+        return list(out.cpu().numpy().astype(np.float64))
+
+    def get_all_possible_observation(self):
+        """``PackingGame.get_all_possible_observation`` for every env (binPhy.py:171-180):
+        float32 [N, k * 3533] on device."""
+        out = self._new_obs(self.buffer_size * self.loc_obs_len)
+        self._check(self._lib.irbpp_get_all_possible_observation(self._h, out.data_ptr(), self._stream()))
+        return out
+
+    def close_extras(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.irbpp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- parity / debugging views (float64, host) --
+    def launch_count(self):
+        return int(self._lib.irbpp_launch_count(self._h))
+
+    def debug_state(self):
+        n, k = self.num_envs, max(self.buffer_size, 1)
+        hm = np.zeros((n, 32, 32)); queue = np.zeros((n, k), np.int32)
+        cursor = np.zeros(n, np.int32); packed = np.zeros(n, np.int32)
+        self._check(self._lib.irbpp_debug_state(self._h, hm.ctypes.data, queue.ctypes.data, cursor.ctypes.data,
+                                                packed.ctypes.data))
+        return {"heightmap": hm, "queue": queue, "cursor": cursor, "packed": packed}
+
+    def debug_set_heightmap(self, heightmap):
+        hm = np.ascontiguousarray(heightmap, dtype=np.float64).reshape(self.num_envs, 32, 32)
+        self._check(self._lib.irbpp_debug_set_heightmap(self._h, hm.ctypes.data))
+
+    def debug_scan(self, item_ids):
+        n, R, sel = self.num_envs, self.library.num_rotations, self.selected_action
+        items = np.ascontiguousarray(item_ids, dtype=np.int32).reshape(n)
+        pz = np.zeros((n, R, 16, 16)); pv = np.zeros((n, R, 16, 16)); mk = np.zeros((n, R, 16, 16))
+        cand = np.zeros((n, sel, 5)); nh = np.zeros(n, np.int32)
+        self._check(self._lib.irbpp_debug_scan(self._h, items.ctypes.data, pz.ctypes.data, pv.ctypes.data,
+                                               mk.ctypes.data, cand.ctypes.data, nh.ctypes.data))
+        return {"posZmap": pz, "posZValid": pv, "naiveMask": mk, "cand": cand, "num_hull": nh}
+
+    def debug_hulls(self, posZValid, mask):
+        n, R, sel = self.num_envs, self.library.num_rotations, self.selected_action
+        pv = np.ascontiguousarray(posZValid, dtype=np.float64).reshape(n, R, 16, 16)
+        mk = np.ascontiguousarray(mask, dtype=np.float64).reshape(n, R, 16, 16)
+        cand = np.zeros((n, sel, 5)); nh = np.zeros(n, np.int32)
+        self._check(self._lib.irbpp_debug_hulls(self._h, pv.ctypes.data, mk.ctypes.data, cand.ctypes.data,
+                                                nh.ctypes.data))
+        return {"cand": cand, "num_hull": nh}

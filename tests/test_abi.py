@@ -1,0 +1,118 @@
+"""Host-side checks that need no GPU: the C-ABI library builds, loads and exports every symbol that
+include/irbpp.h declares; the device contour routines (compiled as host C++ by a test-only harness)
+agree with the oracle."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+
+@pytest.fixture(scope="module")
+def built_lib():
+    from irbpp_b200 import build
+    return build.build()
+
+
+def test_header_symbols_exported(built_lib):
+    from irbpp_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "irbpp.h")).read()
+    declared = set(re.findall(r"\b(irbpp_[a-z_]+)\s*\(", header))
+    declared.discard("irbpp_env")
+    assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
+    lib = ctypes.CDLL(built_lib)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert _lib.load().irbpp_abi_version() == _lib.ABI_VERSION
+
+
+def test_create_rejects_bad_config_without_gpu(built_lib):
+    """Argument validation happens before any CUDA call, so it is checkable here."""
+    from irbpp_b200 import _lib
+    lib = _lib.load()
+    cfg = _lib.IrbppConfig()
+    cfg.num_envs, cfg.num_rotations, cfg.selected_action, cfg.buffer_size = 4, 4, 500, 1
+    cfg.bin_dimension[0], cfg.bin_dimension[1], cfg.bin_dimension[2] = 0.32, 0.32, 0.30
+    cfg.resolution_act, cfg.resolution_h, cfg.resolution_z = 0.02, 0.01, 0.01
+    h = ctypes.c_void_p()
+    cfg.num_rotations = 0
+    assert lib.irbpp_create(ctypes.byref(cfg), ctypes.byref(h)) == _lib.IRBPP_EINVAL
+    cfg.num_rotations = 4
+    cfg.resolution_h = 0.02      # heightmap would be 16x16: unsupported grid
+    assert lib.irbpp_create(ctypes.byref(cfg), ctypes.byref(h)) == _lib.IRBPP_EINVAL
+    assert b"unsupported grid" in lib.irbpp_last_error(None)
+    cfg.resolution_h = 0.01
+    cfg.selected_action = 2000   # more rows than poses
+    assert lib.irbpp_create(ctypes.byref(cfg), ctypes.byref(h)) == _lib.IRBPP_EINVAL
+
+
+def test_no_cpu_fallback_without_gpu(built_lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from irbpp_b200 import _lib
+    lib = _lib.load()
+    cfg = _lib.IrbppConfig()
+    cfg.num_envs, cfg.num_rotations, cfg.selected_action, cfg.buffer_size = 4, 4, 500, 1
+    cfg.bin_dimension[0], cfg.bin_dimension[1], cfg.bin_dimension[2] = 0.32, 0.32, 0.30
+    cfg.resolution_act, cfg.resolution_h, cfg.resolution_z = 0.02, 0.01, 0.01
+    h = ctypes.c_void_p()
+    assert lib.irbpp_create(ctypes.byref(cfg), ctypes.byref(h)) == _lib.IRBPP_ECUDA
+    assert b"no CPU path" in lib.irbpp_last_error(None)
+
+
+@pytest.fixture(scope="module")
+def contour_harness(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("harness") / "contour_host.so")
+    src = os.path.join(ROOT, "tests", "host_harness", "contour_host.cpp")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", out, src], check=True)
+    return ctypes.CDLL(out)
+
+
+def _dev_bits(lib, img, legacy, big):
+    rows = np.zeros(16, np.uint16)
+    for y in range(16):
+        rows[y] = sum(1 << x for x in range(16) if img[y, x])
+    out = np.zeros(8, np.uint32)
+    rc = lib.hull_bits(rows.ctypes.data_as(ctypes.c_void_p), legacy, big, out.ctypes.data_as(ctypes.c_void_p))
+    return rc, {(b >> 4, b & 15) for b in range(256) if (int(out[b >> 5]) >> (b & 31)) & 1}
+
+
+def test_device_contour_routines_match_oracle(contour_harness):
+    from oracle import contours_port as cp
+    rng = np.random.default_rng(0)
+    n_ovf = 0
+    for it in range(1200):
+        kind = it % 4
+        if kind == 0:
+            img = (rng.random((16, 16)) < rng.uniform(0.05, 0.95)).astype(np.uint8)
+        elif kind == 1:
+            img = np.zeros((16, 16), np.uint8)
+            for _ in range(int(rng.integers(1, 7))):
+                x0, y0 = rng.integers(0, 14, 2); w, h = rng.integers(1, 9, 2)
+                img[x0:x0 + w, y0:y0 + h] = rng.integers(0, 2)
+        elif kind == 2:
+            img = np.ones((16, 16), np.uint8)
+            for _ in range(int(rng.integers(1, 9))):
+                x0, y0 = rng.integers(0, 15, 2); w, h = rng.integers(1, 5, 2)
+                img[x0:x0 + w, y0:y0 + h] = 0
+        else:
+            img = ((np.add.outer(np.arange(16), np.arange(16)) % 2) == 0).astype(np.uint8)
+            img &= (rng.random((16, 16)) < 0.9).astype(np.uint8)
+        for legacy in (0, 1):
+            want, maxlen = set(), 0
+            for c in cp.find_outer_contours(img):
+                maxlen = max(maxlen, len(c))
+                want |= {(int(p[0]), int(p[1])) for p in cp.convex_vertices(cp.approx_poly_dp_closed(c, 1.0, bool(legacy)))}
+            rc_fast, got_fast = _dev_bits(contour_harness, img, legacy, 0)
+            rc_big, got_big = _dev_bits(contour_harness, img, legacy, 1)
+            assert rc_big == 0 and got_big == want
+            assert (rc_fast == 1) == (maxlen > 64)          # fast path reports overflow exactly when it must
+            if rc_fast == 0:
+                assert got_fast == want
+            n_ovf += rc_fast
+    assert n_ovf > 0                                         # the overflow path was exercised
