@@ -65,7 +65,7 @@ class ClockSampler(object):
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -213,6 +213,9 @@ def main_gpu(args):
         torch.cuda.synchronize(dev)
 
     # ---- device-resident loop ("value") ----
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                             # sampled from burn-in through the timed steps (same load)
     obs = env.reset()
     for _ in range(BURN_IN + args.warmup):          # burn-in: bins spread over all episode phases
         acts = device_policy(torch, obs, gen)
@@ -220,9 +223,6 @@ def main_gpu(args):
     torch.cuda.synchronize(dev)
     launches0 = env.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     barrier()
     t_wall0 = time.perf_counter()
     for k in range(args.steps):

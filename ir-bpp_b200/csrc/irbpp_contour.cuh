@@ -10,9 +10,11 @@
 // the float comparisons OpenCV performs are between exactly representable values and are restated
 // as integer cross-multiplications.
 //
-// The code is templated on a scratch accessor so the same routine serves the fast path (one thread
-// per (rotation, level) task, <=64-point contours, kept-set in a 64-bit register) and the overflow
-// path (one thread, 1024-point buffers in shared memory).
+// The level image is 8 words, two 16-bit rows per word (row y = bits (y&1)*16.. of word y>>1, bit x =
+// column x).  Border following works on the 8-neighbourhood ring of the current pixel (one byte built
+// from three row words) instead of probing pixels one by one.  The code is templated on a scratch
+// accessor so the same routine serves the fast path (one thread per (rotation, level) task, <= 64
+// point contours, kept-set in a 64-bit register) and the overflow path (one thread, long buffers).
 #pragma once
 #include <stdint.h>
 
@@ -28,31 +30,38 @@ __device__ __forceinline__ int ddy(int s) {
     return (int)((0xA901u >> (2 * s)) & 3u) - 1;
 }
 
-// ---- scratch accessors -------------------------------------------------------------------------
-// Row words use PADDED x: bit (x+1) is column x, bits 0 and 17 are the zero frame; rows 0 and 17 of
-// fg are the zero frame.  Marks hold "positive" (low half) and "negative" (high half) Suzuki labels
-// per unpadded column.
+// row y of the image as 16 bits, 0 outside the image
+__device__ __forceinline__ uint32_t row16(const uint32_t* bm, int y) {
+    return ((unsigned)y < 16u) ? ((bm[y >> 1] >> ((y & 1) * 16)) & 0xFFFFu) : 0u;
+}
 
+// 8-neighbourhood of (x, y) as a byte: bit s set <=> the neighbour in direction s is foreground
+__device__ __forceinline__ uint32_t neighbour_ring(const uint32_t* bm, int x, int y) {
+    const uint32_t wm = ((row16(bm, y - 1) << 1) >> x) & 7u;   // bit0 = col x-1, bit1 = col x, bit2 = col x+1
+    const uint32_t w0 = ((row16(bm, y) << 1) >> x) & 7u;
+    const uint32_t wp = ((row16(bm, y + 1) << 1) >> x) & 7u;
+    const uint32_t rev = ((wm & 1u) << 2) | (wm & 2u) | (wm >> 2);   // NE, N, NW in direction order
+    return (w0 >> 2) | (rev << 1) | ((w0 & 1u) << 4) | (wp << 5);
+}
+
+// ---- scratch accessors -------------------------------------------------------------------------
+// marks: one word per image row; low half = "positive" Suzuki label per column, high half = "negative".
 template <int STRIDE, int CAP_>
 struct StridedScratch {
     static constexpr int CAP = CAP_;
-    uint32_t* w;   // 18 fg rows then 16 mark rows, element stride STRIDE
-    uint8_t* b;    // CAP contour points then CAP result points, element stride STRIDE
+    uint32_t* w;   // 16 mark rows, element stride STRIDE
+    uint8_t* b;    // CAP contour points, element stride STRIDE
     uint64_t kept;
-    __device__ __forceinline__ uint32_t fg(int y) const { return w[y * STRIDE]; }
-    __device__ __forceinline__ void set_fg(int y, uint32_t v) { w[y * STRIDE] = v; }
-    __device__ __forceinline__ uint32_t mk(int y) const { return w[(18 + y) * STRIDE]; }
-    __device__ __forceinline__ void set_mk(int y, uint32_t v) { w[(18 + y) * STRIDE] = v; }
+    __device__ __forceinline__ uint32_t mk(int y) const { return w[y * STRIDE]; }
+    __device__ __forceinline__ void set_mk(int y, uint32_t v) { w[y * STRIDE] = v; }
     __device__ __forceinline__ int pt(int i) const { return b[i * STRIDE]; }
     __device__ __forceinline__ void set_pt(int i, int v) { b[i * STRIDE] = (uint8_t)v; }
-    __device__ __forceinline__ int ds(int i) const { return b[(CAP + i) * STRIDE]; }
-    __device__ __forceinline__ void set_ds(int i, int v) { b[(CAP + i) * STRIDE] = (uint8_t)v; }
     __device__ __forceinline__ void kept_clear(int) { kept = 0ull; }
     __device__ __forceinline__ void kept_set(int i) { kept |= (1ull << i); }
     __device__ __forceinline__ int kept_count(int) const { return __popcll(kept); }
     // next kept index strictly after i, cyclically
     __device__ __forceinline__ int kept_next(int i, int) const {
-        uint64_t hi = (i >= 63) ? 0ull : (kept & ~((2ull << i) - 1ull));
+        const uint64_t hi = (i >= 63) ? 0ull : (kept & ~((2ull << i) - 1ull));
         return hi ? (__ffsll((long long)hi) - 1) : (__ffsll((long long)kept) - 1);
     }
 };
@@ -60,49 +69,40 @@ struct StridedScratch {
 template <int CAP_>
 struct FlatScratch {
     static constexpr int CAP = CAP_;
-    uint32_t* w;     // 18 + 16 words
-    uint8_t* b;      // CAP points, CAP result points, CAP kept flags
-    __device__ __forceinline__ uint32_t fg(int y) const { return w[y]; }
-    __device__ __forceinline__ void set_fg(int y, uint32_t v) { w[y] = v; }
-    __device__ __forceinline__ uint32_t mk(int y) const { return w[18 + y]; }
-    __device__ __forceinline__ void set_mk(int y, uint32_t v) { w[18 + y] = v; }
+    uint32_t* w;     // 16 mark words
+    uint8_t* b;      // CAP points, CAP kept flags
+    __device__ __forceinline__ uint32_t mk(int y) const { return w[y]; }
+    __device__ __forceinline__ void set_mk(int y, uint32_t v) { w[y] = v; }
     __device__ __forceinline__ int pt(int i) const { return b[i]; }
     __device__ __forceinline__ void set_pt(int i, int v) { b[i] = (uint8_t)v; }
-    __device__ __forceinline__ int ds(int i) const { return b[CAP + i]; }
-    __device__ __forceinline__ void set_ds(int i, int v) { b[CAP + i] = (uint8_t)v; }
-    __device__ __forceinline__ void kept_clear(int n) { for (int i = 0; i < n; ++i) b[2 * CAP + i] = 0; }
-    __device__ __forceinline__ void kept_set(int i) { b[2 * CAP + i] = 1; }
-    __device__ __forceinline__ int kept_count(int n) const { int c = 0; for (int i = 0; i < n; ++i) c += b[2 * CAP + i]; return c; }
+    __device__ __forceinline__ void kept_clear(int n) { for (int i = 0; i < n; ++i) b[CAP + i] = 0; }
+    __device__ __forceinline__ void kept_set(int i) { b[CAP + i] = 1; }
+    __device__ __forceinline__ int kept_count(int n) const { int c = 0; for (int i = 0; i < n; ++i) c += b[CAP + i]; return c; }
     __device__ __forceinline__ int kept_next(int i, int n) const {
         int k = i;
-        do { k = (k + 1 == n) ? 0 : k + 1; } while (!b[2 * CAP + k] && k != i);
+        do { k = (k + 1 == n) ? 0 : k + 1; } while (!b[CAP + k] && k != i);
         return k;
     }
 };
 
 // ---- border following (Suzuki-Abe, CHAIN_APPROX_SIMPLE) -----------------------------------------
-// (x0, y0) in padded coordinates (1..16).  Marks every visited border pixel; stores the emitted
-// points as (x<<4 | y) unpadded.  Returns the number of points, or -1 if it exceeded S::CAP (marks
-// are still complete in that case).
+// (x0, y0) unpadded.  Marks every visited border pixel; stores the emitted points as (x<<4 | y).
+// Returns the number of points, or -1 if it exceeded S::CAP (marks are still complete in that case).
 template <class S>
-__device__ int follow_border(S& sc, int x0, int y0, bool hole) {
-    auto pix = [&](int x, int y) -> bool { return (sc.fg(y) >> x) & 1u; };
-    auto mark_neg = [&](int x, int y) { sc.set_mk(y - 1, sc.mk(y - 1) | (0x10000u << (x - 1))); };
-    auto mark_pos_if_unmarked = [&](int x, int y) {
-        uint32_t m = sc.mk(y - 1);
-        if (!((m | (m >> 16)) & (1u << (x - 1)))) sc.set_mk(y - 1, m | (1u << (x - 1)));
-    };
-    int s_end = hole ? 0 : 4;
-    int s = s_end;
-    bool found = false;
-    do {
-        s = (s - 1) & 7;
-        if (pix(x0 + ddx(s), y0 + ddy(s))) { found = true; break; }
-    } while (s != s_end);
-    if (!found) {  // isolated pixel
-        mark_neg(x0, y0);
-        sc.set_pt(0, ((x0 - 1) << 4) | (y0 - 1));
+__device__ int follow_border(S& sc, const uint32_t* bm, int x0, int y0, bool hole) {
+    const int s_start = hole ? 0 : 4;
+    uint32_t ring = neighbour_ring(bm, x0, y0);
+    if (!ring) {  // isolated pixel
+        sc.set_mk(y0, sc.mk(y0) | (0x10000u << x0));
+        sc.set_pt(0, (x0 << 4) | y0);
         return 1;
+    }
+    // clockwise search from s_start-1 down to s_start: highest set bit of the ring rotated by s_start
+    int s;
+    {
+        const uint32_t r2 = ((ring | (ring << 8)) >> s_start) & 0xFFu;
+        const int j = 31 - __clz((int)r2);
+        s = (s_start + j) & 7;
     }
     const int x1 = x0 + ddx(s), y1 = y0 + ddy(s);
     int x3 = x0, y3 = y0;
@@ -110,19 +110,18 @@ __device__ int follow_border(S& sc, int x0, int y0, bool hole) {
     int n = 0;
     bool ovf = false;
     for (;;) {
-        s_end = s;
-        int x4, y4;
-        for (;;) {
-            ++s;
-            x4 = x3 + ddx(s & 7);
-            y4 = y3 + ddy(s & 7);
-            if (pix(x4, y4)) break;
+        const int s_end = s;
+        // counter-clockwise search starting at s_end+1: lowest set bit of the ring rotated by s_end+1
+        const uint32_t rot = ((ring | (ring << 8)) >> ((s_end + 1) & 7)) & 0xFFu;
+        s = (s_end + __ffs((int)rot)) & 7;        // (s_end + 1 + (ffs-1)) & 7
+        const int x4 = x3 + ddx(s), y4 = y3 + ddy(s);
+        {
+            const uint32_t m = sc.mk(y3);
+            if ((unsigned)(s - 1) < (unsigned)s_end) sc.set_mk(y3, m | (0x10000u << x3));
+            else if (!((m | (m >> 16)) & (1u << x3))) sc.set_mk(y3, m | (1u << x3));
         }
-        s &= 7;
-        if ((unsigned)(s - 1) < (unsigned)s_end) mark_neg(x3, y3);
-        else mark_pos_if_unmarked(x3, y3);
         if (s != prev_s) {
-            if (n < S::CAP) sc.set_pt(n, ((x3 - 1) << 4) | (y3 - 1));
+            if (n < S::CAP) sc.set_pt(n, (x3 << 4) | y3);
             else ovf = true;
             ++n;
         }
@@ -130,6 +129,7 @@ __device__ int follow_border(S& sc, int x0, int y0, bool hole) {
         if (x4 == x0 && y4 == y0 && x3 == x1 && y3 == y1) break;
         x3 = x4; y3 = y4;
         s = (s + 4) & 7;
+        ring = neighbour_ring(bm, x3, y3);
     }
     return ovf ? -1 : n;
 }
@@ -149,7 +149,8 @@ __device__ void approx_and_emit(S& sc, int n, bool legacy, Emit emit) {
         int k = pos;
         for (int j = 1; j < n; ++j) {
             k = (k + 1 == n) ? 0 : k + 1;
-            const int ex = PX(k) - sx, ey = PY(k) - sy;
+            const int p = sc.pt(k);
+            const int ex = (p >> 4) - sx, ey = (p & 15) - sy;
             const int d = ex * ex + ey * ey;
             if (d > maxd) { maxd = d; far = j; }
         }
@@ -162,7 +163,7 @@ __device__ void approx_and_emit(S& sc, int n, bool legacy, Emit emit) {
     // 2. Douglas-Peucker.  A leaf slice (s,e) keeps P[s]; the kept set is order independent, so the
     // larger half is deferred and the explicit stack stays logarithmic.
     sc.kept_clear(n);
-    int st_s[16], st_e[16];
+    int st_s[12], st_e[12];
     int sp = 0;
     st_s[sp] = fp; st_e[sp] = pos; ++sp;
     st_s[sp] = pos; st_e[sp] = fp; ++sp;
@@ -179,7 +180,8 @@ __device__ void approx_and_emit(S& sc, int n, bool legacy, Emit emit) {
             int k = s;
             for (int t = 1; t < len; ++t) {
                 k = (k + 1 == n) ? 0 : k + 1;
-                const int vx = PX(k) - sx, vy = PY(k) - sy;
+                const int p = sc.pt(k);
+                const int vx = (p >> 4) - sx, vy = (p & 15) - sy;
                 int num;
                 if (legacy) {
                     const int cr = vy * dx - vx * dy;
@@ -203,21 +205,19 @@ __device__ void approx_and_emit(S& sc, int n, bool legacy, Emit emit) {
             else          { st_s[sp] = s;  st_e[sp] = bi; ++sp; s = bi; }
         }
     }
-    // 3. ring Q = kept points in contour order starting at pos; clean-up of nearly collinear points
+    // 3. ring Q = kept points in contour order starting at pos; OpenCV's clean-up pass removes nearly
+    // collinear points on diagonal chords.  It writes into a copy of Q and returns the first
+    // `new_count` entries; that sequence is regenerated on the fly here instead of being stored.
     const int c = sc.kept_count(n);
-    {
-        int ci = pos;
-        for (int k = 0; k < c; ++k) { sc.set_ds(k, sc.pt(ci)); ci = sc.kept_next(ci, n); }
-    }
-    int new_count = c;
-    if (c > 2) {
-        int last = pos;
-        for (int k = 0; k + 1 < c; ++k) last = sc.kept_next(last, n);
+    int last = pos;                                   // Q[c-1]
+    for (int k = 0; k + 1 < c; ++k) last = sc.kept_next(last, n);
+    // generator of the written values: calls sink(value) for each write, returns the final new_count
+    auto cleanup = [&](auto sink, int max_writes) -> int {
+        int new_count = c;
         int start = sc.pt(last);
         int ci = pos;
         int pt = sc.pt(ci); ci = sc.kept_next(ci, n);
-        int wpos = 0;
-        int i = 0;
+        int i = 0, writes = 0;
         while (i < c && new_count > 2) {
             const int end = sc.pt(ci); ci = sc.kept_next(ci, n);
             const int dx = (end >> 4) - (start >> 4), dy = (end & 15) - (start & 15);
@@ -227,61 +227,97 @@ __device__ void approx_and_emit(S& sc, int n, bool legacy, Emit emit) {
             if (2 * dist * dist <= dx * dx + dy * dy && dx != 0 && dy != 0 && ip >= 0) {
                 --new_count;
                 start = end;
-                sc.set_ds(wpos, end); wpos = (wpos + 1 == c) ? 0 : wpos + 1;
+                if (writes < max_writes) sink(end);
+                ++writes;
                 pt = sc.pt(ci); ci = sc.kept_next(ci, n);
                 i += 2;
                 continue;
             }
             start = pt;
-            sc.set_ds(wpos, pt); wpos = (wpos + 1 == c) ? 0 : wpos + 1;
+            if (writes < max_writes) sink(pt);
+            ++writes;
             pt = end;
             ++i;
         }
+        return new_count | (writes << 16);
+    };
+    int nc = c, writes = c;
+    if (c > 2) {
+        const int r = cleanup([](int) {}, 0);
+        nc = r & 0xFFFF; writes = r >> 16;
     }
-    // 4. find_convex_vetex: all points if <= 3, else strictly clockwise turns (cross < 0)
-    if (new_count <= 3) {
-        for (int k = 0; k < new_count; ++k) { const int p = sc.ds(k); emit(p >> 4, p & 15); }
-    } else {
-        int a = sc.ds(new_count - 1), bpt = sc.ds(0);
-        for (int k = 0; k < new_count; ++k) {
-            const int cpt = sc.ds(k + 1 == new_count ? 0 : k + 1);
-            const int abx = (bpt >> 4) - (a >> 4), aby = (bpt & 15) - (a & 15);
-            const int acx = (cpt >> 4) - (a >> 4), acy = (cpt & 15) - (a & 15);
-            if (abx * acy - aby * acx < 0) emit(bpt >> 4, bpt & 15);
-            a = bpt; bpt = cpt;
+    if (nc == c) {
+        // nothing dropped: the polygon is Q itself
+        if (c <= 3) {
+            int ci = pos;
+            for (int k = 0; k < c; ++k) { const int p = sc.pt(ci); emit(p >> 4, p & 15); ci = sc.kept_next(ci, n); }
+        } else {
+            int a = sc.pt(last), ci = pos, bpt = sc.pt(ci);
+            for (int k = 0; k < c; ++k) {
+                ci = sc.kept_next(ci, n);
+                const int cpt = sc.pt(ci);
+                const int abx = (bpt >> 4) - (a >> 4), aby = (bpt & 15) - (a & 15);
+                const int acx = (cpt >> 4) - (a >> 4), acy = (cpt & 15) - (a & 15);
+                if (abx * acy - aby * acx < 0) emit(bpt >> 4, bpt & 15);      // find_convex_vetex: cross < 0
+                a = bpt; bpt = cpt;
+            }
         }
+        return;
+    }
+    if (nc <= 3) {
+        // result = dst[0..nc): written values first, untouched copies of Q beyond them
+        int k = 0;
+        cleanup([&](int v) { emit(v >> 4, v & 15); ++k; }, nc);
+        int ci = pos;
+        for (int q = 0; q < nc; ++q) { if (q >= k) { const int p = sc.pt(ci); emit(p >> 4, p & 15); } ci = sc.kept_next(ci, n); }
+        (void)writes;
+        return;
+    }
+    // nc > 3: all nc entries were written; streaming convex filter over the ring w_0 .. w_{nc-1}
+    {
+        int w0 = -1, w1 = -1, a = -1, bpt = -1, k = 0;
+        auto test = [&](int A, int B, int C) {
+            const int abx = (B >> 4) - (A >> 4), aby = (B & 15) - (A & 15);
+            const int acx = (C >> 4) - (A >> 4), acy = (C & 15) - (A & 15);
+            if (abx * acy - aby * acx < 0) emit(B >> 4, B & 15);
+        };
+        cleanup([&](int v) {
+            if (k == 0) { w0 = v; a = v; }
+            else if (k == 1) { w1 = v; bpt = v; }
+            else { test(a, bpt, v); a = bpt; bpt = v; }
+            ++k;
+        }, nc);
+        test(a, bpt, w0);      // (w_{nc-2}, w_{nc-1}, w_0)
+        test(bpt, w0, w1);     // (w_{nc-1}, w_0, w_1)
     }
 }
 
 // ---- one level image: raster scan for border starts, follow, approximate, emit --------------------
-// rows16[y] (y = 0..15) holds the unpadded 16-bit row y of the level image.  Returns false if some
-// outer contour overflowed S::CAP points (the caller re-runs the task on the overflow path; emitting
-// the other contours twice is harmless because emission is a set union).
-template <class S, class RowFn, class Emit>
-__device__ bool process_level_image(S& sc, RowFn rows16, bool legacy, Emit emit) {
-    sc.set_fg(0, 0u);
-    sc.set_fg(17, 0u);
-    for (int y = 0; y < 16; ++y) { sc.set_fg(y + 1, (rows16(y) & 0xFFFFu) << 1); sc.set_mk(y, 0u); }
+// Returns false if some outer contour overflowed S::CAP points (the caller re-runs the task on the
+// overflow path; emitting the other contours twice is harmless because emission is a set union).
+template <class S, class Emit>
+__device__ bool process_level_image(S& sc, const uint32_t* bm, bool legacy, Emit emit) {
+    for (int y = 0; y < 16; ++y) sc.set_mk(y, 0u);
     bool ok = true;
-    for (int y = 1; y <= 16; ++y) {
-        uint32_t window = 0x1FFFEu;            // padded columns still to visit in this row
-        const uint32_t f = sc.fg(y);
+    for (int y = 0; y < 16; ++y) {
+        const uint32_t f = row16(bm, y);
         if (!f) continue;
+        uint32_t window = 0xFFFFu;                          // columns still to visit in this row
         for (;;) {
-            const uint32_t m = sc.mk(y - 1);
-            const uint32_t posP = (m & 0xFFFFu) << 1, negP = (m >> 16) << 1;
-            const uint32_t outer = (f & ~posP & ~negP) & ~(f << 1);   // label 1 and left neighbour 0
-            const uint32_t hole = (f & ~negP) & ~(f >> 1);            // label >= 1 and right neighbour 0
+            const uint32_t m = sc.mk(y);
+            const uint32_t posm = m & 0xFFFFu, negm = m >> 16;
+            const uint32_t outer = (f & ~posm & ~negm) & ~(f << 1);   // label 1 and left neighbour 0
+            const uint32_t hole = (f & ~negm) & ~(f >> 1);            // label >= 1 and right neighbour 0
             const uint32_t c = (outer | hole) & window;
             if (!c) break;
             const int x = __ffs((int)c) - 1;
             const bool is_hole = !((outer >> x) & 1u);
-            const int n = follow_border(sc, x, y, is_hole);
+            const int n = follow_border(sc, bm, x, y, is_hole);
             if (!is_hole) {
                 if (n < 0) ok = false;
                 else approx_and_emit(sc, n, legacy, emit);
             }
-            window = (x >= 16) ? 0u : (0x1FFFEu & ~((2u << x) - 1u));
+            window = 0xFFFFu & ~((2u << x) - 1u);
         }
     }
     return ok;

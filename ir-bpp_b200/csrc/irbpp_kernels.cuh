@@ -21,6 +21,7 @@
 #include <stdint.h>
 #include <math.h>
 #include "irbpp_contour.cuh"
+#include "irbpp_math.cuh"
 
 namespace irbpp {
 
@@ -30,11 +31,12 @@ constexpr int STEP = 2;                  // stepSize = resolutionAct / resolutio
 constexpr int NPOSE = AX * AY;           // 256 poses per rotation
 constexpr int CTA_THREADS = 128;
 constexpr int CTA_WARPS = CTA_THREADS / 32;
-constexpr int NTRACE = 64;               // threads that run level-image tasks
+constexpr int QUOTA = 16;                // level images a warp (= rotation) contributes per round
+constexpr int NSLOT = CTA_WARPS * QUOTA; // level-image tasks per round (and per-thread scratch slots)
+constexpr int SLOT_WORDS = 9;            // 8 bitmap words + 1 pad (bank spread)
 constexpr int FAST_CAP = 64;             // contour points on the fast path
 constexpr int BIG_CAP = 1024;            // contour points on the overflow path
 constexpr int LEVEL_OFFSET = 32;         // levels in [-32, 31] -> presence bit (level + 32)
-constexpr int SLOTS_PER_WARP = 64;       // level bitmaps a warp can produce per rotation
 constexpr int MAX_QUEUE = 16;            // buffer_size limit
 constexpr double POSZ_INVALID = 1e3;     // space.py:101,126
 
@@ -93,25 +95,29 @@ struct Params {
 };
 
 // ---- shared memory carve-up -----------------------------------------------------------------------
+// Region X is time-multiplexed: heightmap (phases A, B) -> per-thread contour scratch (phase C) ->
+// float32 observation staging (phase D).
 struct SmemLayout {
-    int posz_off, maskbits_off, candbits_off, bitmaps_off, scratch_off, big_off, misc_off, stage_off, total;
+    int x_size, posz_off, slots_off, maskbits_off, candbits_off, misc_off, big_off, total;
 };
+
+constexpr int SCRATCH_BYTES = NSLOT * (16 * 4 + FAST_CAP);     // marks + contour points per task thread
 
 __host__ __device__ inline SmemLayout smem_layout(int R, int sel) {
     SmemLayout L;
-    int o = 0;
-    /* hm at 0 */ o += 2 * HX * (HY / 2) * 8;                         // 8192
+    int x = 2 * HX * (HY / 2) * 8;                                     // heightmap, 8192
+    if (x < SCRATCH_BYTES) x = SCRATCH_BYTES;
+    const int stage_need = sel * 5 * 4 + sel * 2 + 16;
+    if (x < stage_need) x = stage_need;
+    x = (x + 15) & ~15;
+    L.x_size = x;
+    int o = x;
     L.posz_off = o; o += R * NPOSE * 8;
+    L.slots_off = o; o += NSLOT * SLOT_WORDS * 4;
     L.maskbits_off = o; o += R * 8 * 4;
     L.candbits_off = o; o += R * 8 * 4;
     L.misc_off = o; o += 384;
-    // region reused by phase D as the float32 observation staging area
-    L.stage_off = o;
-    L.bitmaps_off = o; o += CTA_WARPS * SLOTS_PER_WARP * 8 * 4;       // 8192
-    L.scratch_off = o; o += NTRACE * ((18 + 16) * 4 + 2 * FAST_CAP);  // 64 * 264
-    L.big_off = o; o += (18 + 16) * 4 + 3 * BIG_CAP + 8;
-    int stage_need = sel * 5 * 4 + sel * 2 + 16;
-    if (o - L.stage_off < stage_need) o = L.stage_off + stage_need;
+    L.big_off = o; o += 16 * 4 + 2 * BIG_CAP;
     L.total = (o + 15) & ~15;
     return L;
 }
@@ -128,20 +134,6 @@ struct Misc {                    // small CTA-wide scalars in shared memory (<= 
 
 __device__ __forceinline__ int hm_index(int x, int y) { return ((y & 1) * HX + x) * (HY / 2) + (y >> 1); }
 
-// NumPy float64 floor_divide (npy_divmod), cvTools.py:78
-__device__ __forceinline__ double npy_floor_divide(double a, double b) {
-    double mod = fmod(a, b);
-    double div = (a - mod) / b;
-    if (mod != 0.0) { if ((b < 0) != (mod < 0)) div -= 1.0; }
-    double fl;
-    if (div != 0.0) { fl = floor(div); if (div - fl > 0.5) fl += 1.0; }
-    else fl = copysign(0.0, a / b);
-    return fl;
-}
-
-// np.round(v, 6) <= 0   <=>   rint(v * 1e6) <= 0
-__device__ __forceinline__ bool round6_le0(double v) { return rint(v * 1e6) <= 0.0; }
-
 __device__ __forceinline__ int draw_item(const Params& P, int env, int& cursor) {
     int id = P.seq[(int64_t)env * P.L + (cursor % P.L)];
     ++cursor;
@@ -149,17 +141,16 @@ __device__ __forceinline__ int draw_item(const Params& P, int env, int& cursor) 
 }
 
 // ---- phase B: one warp scans one rotation -----------------------------------------------------------
-// Writes posz[r][256], maskbits[r][8]; returns the per-lane levels (lv[pass]) and the presence mask.
+// Writes posz[r][256] and maskbits[r][8] (space.py:98-129).
 __device__ __forceinline__ void scan_rotation(const Params& P, const double* hm_s, double* posz_s,
-                                              uint32_t* maskbits_s, int item, int r, int lane,
-                                              int (&lv)[8], uint64_t& present, int& err) {
+                                              uint32_t* maskbits_s, int item, int r, int lane) {
     const ShapeRot* sr = P.srot + (int64_t)item * P.R + r;
     const int w = sr->w, h = sr->h, nX = sr->nX, nY = sr->nY;
     const double ez = sr->ez;
     const double init = sr->any_zero ? 0.0 : -INFINITY;
     const double* __restrict__ B = P.Bs + sr->off;
-    uint32_t pres_lo = 0, pres_hi = 0;
-#pragma unroll
+    const int hpairs = h >> 1;
+#pragma unroll 1
     for (int pass = 0; pass < 8; ++pass) {
         const int p = pass * 32 + lane;
         const int X = p >> 4, Y = p & 15;
@@ -168,48 +159,45 @@ __device__ __forceinline__ void scan_rotation(const Params& P, const double* hm_
         bool feas = false;
         if (valid) {
             acc = init;
+            const double* h0 = hm_s + (STEP * X) * (HY / 2) + Y;        // even heightmap columns
+            const double* brow = B;
             for (int i = 0; i < w; ++i) {
-                const double* hrow = hm_s + (STEP * X + i) * (HY / 2) + Y;
-                const double* brow = B + i * h;
-                for (int j = 0; j < h; ++j) {
-                    const double v = hrow[(j & 1) * (HX * (HY / 2)) + (j >> 1)] - __ldg(brow + j);
-                    acc = (v > acc) ? v : acc;
+                const double* h1 = h0 + HX * (HY / 2);                   // odd heightmap columns
+                int jj = 0;
+                for (; jj < hpairs; ++jj) {
+                    const double v0 = h0[jj] - __ldg(brow + 2 * jj);
+                    const double v1 = h1[jj] - __ldg(brow + 2 * jj + 1);
+                    acc = (v0 > acc) ? v0 : acc;
+                    acc = (v1 > acc) ? v1 : acc;
                 }
+                if (h & 1) {
+                    const double v0 = h0[jj] - __ldg(brow + 2 * jj);
+                    acc = (v0 > acc) ? v0 : acc;
+                }
+                h0 += HY / 2;
+                brow += h;
             }
             feas = round6_le0(acc + ez - P.binz);
         }
         posz_s[r * NPOSE + p] = acc;
         const uint32_t mb = __ballot_sync(0xffffffffu, feas);
         if (lane == 0) maskbits_s[r * 8 + pass] = mb;
-        int L = -1;
-        if (feas) {
-            const double fl = npy_floor_divide(acc, P.resZ);
-            L = (int)fl;
-            if (L < -LEVEL_OFFSET || L >= LEVEL_OFFSET) { err = 1; L = -1; }
-            if (L != -1) {
-                const int b = L + LEVEL_OFFSET;
-                if (b < 32) pres_lo |= 1u << b; else pres_hi |= 1u << (b - 32);
-            }
-        }
-        lv[pass] = L;
     }
-    pres_lo = __reduce_or_sync(0xffffffffu, pres_lo);
-    pres_hi = __reduce_or_sync(0xffffffffu, pres_hi);
-    present = ((uint64_t)pres_hi << 32) | pres_lo;
 }
 
-// levels from caller-supplied maps (MODE_DEBUG_HULLS)
+// level quantisation (cvTools.py:78-79): lv[pass] = posZ // resZ for feasible poses, -1 otherwise;
+// `present` gets bit (level + LEVEL_OFFSET) for every level in this rotation
 __device__ __forceinline__ void levels_from_maps(const Params& P, const double* posz_s, const uint32_t* maskbits_s,
                                                  int r, int lane, int (&lv)[8], uint64_t& present, int& err) {
     uint32_t pres_lo = 0, pres_hi = 0;
+    const double inv = 1.0 / P.resZ;
 #pragma unroll
     for (int pass = 0; pass < 8; ++pass) {
         const int p = pass * 32 + lane;
         const bool feas = (maskbits_s[r * 8 + pass] >> lane) & 1u;
         int L = -1;
         if (feas) {
-            const double fl = npy_floor_divide(posz_s[r * NPOSE + p], P.resZ);
-            L = (int)fl;
+            L = (int)floor_divide_exact(posz_s[r * NPOSE + p], P.resZ, inv);
             if (L < -LEVEL_OFFSET || L >= LEVEL_OFFSET) { err = 1; L = -1; }
             if (L != -1) {
                 const int b = L + LEVEL_OFFSET;
@@ -223,11 +211,12 @@ __device__ __forceinline__ void levels_from_maps(const Params& P, const double* 
     present = ((uint64_t)pres_hi << 32) | pres_lo;
 }
 
-// one 16x16 bitmap (8 words, two rows each) per level present in this rotation, by warp ballots
-__device__ __forceinline__ int build_level_bitmaps(uint32_t* bitmaps_s, int warp, int lane, const int (&lv)[8],
-                                                   uint64_t present) {
+// up to QUOTA 16x16 bitmaps (8 words, two rows each) for the next levels in `present`, by warp ballots;
+// consumed levels are removed from `present`
+__device__ __forceinline__ int build_level_bitmaps(uint32_t* slots_s, int warp, int lane, const int (&lv)[8],
+                                                   uint64_t& present) {
     int k = 0;
-    while (present) {
+    while (present && k < QUOTA) {
         const int b = __ffsll((long long)present) - 1;
         present &= present - 1;
         const int L = b - LEVEL_OFFSET;
@@ -237,29 +226,29 @@ __device__ __forceinline__ int build_level_bitmaps(uint32_t* bitmaps_s, int warp
             const uint32_t bits = __ballot_sync(0xffffffffu, lv[pass] == L);
             if (lane == pass) mine = bits;
         }
-        if (lane < 8) bitmaps_s[(warp * SLOTS_PER_WARP + k) * 8 + lane] = mine;
+        if (lane < 8) slots_s[(warp * QUOTA + k) * SLOT_WORDS + lane] = mine;
         ++k;
     }
     return k;
 }
 
 // ---- the kernel -------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(CTA_THREADS) irbpp_env_kernel(const Params P) {
+__global__ void __launch_bounds__(CTA_THREADS, 8) irbpp_env_kernel(const Params P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int env = blockIdx.x;
     const int slot = blockIdx.y;                 // MODE_ALL_OBS only
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const SmemLayout SL = smem_layout(P.R, P.sel);
-    double* hm_s = reinterpret_cast<double*>(smem_raw);
+    double* hm_s = reinterpret_cast<double*>(smem_raw);                      // region X, phases A-B
+    unsigned char* scratch_s = smem_raw;                                      // region X, phase C
+    float* stage_f = reinterpret_cast<float*>(smem_raw);                      // region X, phase D
+    uint16_t* stage_c = reinterpret_cast<uint16_t*>(smem_raw + P.sel * 5 * 4);
     double* posz_s = reinterpret_cast<double*>(smem_raw + SL.posz_off);
+    uint32_t* slots_s = reinterpret_cast<uint32_t*>(smem_raw + SL.slots_off);
     uint32_t* maskbits_s = reinterpret_cast<uint32_t*>(smem_raw + SL.maskbits_off);
     uint32_t* candbits_s = reinterpret_cast<uint32_t*>(smem_raw + SL.candbits_off);
-    uint32_t* bitmaps_s = reinterpret_cast<uint32_t*>(smem_raw + SL.bitmaps_off);
-    unsigned char* scratch_s = smem_raw + SL.scratch_off;
     unsigned char* big_s = smem_raw + SL.big_off;
     Misc* misc = reinterpret_cast<Misc*>(smem_raw + SL.misc_off);
-    float* stage_f = reinterpret_cast<float*>(smem_raw + SL.stage_off);
-    uint16_t* stage_c = reinterpret_cast<uint16_t*>(smem_raw + SL.stage_off + P.sel * 5 * 4);
 
     const int mode = P.mode;
     if (mode == MODE_RESET && P.which && !P.which[env]) return;
@@ -418,86 +407,102 @@ __global__ void __launch_bounds__(CTA_THREADS) irbpp_env_kernel(const Params P) 
     }
 
     float* obs_g = P.obs + (int64_t)env * P.obs_stride + (mode == MODE_ALL_OBS ? slot * P.loc_len : 0);
+    const int item = misc->item;
+    const int ncand = P.sel * 5;
 
-    if (!emit_loc) {
-        // order observation: [next k item ids | heightmap]  (binPhy.py:229-230)
-        for (int i = tid; i < P.K; i += CTA_THREADS) obs_g[i] = (float)queue_g[i];
+    // the heightmap is final for this call: emit its float32 copy and write the state back now, so
+    // region X can be recycled after the scan
+    {
+        const int hm_obs_off = emit_loc ? ncand + 9 : P.K;
         for (int i = tid; i < HX * HY; i += CTA_THREADS)
-            obs_g[P.K + i] = (float)hm_s[hm_index(i >> 5, i & 31)];
+            obs_g[hm_obs_off + i] = (float)hm_s[hm_index(i >> 5, i & 31)];
         if (mode == MODE_STEP || mode == MODE_RESET) {
             double2* dst = reinterpret_cast<double2*>(hm_g);
             const double2* src = reinterpret_cast<const double2*>(hm_s);
             for (int i = tid; i < HX * HY / 2; i += CTA_THREADS) dst[i] = src[i];
         }
+    }
+    if (!emit_loc) {
+        // order observation: [next k item ids | heightmap]  (binPhy.py:229-230)
+        for (int i = tid; i < P.K; i += CTA_THREADS) obs_g[i] = (float)queue_g[i];
         if (tid == 0 && misc->error) P.r_error[env] = (uint8_t)misc->error;
         return;
     }
 
-    // ---- phases B + C: rotations in groups of CTA_WARPS ----
-    const int item = misc->item;
+    // ---- phase B: drop height + feasibility of every pose, one warp per rotation ----
+    if (mode != MODE_DEBUG_HULLS) {
+        for (int r = warp; r < P.R; r += CTA_WARPS) scan_rotation(P, hm_s, posz_s, maskbits_s, item, r, lane);
+    }
+    __syncthreads();                       // heightmap dead from here on: region X becomes contour scratch
+
+    // ---- phase C: candidate extraction, rotations in groups of CTA_WARPS ----
     const int ngroups = (P.R + CTA_WARPS - 1) / CTA_WARPS;
     for (int g = 0; g < ngroups; ++g) {
         const int r = g * CTA_WARPS + warp;
-        int nl = 0;
+        int lv[8];
+        uint64_t present = 0;
         if (r < P.R) {
-            int lv[8];
-            uint64_t present = 0;
             int err = 0;
-            if (mode == MODE_DEBUG_HULLS) levels_from_maps(P, posz_s, maskbits_s, r, lane, lv, present, err);
-            else scan_rotation(P, hm_s, posz_s, maskbits_s, item, r, lane, lv, present, err);
+            levels_from_maps(P, posz_s, maskbits_s, r, lane, lv, present, err);
             if (__any_sync(0xffffffffu, err) && lane == 0) misc->error = 4;
             present &= ~(1ull << (LEVEL_OFFSET - 1));        // level -1 is skipped (cvTools.py:84)
-            nl = build_level_bitmaps(bitmaps_s, warp, lane, lv, present);
         }
-        if (lane == 0) misc->nlev[warp] = nl;
-        __syncthreads();
-        // one thread per (rotation, level) image
-        if (tid < NTRACE) {
+        for (;;) {                                           // rounds of at most QUOTA levels per rotation
+            int nl = 0;
+            if (r < P.R) nl = build_level_bitmaps(slots_s, warp, lane, lv, present);
+            if (lane == 0) misc->nlev[warp] = nl;
+            __syncthreads();
             int pre[CTA_WARPS + 1];
             pre[0] = 0;
 #pragma unroll
             for (int q = 0; q < CTA_WARPS; ++q) pre[q + 1] = pre[q] + misc->nlev[q];
-            StridedScratch<NTRACE, FAST_CAP> sc;
-            sc.w = reinterpret_cast<uint32_t*>(scratch_s) + tid;
-            sc.b = scratch_s + NTRACE * (18 + 16) * 4 + tid;
-            sc.kept = 0;
-            for (int t = tid; t < pre[CTA_WARPS]; t += NTRACE) {
+            const int ntask = pre[CTA_WARPS];
+            if (ntask == 0) break;                           // uniform: every warp sees the same counts
+            // one thread per (rotation, level) image; tasks are dealt round-robin to the warps
+            const int t = lane * CTA_WARPS + warp;
+            if (lane < QUOTA && t < ntask) {
                 int wq = 0;
 #pragma unroll
                 for (int q = 1; q < CTA_WARPS; ++q) if (t >= pre[q]) wq = q;
-                const int rr = g * CTA_WARPS + wq;
-                const uint32_t* bm = bitmaps_s + (wq * SLOTS_PER_WARP + (t - pre[wq])) * 8;
-                uint32_t* cb = candbits_s + rr * 8;
+                const int sl = wq * QUOTA + (t - pre[wq]);
+                const int sidx = warp * QUOTA + lane;
+                StridedScratch<NSLOT, FAST_CAP> sc;
+                sc.w = reinterpret_cast<uint32_t*>(scratch_s) + sidx;
+                sc.b = scratch_s + NSLOT * 16 * 4 + sidx;
+                sc.kept = 0;
+                const uint32_t* bm = slots_s + sl * SLOT_WORDS;
+                uint32_t* cb = candbits_s + (g * CTA_WARPS + wq) * 8;
                 const bool okc = process_level_image(
-                    sc, [&](int y) { return bm[y >> 1] >> ((y & 1) * 16); }, P.legacy != 0,
+                    sc, bm, P.legacy != 0,
                     [&](int x, int y) { const int b = x * 16 + y; atomicOr(cb + (b >> 5), 1u << (b & 31)); });
                 if (!okc) {
                     const int k = atomicAdd(&misc->ovf_count, 1);
-                    if (k < 32) misc->ovf_task[k] = (wq << 16) | (t - pre[wq]);
+                    if (k < 32) misc->ovf_task[k] = (wq << 16) | sl;
                 }
-            }
-        }
-        __syncthreads();
-        if (misc->ovf_count > 0) {          // rare: contours longer than FAST_CAP points, serial path
-            if (tid == 0) {
-                FlatScratch<BIG_CAP> bs;
-                bs.w = reinterpret_cast<uint32_t*>(big_s);
-                bs.b = big_s + (18 + 16) * 4;
-                const int n_ovf = misc->ovf_count;
-                if (n_ovf > 32) misc->error = 5;
-                for (int k = 0; k < (n_ovf < 32 ? n_ovf : 32); ++k) {
-                    const int wq = misc->ovf_task[k] >> 16, sl = misc->ovf_task[k] & 0xFFFF;
-                    const uint32_t* bm = bitmaps_s + (wq * SLOTS_PER_WARP + sl) * 8;
-                    uint32_t* cb = candbits_s + (g * CTA_WARPS + wq) * 8;
-                    const bool okc = process_level_image(
-                        bs, [&](int y) { return bm[y >> 1] >> ((y & 1) * 16); }, P.legacy != 0,
-                        [&](int x, int y) { const int b = x * 16 + y; cb[b >> 5] |= 1u << (b & 31); });
-                    if (!okc) misc->error = 6;
-                }
-                misc->ovf_count = 0;
             }
             __syncthreads();
+            if (misc->ovf_count > 0) {          // rare: contours longer than FAST_CAP points, serial path
+                if (tid == 0) {
+                    FlatScratch<BIG_CAP> bs;
+                    bs.w = reinterpret_cast<uint32_t*>(big_s);
+                    bs.b = big_s + 16 * 4;
+                    const int n_ovf = misc->ovf_count;
+                    if (n_ovf > 32) misc->error = 5;
+                    for (int k = 0; k < (n_ovf < 32 ? n_ovf : 32); ++k) {
+                        const int wq = misc->ovf_task[k] >> 16, sl = misc->ovf_task[k] & 0xFFFF;
+                        const uint32_t* bm = slots_s + sl * SLOT_WORDS;
+                        uint32_t* cb = candbits_s + (g * CTA_WARPS + wq) * 8;
+                        const bool okc = process_level_image(
+                            bs, bm, P.legacy != 0,
+                            [&](int x, int y) { const int b = x * 16 + y; cb[b >> 5] |= 1u << (b & 31); });
+                        if (!okc) misc->error = 6;
+                    }
+                    misc->ovf_count = 0;
+                }
+                __syncthreads();
+            }
         }
+        __syncthreads();     // nobody may still be reading misc->nlev when the next group rewrites it
     }
 
     // ---- phase D: select / pad, observation assembly ----
@@ -533,7 +538,7 @@ __global__ void __launch_bounds__(CTA_THREADS) irbpp_env_kernel(const Params P) 
         stage_c[row] = 0;
         if (dbg_cand) { double* q = dbg_cand + row * 5; q[0] = q[1] = q[2] = q[3] = q[4] = 0.0; }
     };
-    // (the staging area aliases the bitmaps / scratch regions, which are dead from here on)
+    // (the staging area is region X: heightmap and contour scratch are dead from here on)
     if (Ktot == 0) {
         // no hull candidate at all (binPhy.py:217-225): the `sel` smallest posZValid, stable order
         const int total = P.R * NPOSE;
@@ -598,20 +603,12 @@ __global__ void __launch_bounds__(CTA_THREADS) irbpp_env_kernel(const Params P) 
     __syncthreads();
 
     // observation: [candidates sel*5 | next_item_vec 9 | heightmap]  (binPhy.py:196-227)
-    const int ncand = sel * 5;
     for (int i = tid; i < ncand; i += CTA_THREADS) obs_g[i] = stage_f[i];
     if (tid < 9) obs_g[ncand + tid] = (tid == 0) ? (float)item : 0.0f;
-    for (int i = tid; i < HX * HY; i += CTA_THREADS)
-        obs_g[ncand + 9 + i] = (float)hm_s[hm_index(i >> 5, i & 31)];
 
     if (write_state) {
         uint16_t* cg = P.cand + (int64_t)env * sel;
         for (int i = tid; i < sel; i += CTA_THREADS) cg[i] = stage_c[i];
-        if (mode == MODE_STEP || mode == MODE_RESET) {
-            double2* dst = reinterpret_cast<double2*>(hm_g);
-            const double2* src = reinterpret_cast<const double2*>(hm_s);
-            for (int i = tid; i < HX * HY / 2; i += CTA_THREADS) dst[i] = src[i];
-        }
         if (tid == 0) { P.cur_item[env] = item; P.mask_any[env] = (uint8_t)misc->any_mask; }
     }
     if (tid == 0 && misc->error) P.r_error[env] = (uint8_t)misc->error;
