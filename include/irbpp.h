@@ -154,6 +154,11 @@ int irbpp_debug_hulls(irbpp_handle h, const double* posZValid, const double* mas
 /* Kernel launches issued by this handle so far (bench.py's gpu_launches). */
 int64_t irbpp_launch_count(irbpp_handle h);
 
+/* Profiling aid: when enabled, thread 0 of every CTA adds the SM cycles it spent in each kernel phase
+ * (0 load+apply, 1 scan, 2 candidate extraction, 3 select/pad, 4 stores) to 8 counters.  The call
+ * returns the counters accumulated so far in out8 (may be NULL), clears them and sets the switch. */
+int irbpp_debug_phase_cycles(irbpp_handle h, int32_t enable, uint64_t* out8);
+
 #ifdef __cplusplus
 }
 #endif

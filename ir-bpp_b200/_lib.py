@@ -6,7 +6,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libirbpp.so")
+LIB_PATH = os.environ.get("IRBPP_LIB") or os.path.join(HERE, "lib", "libirbpp.so")   # IRBPP_LIB: build-variant experiments
 
 c_i32, c_i64, c_f64 = ctypes.c_int32, ctypes.c_int64, ctypes.c_double
 c_void_p, c_char_p = ctypes.c_void_p, ctypes.c_char_p
@@ -46,6 +46,7 @@ SIGNATURES = {
     "irbpp_debug_scan": (c_i32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "irbpp_debug_hulls": (c_i32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "irbpp_launch_count": (c_i64, [c_void_p]),
+    "irbpp_debug_phase_cycles": (c_i32, [c_void_p, c_i32, c_void_p]),
 }
 
 _LIB = None

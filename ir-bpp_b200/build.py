@@ -10,6 +10,8 @@ DEPS = [SRC, os.path.join(HERE, "csrc", "irbpp_kernels.cuh"), os.path.join(HERE,
         os.path.join(ROOT, "include", "irbpp.h")]
 OUT_DIR = os.path.join(HERE, "lib")
 OUT = os.path.join(OUT_DIR, "libirbpp.so")
+# experiment hook: extra -D flags and an alternative output name (IRBPP_LIB selects it at load time)
+EXTRA_DEFS = os.environ.get("IRBPP_BUILD_DEFS", "").split()
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-fmad=false",                      # float64 must round exactly like NumPy: no FMA contraction
@@ -30,18 +32,21 @@ def up_to_date():
     return all(os.path.getmtime(d) <= t for d in DEPS)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, out=None, defs=None):
     """Compile ``csrc/irbpp.cu`` -> ``lib/libirbpp.so`` (nvcc cross-compiles without a GPU)."""
-    if not force and up_to_date():
-        return OUT
+    defs = EXTRA_DEFS if defs is None else defs
+    if out is None:
+        out = OUT
+        if not force and not defs and up_to_date():
+            return OUT
     os.makedirs(OUT_DIR, exist_ok=True)
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
+    cmd = [nvcc_path()] + NVCC_FLAGS + list(defs) + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, SRC]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose:
         sys.stderr.write(res.stderr)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n%s\n%s" % (" ".join(cmd), res.stderr))
-    return OUT
+    return out
 
 
 if __name__ == "__main__":

@@ -37,6 +37,7 @@ struct irbpp_env {
     // shape pools
     ShapeRot* srot_dev = nullptr; double* Bs_dev = nullptr; double* Ts_dev = nullptr;
     double* vol_dev = nullptr; double* rew_dev = nullptr; int32_t* seq_dev = nullptr;
+    unsigned long long* phase_dev = nullptr;
 };
 
 static int fail(irbpp_env* h, int code, const char* fmt, ...) {
@@ -488,5 +489,16 @@ int irbpp_debug_hulls(irbpp_handle h, const double* posZValid, const double* mas
 }
 
 int64_t irbpp_launch_count(irbpp_handle h) { return h ? h->launches : 0; }
+
+int irbpp_debug_phase_cycles(irbpp_handle h, int32_t enable, uint64_t* out8) {
+    if (!h) return IRBPP_EINVAL;
+    cudaSetDevice(h->cfg.device);
+    if (!h->phase_dev) CUDA_TRY(h, dev_alloc(h, &h->phase_dev, 8));
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    if (out8) CUDA_TRY(h, cudaMemcpy(out8, h->phase_dev, 8 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    CUDA_TRY(h, cudaMemset(h->phase_dev, 0, 8 * sizeof(uint64_t)));
+    h->P.phase_cycles = enable ? h->phase_dev : nullptr;
+    return IRBPP_OK;
+}
 
 }  // extern "C"

@@ -323,4 +323,57 @@ __device__ bool process_level_image(S& sc, const uint32_t* bm, bool legacy, Emit
     return ok;
 }
 
+// ---- warp-lockstep variant --------------------------------------------------------------------------
+// Called by ALL 32 lanes of a warp (lanes without a task pass has_task = false).  Lane-private work is
+// the same as process_level_image, but the lanes advance contour by contour together: every lane
+// first finds ITS next border start, then all lanes with one follow their borders at the same time,
+// then the lanes holding an outer border approximate it at the same time.  This keeps the lanes of a
+// warp inside the same loops (SIMT efficiency = how similar the trip counts are) instead of
+// serialising on where in the raster scan each image happens to have a contour.
+template <class S, class Emit>
+__device__ bool process_level_image_lockstep(S& sc, const uint32_t* bm, bool has_task, bool legacy, Emit emit) {
+    bool active = has_task;
+    bool ok = true;
+    int y = 0;
+    uint32_t window = 0xFFFFu;
+    if (active) { for (int q = 0; q < 16; ++q) sc.set_mk(q, 0u); }
+    for (;;) {
+        int x = 0;
+        bool is_hole = false;
+        if (active) {
+            bool found = false;
+            while (y < 16) {
+                const uint32_t f = row16(bm, y);
+                if (f) {
+                    const uint32_t m = sc.mk(y);
+                    const uint32_t posm = m & 0xFFFFu, negm = m >> 16;
+                    const uint32_t outer = (f & ~posm & ~negm) & ~(f << 1);   // label 1 and left neighbour 0
+                    const uint32_t hole = (f & ~negm) & ~(f >> 1);            // label >= 1 and right neighbour 0
+                    const uint32_t c = (outer | hole) & window;
+                    if (c) {
+                        x = __ffs((int)c) - 1;
+                        is_hole = !((outer >> x) & 1u);
+                        found = true;
+                        break;
+                    }
+                }
+                ++y;
+                window = 0xFFFFu;
+            }
+            active = found;
+        }
+        if (!__any_sync(0xffffffffu, active)) break;
+        int n = 0;
+        if (active) {
+            n = follow_border(sc, bm, x, y, is_hole);
+            window = 0xFFFFu & ~((2u << x) - 1u);
+        }
+        if (active && !is_hole) {
+            if (n < 0) ok = false;
+            else approx_and_emit(sc, n, legacy, emit);
+        }
+    }
+    return ok;
+}
+
 }  // namespace irbpp

@@ -31,8 +31,18 @@ constexpr int STEP = 2;                  // stepSize = resolutionAct / resolutio
 constexpr int NPOSE = AX * AY;           // 256 poses per rotation
 constexpr int CTA_THREADS = 128;
 constexpr int CTA_WARPS = CTA_THREADS / 32;
-constexpr int QUOTA = 16;                // level images a warp (= rotation) contributes per round
+#ifndef IRBPP_QUOTA
+#define IRBPP_QUOTA 16
+#endif
+constexpr int QUOTA = IRBPP_QUOTA;       // level images a warp (= rotation) contributes per round
 constexpr int NSLOT = CTA_WARPS * QUOTA; // level-image tasks per round (and per-thread scratch slots)
+#ifndef IRBPP_TRACE_WARPS
+#define IRBPP_TRACE_WARPS 2
+#endif
+constexpr int TRACE_WARPS = IRBPP_TRACE_WARPS;          // warps that run the level-image tasks
+constexpr int TRACE_LANES = NSLOT / TRACE_WARPS;        // task lanes per tracing warp (<= 32)
+constexpr int TRACE_WARPS_DIV = 1;
+static_assert(TRACE_LANES <= 32 && TRACE_LANES * TRACE_WARPS == NSLOT, "task lanes must tile the slots");
 constexpr int SLOT_WORDS = 9;            // 8 bitmap words + 1 pad (bank spread)
 constexpr int FAST_CAP = 64;             // contour points on the fast path
 constexpr int BIG_CAP = 1024;            // contour points on the overflow path
@@ -91,6 +101,7 @@ struct Params {
     float* r_reward; uint8_t* r_done; uint8_t* r_valid; uint8_t* r_error;
     int32_t* r_counter; int32_t* r_eplen; double* r_ratio; double* r_eprew;
     double* dbg_posz; double* dbg_poszv; double* dbg_mask; double* dbg_cand; int32_t* dbg_nhull;
+    unsigned long long* phase_cycles;    // [8] summed SM cycles per phase (thread 0 of every CTA), or NULL
     int32_t mode;
 };
 
@@ -252,6 +263,14 @@ __global__ void __launch_bounds__(CTA_THREADS, 8) irbpp_env_kernel(const Params 
 
     const int mode = P.mode;
     if (mode == MODE_RESET && P.which && !P.which[env]) return;
+    long long t_prev = P.phase_cycles ? clock64() : 0;
+    auto phase_mark = [&](int idx) {
+        if (P.phase_cycles && tid == 0) {
+            const long long now = clock64();
+            atomicAdd(P.phase_cycles + idx, (unsigned long long)(now - t_prev));
+            t_prev = now;
+        }
+    };
 
     // ---- load heightmap (column-parity planes, 8 KB) ----
     double* hm_g = P.hm + (int64_t)env * (HX * HY);
@@ -406,6 +425,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 8) irbpp_env_kernel(const Params 
         __syncthreads();
     }
 
+    phase_mark(0);   // load + phase A
     float* obs_g = P.obs + (int64_t)env * P.obs_stride + (mode == MODE_ALL_OBS ? slot * P.loc_len : 0);
     const int item = misc->item;
     const int ncand = P.sel * 5;
@@ -434,6 +454,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 8) irbpp_env_kernel(const Params 
         for (int r = warp; r < P.R; r += CTA_WARPS) scan_rotation(P, hm_s, posz_s, maskbits_s, item, r, lane);
     }
     __syncthreads();                       // heightmap dead from here on: region X becomes contour scratch
+    phase_mark(1);   // heightmap write-back + scan
 
     // ---- phase C: candidate extraction, rotations in groups of CTA_WARPS ----
     const int ngroups = (P.R + CTA_WARPS - 1) / CTA_WARPS;
@@ -458,22 +479,26 @@ __global__ void __launch_bounds__(CTA_THREADS, 8) irbpp_env_kernel(const Params 
             for (int q = 0; q < CTA_WARPS; ++q) pre[q + 1] = pre[q] + misc->nlev[q];
             const int ntask = pre[CTA_WARPS];
             if (ntask == 0) break;                           // uniform: every warp sees the same counts
-            // one thread per (rotation, level) image; tasks are dealt round-robin to the warps
-            const int t = lane * CTA_WARPS + warp;
-            if (lane < QUOTA && t < ntask) {
+            // one lane per (rotation, level) image; the first TRACE_WARPS warps take the tasks, all their
+            // lanes enter the lock-step routine together
+            if (warp < TRACE_WARPS) {
+                const int li = lane / TRACE_WARPS_DIV;                 // (unused when TRACE_LANES == 32)
+                (void)li;
+                const int t = lane * TRACE_WARPS + warp;
+                const bool has = (lane < TRACE_LANES) && (t < ntask);
                 int wq = 0;
 #pragma unroll
-                for (int q = 1; q < CTA_WARPS; ++q) if (t >= pre[q]) wq = q;
-                const int sl = wq * QUOTA + (t - pre[wq]);
-                const int sidx = warp * QUOTA + lane;
+                for (int q = 1; q < CTA_WARPS; ++q) if (has && t >= pre[q]) wq = q;
+                const int sl = has ? wq * QUOTA + (t - pre[wq]) : 0;
+                const int sidx = warp * TRACE_LANES + (lane < TRACE_LANES ? lane : 0);
                 StridedScratch<NSLOT, FAST_CAP> sc;
                 sc.w = reinterpret_cast<uint32_t*>(scratch_s) + sidx;
                 sc.b = scratch_s + NSLOT * 16 * 4 + sidx;
                 sc.kept = 0;
                 const uint32_t* bm = slots_s + sl * SLOT_WORDS;
                 uint32_t* cb = candbits_s + (g * CTA_WARPS + wq) * 8;
-                const bool okc = process_level_image(
-                    sc, bm, P.legacy != 0,
+                const bool okc = process_level_image_lockstep(
+                    sc, bm, has, P.legacy != 0,
                     [&](int x, int y) { const int b = x * 16 + y; atomicOr(cb + (b >> 5), 1u << (b & 31)); });
                 if (!okc) {
                     const int k = atomicAdd(&misc->ovf_count, 1);
@@ -505,6 +530,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 8) irbpp_env_kernel(const Params 
         __syncthreads();     // nobody may still be reading misc->nlev when the next group rewrites it
     }
 
+    phase_mark(2);   // levels, bitmaps, contour tasks
     // ---- phase D: select / pad, observation assembly ----
     if (tid < 32) {
         int c = 0;
@@ -602,6 +628,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 8) irbpp_env_kernel(const Params 
     }
     __syncthreads();
 
+    phase_mark(3);   // select / pad into the staging area
     // observation: [candidates sel*5 | next_item_vec 9 | heightmap]  (binPhy.py:196-227)
     for (int i = tid; i < ncand; i += CTA_THREADS) obs_g[i] = stage_f[i];
     if (tid < 9) obs_g[ncand + tid] = (tid == 0) ? (float)item : 0.0f;
@@ -624,6 +651,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 8) irbpp_env_kernel(const Params 
         }
     }
     if (P.dbg_nhull && tid == 0) P.dbg_nhull[env] = Ktot;
+    phase_mark(4);   // observation / state stores
 }
 
 }  // namespace irbpp

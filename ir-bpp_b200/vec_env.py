@@ -322,6 +322,12 @@ class GpuVecEnv(VecEnv):
     def launch_count(self):
         return int(self._lib.irbpp_launch_count(self._h))
 
+    def debug_phase_cycles(self, enable=True):
+        """Read-and-clear the per-phase SM-cycle counters (see include/irbpp.h) and set the switch."""
+        out = np.zeros(8, dtype=np.uint64)
+        self._check(self._lib.irbpp_debug_phase_cycles(self._h, 1 if enable else 0, out.ctypes.data))
+        return out
+
     def debug_state(self):
         n, k = self.num_envs, max(self.buffer_size, 1)
         hm = np.zeros((n, 32, 32)); queue = np.zeros((n, k), np.int32)

@@ -11,6 +11,7 @@ static inline int __ffs(int x) { return __builtin_ffs(x); }
 static inline int __ffsll(long long x) { return __builtin_ffsll(x); }
 static inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
 static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
+static inline int __any_sync(unsigned, int p) { return p; }   // one "lane": the lock-step variant degenerates to serial
 #include "../../ir-bpp_b200/csrc/irbpp_contour.cuh"
 #include "../../ir-bpp_b200/csrc/irbpp_math.cuh"
 
@@ -19,13 +20,14 @@ extern "C" int hull_bits(const uint16_t* rows, int legacy, int use_big, uint32_t
     uint32_t bm[8];
     for (int i = 0; i < 8; ++i) bm[i] = (uint32_t)rows[2 * i] | ((uint32_t)rows[2 * i + 1] << 16);
     auto emit = [&](int x, int y) { const int b = x * 16 + y; out_bits[b >> 5] |= 1u << (b & 31); };
-    if (use_big) {
+    if (use_big == 1) {
         static uint32_t w[16]; static uint8_t b[2 * 1024];
         irbpp::FlatScratch<1024> sc; sc.w = w; sc.b = b;
         return irbpp::process_level_image(sc, bm, legacy != 0, emit) ? 0 : 1;
     }
     static uint32_t w[16]; static uint8_t b[64];
     irbpp::StridedScratch<1, 64> sc; sc.w = w; sc.b = b; sc.kept = 0;
+    if (use_big == 0) return irbpp::process_level_image_lockstep(sc, bm, true, legacy != 0, emit) ? 0 : 1;
     return irbpp::process_level_image(sc, bm, legacy != 0, emit) ? 0 : 1;
 }
 
