@@ -300,7 +300,8 @@ def main_gpu(args):
                            "timing": "sum of per-step CUDA-event intervals on the launching stream"
                                      + (" + end-of-rollout all-gather" if world > 1 else "") + ", max over ranks"},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": traffic, "peak_source": peak_src, "kernel": "irbpp_env_kernel",
+                             "traffic": traffic, "peak_source": peak_src,
+                             "kernel": "irbpp_scan_kernel + irbpp_candidates_kernel (one step = both launches)",
                              "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": bytes_step},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": 1e3 * t_e2e / e2e_steps,

@@ -155,7 +155,8 @@ int irbpp_debug_hulls(irbpp_handle h, const double* posZValid, const double* mas
 int64_t irbpp_launch_count(irbpp_handle h);
 
 /* Profiling aid: when enabled, thread 0 of every CTA adds the SM cycles it spent in each kernel phase
- * (0 load+apply, 1 scan, 2 candidate extraction, 3 select/pad, 4 stores) to 8 counters.  The call
+ * (0 scan kernel: load + apply action, 1 scan kernel: observation heightmap + scan + level bitmaps,
+ * 2 candidates kernel: contour tasks, 3 candidates kernel: select / pad) to 8 counters.  The call
  * returns the counters accumulated so far in out8 (may be NULL), clears them and sets the switch. */
 int irbpp_debug_phase_cycles(irbpp_handle h, int32_t enable, uint64_t* out8);
 

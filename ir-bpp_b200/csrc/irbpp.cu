@@ -1,6 +1,7 @@
 // irbpp.cu -- C-ABI (include/irbpp.h) host side: state ownership, table preprocessing, launches.
 //
-// No CPU fallback lives here: every entry point that computes anything launches irbpp_env_kernel.
+// No CPU fallback lives here: every entry point that computes anything launches the CUDA kernels of
+// irbpp_kernels.cuh (irbpp_scan_kernel -> irbpp_candidates_kernel).
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdarg.h>
@@ -21,7 +22,7 @@ static std::string g_create_error;
 struct irbpp_env {
     irbpp_config cfg;
     Params P;                      // device pointers + configuration (mode/inputs filled per launch)
-    SmemLayout SL;
+    int cand_smem = 0;
     std::string err;
     bool shapes_loaded = false, sequences_set = false, was_reset = false, waiting_step = false;
     cudaStream_t pending_stream = nullptr;
@@ -124,7 +125,7 @@ int irbpp_create(const irbpp_config* cfg, irbpp_handle* out) {
     P.binz = cfg->bin_dimension[2];
     P.resZ = cfg->resolution_z;
     P.binvol = (cfg->bin_dimension[0] * cfg->bin_dimension[1]) * cfg->bin_dimension[2];   // np.prod
-    h->SL = smem_layout(P.R, P.sel);
+    h->cand_smem = (int)sizeof(CandSmem);
 
 #define TRY_ALLOC(expr)                                                                          \
     do { cudaError_t e2_ = (expr); if (e2_ != cudaSuccess) {                                      \
@@ -137,6 +138,11 @@ int irbpp_create(const irbpp_config* cfg, irbpp_handle* out) {
     TRY_ALLOC(dev_alloc(h, &P.ep_len, N)); TRY_ALLOC(dev_alloc(h, &P.vol_sum, N));
     TRY_ALLOC(dev_alloc(h, &P.ep_rew, N)); TRY_ALLOC(dev_alloc(h, &P.mask_any, N));
     TRY_ALLOC(dev_alloc(h, &h->actions_dev, N)); TRY_ALLOC(dev_alloc(h, &h->which_dev, N));
+    // scan -> candidates hand-over scratch
+    TRY_ALLOC(dev_alloc(h, &P.posz, (size_t)N * P.R * NPOSE));
+    TRY_ALLOC(dev_alloc(h, &P.maskbits, (size_t)N * P.R * 8));
+    TRY_ALLOC(dev_alloc(h, &P.bitmaps, (size_t)N * P.R * MAX_LEVELS * 8));
+    TRY_ALLOC(dev_alloc(h, &P.nlevels, (size_t)N * P.R));
     // result block (8-byte fields first so every array stays aligned)
     h->results_bytes = (size_t)N * (8 + 8 + 4 + 4 + 4 + 1 + 1 + 1);
     TRY_ALLOC(cudaMalloc(&h->results_dev, h->results_bytes + 64));
@@ -155,7 +161,7 @@ int irbpp_create(const irbpp_config* cfg, irbpp_handle* out) {
         P.r_valid = reinterpret_cast<uint8_t*>(b); b += N;
         P.r_error = reinterpret_cast<uint8_t*>(b);
     }
-    TRY_ALLOC(cudaFuncSetAttribute(irbpp_env_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->SL.total));
+    TRY_ALLOC(cudaFuncSetAttribute(irbpp_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->cand_smem));
 #undef TRY_ALLOC
     *out = h;
     return IRBPP_OK;
@@ -267,12 +273,21 @@ int irbpp_set_sequences(irbpp_handle h, const int32_t* ids, int32_t length) {
     return IRBPP_OK;
 }
 
-static int launch(irbpp_env* h, Params& P, cudaStream_t s, int grid_y = 1) {
-    dim3 grid(P.N, grid_y);
-    irbpp_env_kernel<<<grid, CTA_THREADS, h->SL.total, s>>>(P);
+// one pass of the pipeline: scan kernel (or the levels kernel for caller-supplied maps), then the
+// candidates kernel when the observation carries candidate rows
+static int launch(irbpp_env* h, Params& P, cudaStream_t s) {
+    if (P.mode == MODE_DEBUG_HULLS) irbpp_levels_kernel<<<P.N, CTA_THREADS, 0, s>>>(P);
+    else irbpp_scan_kernel<<<P.N, CTA_THREADS, 0, s>>>(P);
     h->launches += 1;
     cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return fail(h, IRBPP_ECUDA, "kernel launch: %s", cudaGetErrorString(e));
+    if (e != cudaSuccess) return fail(h, IRBPP_ECUDA, "scan kernel launch: %s", cudaGetErrorString(e));
+    if (mode_emits_loc(P.mode, P.K)) {
+        const int grid = (P.N + ENVS_PER_CTA - 1) / ENVS_PER_CTA;
+        irbpp_candidates_kernel<<<grid, CTA_THREADS, h->cand_smem, s>>>(P);
+        h->launches += 1;
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(h, IRBPP_ECUDA, "candidates kernel launch: %s", cudaGetErrorString(e));
+    }
     return IRBPP_OK;
 }
 
@@ -386,7 +401,12 @@ int irbpp_get_all_possible_observation(irbpp_handle h, float* out, void* stream)
     if (!h->was_reset) return fail(h, IRBPP_ESTATE, "called before reset");
     Params P = h->P;
     P.mode = MODE_ALL_OBS; P.obs = out; P.obs_stride = P.K * P.loc_len;
-    return launch(h, P, (cudaStream_t)stream, P.K);
+    for (int slot = 0; slot < P.K; ++slot) {        // one pipeline pass per buffered item (binPhy.py:175-179)
+        P.slot = slot;
+        rc = launch(h, P, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    return IRBPP_OK;
 }
 
 int irbpp_debug_state(irbpp_handle h, double* heightmap, int32_t* queue, int32_t* cursor, int32_t* packed_count) {
@@ -430,22 +450,27 @@ int irbpp_debug_set_heightmap(irbpp_handle h, const double* heightmap) {
 static int debug_run(irbpp_env* h, Params& P, double* posZmap, double* posZValid, double* naiveMask,
                      double* cand, int32_t* num_hull) {
     const size_t N = P.N, nm = N * P.R * NPOSE, nc = N * P.sel * 5;
-    double *d_pz = nullptr, *d_pv = nullptr, *d_mk = nullptr, *d_cd = nullptr; int32_t* d_nh = nullptr; float* d_obs = nullptr;
-    auto cleanup = [&]() { cudaFree(d_pz); cudaFree(d_pv); cudaFree(d_mk); cudaFree(d_cd); cudaFree(d_nh); cudaFree(d_obs); };
+    double* d_cd = nullptr; int32_t* d_nh = nullptr; float* d_obs = nullptr;
+    auto cleanup = [&]() { cudaFree(d_cd); cudaFree(d_nh); cudaFree(d_obs); };
 #define DBG_TRY(expr) do { cudaError_t e_ = (expr); if (e_ != cudaSuccess) { cleanup(); return fail(h, IRBPP_ECUDA, "%s: %s", #expr, cudaGetErrorString(e_)); } } while (0)
-    if (P.mode == MODE_DEBUG_SCAN) {
-        DBG_TRY(cudaMalloc(&d_pz, nm * 8)); DBG_TRY(cudaMalloc(&d_pv, nm * 8)); DBG_TRY(cudaMalloc(&d_mk, nm * 8));
-        P.dbg_posz = d_pz; P.dbg_poszv = d_pv; P.dbg_mask = d_mk;
-    }
     DBG_TRY(cudaMalloc(&d_cd, nc * 8)); DBG_TRY(cudaMalloc(&d_nh, N * 4));
     DBG_TRY(cudaMalloc(&d_obs, N * (size_t)P.loc_len * 4));
     P.dbg_cand = d_cd; P.dbg_nhull = d_nh; P.obs = d_obs; P.obs_stride = P.loc_len;
     int rc = launch(h, P, nullptr);
     if (rc) { cleanup(); return rc; }
     DBG_TRY(cudaDeviceSynchronize());
-    if (posZmap && d_pz) DBG_TRY(cudaMemcpy(posZmap, d_pz, nm * 8, cudaMemcpyDeviceToHost));
-    if (posZValid && d_pv) DBG_TRY(cudaMemcpy(posZValid, d_pv, nm * 8, cudaMemcpyDeviceToHost));
-    if (naiveMask && d_mk) DBG_TRY(cudaMemcpy(naiveMask, d_mk, nm * 8, cudaMemcpyDeviceToHost));
+    if (posZmap || posZValid || naiveMask) {       // float64 views straight from the hand-over scratch
+        std::vector<double> pz(nm);
+        std::vector<uint32_t> mb(N * P.R * 8);
+        DBG_TRY(cudaMemcpy(pz.data(), P.posz, nm * 8, cudaMemcpyDeviceToHost));
+        DBG_TRY(cudaMemcpy(mb.data(), P.maskbits, mb.size() * 4, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < nm; ++i) {
+            const bool m = (mb[i >> 5] >> (i & 31)) & 1u;
+            if (posZmap) posZmap[i] = pz[i];
+            if (posZValid) posZValid[i] = m ? pz[i] : POSZ_INVALID;
+            if (naiveMask) naiveMask[i] = m ? 1.0 : 0.0;
+        }
+    }
     if (cand) DBG_TRY(cudaMemcpy(cand, d_cd, nc * 8, cudaMemcpyDeviceToHost));
     if (num_hull) DBG_TRY(cudaMemcpy(num_hull, d_nh, N * 4, cudaMemcpyDeviceToHost));
     std::vector<uint8_t> errs(N);
@@ -476,16 +501,14 @@ int irbpp_debug_hulls(irbpp_handle h, const double* posZValid, const double* mas
     int rc = ready(h); if (rc) return rc;
     if (!posZValid || !mask) return fail(h, IRBPP_EINVAL, "null argument");
     const size_t nm = (size_t)h->P.N * h->P.R * NPOSE;
-    double *d_pz = nullptr, *d_mk = nullptr;
-    CUDA_TRY(h, cudaMalloc(&d_pz, nm * 8));
-    CUDA_TRY(h, cudaMalloc(&d_mk, nm * 8));
-    CUDA_TRY(h, cudaMemcpy(d_pz, posZValid, nm * 8, cudaMemcpyHostToDevice));
-    CUDA_TRY(h, cudaMemcpy(d_mk, mask, nm * 8, cudaMemcpyHostToDevice));
+    std::vector<uint32_t> mb((size_t)h->P.N * h->P.R * 8, 0u);
+    for (size_t i = 0; i < nm; ++i) if (mask[i] != 0.0) mb[i >> 5] |= 1u << (i & 31);
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    CUDA_TRY(h, cudaMemcpy(h->P.posz, posZValid, nm * 8, cudaMemcpyHostToDevice));
+    CUDA_TRY(h, cudaMemcpy(h->P.maskbits, mb.data(), mb.size() * 4, cudaMemcpyHostToDevice));
     Params P = h->P;
-    P.mode = MODE_DEBUG_HULLS; P.dbg_in_posz = d_pz; P.dbg_in_mask = d_mk;
-    rc = debug_run(h, P, nullptr, nullptr, nullptr, cand, num_hull);
-    cudaFree(d_pz); cudaFree(d_mk);
-    return rc;
+    P.mode = MODE_DEBUG_HULLS;
+    return debug_run(h, P, nullptr, nullptr, nullptr, cand, num_hull);
 }
 
 int64_t irbpp_launch_count(irbpp_handle h) { return h ? h->launches : 0; }

@@ -1,19 +1,30 @@
-// irbpp_kernels.cuh -- the fused packing-environment kernel for sm_100a.
+// irbpp_kernels.cuh -- the packing-environment step as two kernels for sm_100a.
 //
-// One CTA (128 threads) owns one bin for one call.  Phases, all on shared-memory resident state:
-//   A  apply the chosen candidate: decode (binPhy.py:234-236), prejudge (:238-245), drop height of that
-//      pose, placement test (Interface.py:365-369 semantics), heightmap update (space.py:213 closed
-//      form), reward / episode bookkeeping (binPhy.py:299-327, monitor.py:58-75), item queue
-//      (IRcreator.py:6-24), auto-reset on failure (shmem_vec_env.py:140-144)
-//   B  scan every (rotation, X, Y) pose for the next item: drop height + feasibility
-//      (space.py:98-129), one warp per rotation, lanes = poses
-//   C  candidate extraction (cvTools.py:61-103): level quantisation with NumPy floor_divide semantics,
-//      per-level bitmaps by warp ballots, one thread per (rotation, level) image doing border
-//      following + approxPolyDP + convex filter (irbpp_contour.cuh), results OR-ed into a 256-bit set
-//      per rotation (np.unique == sorted set)
-//   D  select / pad (binPhy.py:205-225), observation assembly (binPhy.py:183-232) written as float32
-//      (envs.py:151,163 cast) with coalesced stores; state written back
+//   irbpp_scan_kernel        one CTA (128 threads) per bin
+//     A  apply the chosen candidate: decode (binPhy.py:234-236), prejudge (:238-245), drop height of that
+//        pose, placement test (Interface.py:365-369 semantics), heightmap update (space.py:213 closed
+//        form), reward / episode bookkeeping (binPhy.py:299-327, monitor.py:58-75), item queue
+//        (IRcreator.py:6-24), auto-reset on failure (shmem_vec_env.py:140-144); float32 copy of the
+//        heightmap + next_item_vec into the observation (binPhy.py:196-203); state write-back
+//     B  scan every (rotation, X, Y) pose for the next item: drop height + feasibility
+//        (space.py:98-129), one warp per rotation, lanes = poses; level quantisation with NumPy
+//        floor_divide semantics (cvTools.py:78-79); one 16x16 bitmap per (rotation, level) by warp
+//        ballots -> global scratch (L2 resident)
+//   irbpp_candidates_kernel  one CTA (128 threads) per 4 bins
+//     C  candidate extraction (cvTools.py:61-103): the level images of the 4 bins are dealt densely to
+//        the lanes (one image per lane, warps in lock step contour by contour): border following +
+//        approxPolyDP + convex filter (irbpp_contour.cuh), results OR-ed into a 256-bit set per
+//        (bin, rotation) in shared memory (np.unique == sorted set)
+//     D  select / pad (binPhy.py:205-225): one warp per bin ranks the set bits and writes the
+//        candidate rows of the observation (float32, envs.py:151,163 cast) and the packed candidate
+//        table the next step decodes its action from
 // (paths relative to the reference root)
+//
+// Why two kernels: phase C is one serial task per lane with ~25 tasks per bin; inside a one-bin CTA it
+// ran at ~3 active lanes per instruction and left the other warps waiting at a barrier (profiles/).
+// Splitting lets phase C pack tasks of several bins into full warps and lets phase B run at full
+// occupancy with 8 KB of shared memory.  The hand-over (float64 drop heights, masks, level bitmaps:
+// ~9 KB per bin) is written and re-read within microseconds and stays in the 126 MB L2.
 //
 // Arithmetic is IEEE float64 exactly as NumPy performs it (compile with -fmad=false); masks are
 // folded into the tables as +/-inf sentinels at load time, which changes no comparison result.
@@ -31,32 +42,23 @@ constexpr int STEP = 2;                  // stepSize = resolutionAct / resolutio
 constexpr int NPOSE = AX * AY;           // 256 poses per rotation
 constexpr int CTA_THREADS = 128;
 constexpr int CTA_WARPS = CTA_THREADS / 32;
-#ifndef IRBPP_QUOTA
-#define IRBPP_QUOTA 16
-#endif
-constexpr int QUOTA = IRBPP_QUOTA;       // level images a warp (= rotation) contributes per round
-constexpr int NSLOT = CTA_WARPS * QUOTA; // level-image tasks per round (and per-thread scratch slots)
-#ifndef IRBPP_TRACE_WARPS
-#define IRBPP_TRACE_WARPS 2
-#endif
-constexpr int TRACE_WARPS = IRBPP_TRACE_WARPS;          // warps that run the level-image tasks
-constexpr int TRACE_LANES = NSLOT / TRACE_WARPS;        // task lanes per tracing warp (<= 32)
-constexpr int TRACE_WARPS_DIV = 1;
-static_assert(TRACE_LANES <= 32 && TRACE_LANES * TRACE_WARPS == NSLOT, "task lanes must tile the slots");
-constexpr int SLOT_WORDS = 9;            // 8 bitmap words + 1 pad (bank spread)
+constexpr int ENVS_PER_CTA = 4;          // bins per CTA of the candidates kernel (one warp each in phase D)
+constexpr int MAX_LEVELS = 64;           // level-image slots per (bin, rotation) in the scratch
+constexpr int SLOT_WORDS = 9;            // 8 bitmap words + 1 pad (bank spread) in shared memory
 constexpr int FAST_CAP = 64;             // contour points on the fast path
 constexpr int BIG_CAP = 1024;            // contour points on the overflow path
 constexpr int LEVEL_OFFSET = 32;         // levels in [-32, 31] -> presence bit (level + 32)
 constexpr int MAX_QUEUE = 16;            // buffer_size limit
+constexpr int MAX_ROT = 32;
 constexpr double POSZ_INVALID = 1e3;     // space.py:101,126
 
 enum Mode : int {
     MODE_RESET = 0,        // reset selected envs, emit observation
     MODE_STEP = 1,         // phase A then observation (online: B-D for queue[0]; buffered: order obs)
     MODE_CANDIDATES = 2,   // get_action_candidates(order): B-D for queue[order]
-    MODE_ALL_OBS = 3,      // get_all_possible_observation: blockIdx.y = queue slot
-    MODE_DEBUG_SCAN = 4,   // B-D for a caller-supplied item, dumps float64 views, no state change
-    MODE_DEBUG_HULLS = 5,  // C-D on caller-supplied posZValid / mask
+    MODE_ALL_OBS = 3,      // get_all_possible_observation: one pipeline pass per queue slot
+    MODE_DEBUG_SCAN = 4,   // B-D for a caller-supplied item, no state change
+    MODE_DEBUG_HULLS = 5,  // C-D on caller-supplied posZValid / mask (levels kernel instead of scan)
 };
 
 struct ShapeRot {          // one (shape, rotation) entry, device resident
@@ -91,56 +93,23 @@ struct Params {
     int32_t* cursor; int32_t* cur_item; int32_t* order_act; int32_t* packed; int32_t* ep_len;
     double* vol_sum; double* ep_rew;
     uint8_t* mask_any;
+    // scan -> candidates hand-over (global scratch, L2 resident)
+    double* posz;                        // [N][R][256] drop heights (posZmap)
+    uint32_t* maskbits;                  // [N][R][8]   feasibility bits (naiveMask)
+    uint32_t* bitmaps;                   // [N][R][MAX_LEVELS][8] level images
+    int32_t* nlevels;                    // [N][R]
     // inputs of this call
     const int64_t* actions;              // MODE_STEP / MODE_CANDIDATES
     const uint8_t* which;                // MODE_RESET (NULL = all)
     const int32_t* dbg_items;            // MODE_DEBUG_SCAN
-    const double* dbg_in_posz; const double* dbg_in_mask;   // MODE_DEBUG_HULLS
+    int32_t slot;                        // MODE_ALL_OBS: queue slot of this pass
     // outputs
     float* obs;                          // [N][obs_stride] (+ slot offset in MODE_ALL_OBS)
     float* r_reward; uint8_t* r_done; uint8_t* r_valid; uint8_t* r_error;
     int32_t* r_counter; int32_t* r_eplen; double* r_ratio; double* r_eprew;
-    double* dbg_posz; double* dbg_poszv; double* dbg_mask; double* dbg_cand; int32_t* dbg_nhull;
+    double* dbg_cand; int32_t* dbg_nhull;
     unsigned long long* phase_cycles;    // [8] summed SM cycles per phase (thread 0 of every CTA), or NULL
     int32_t mode;
-};
-
-// ---- shared memory carve-up -----------------------------------------------------------------------
-// Region X is time-multiplexed: heightmap (phases A, B) -> per-thread contour scratch (phase C) ->
-// float32 observation staging (phase D).
-struct SmemLayout {
-    int x_size, posz_off, slots_off, maskbits_off, candbits_off, misc_off, big_off, total;
-};
-
-constexpr int SCRATCH_BYTES = NSLOT * (16 * 4 + FAST_CAP);     // marks + contour points per task thread
-
-__host__ __device__ inline SmemLayout smem_layout(int R, int sel) {
-    SmemLayout L;
-    int x = 2 * HX * (HY / 2) * 8;                                     // heightmap, 8192
-    if (x < SCRATCH_BYTES) x = SCRATCH_BYTES;
-    const int stage_need = sel * 5 * 4 + sel * 2 + 16;
-    if (x < stage_need) x = stage_need;
-    x = (x + 15) & ~15;
-    L.x_size = x;
-    int o = x;
-    L.posz_off = o; o += R * NPOSE * 8;
-    L.slots_off = o; o += NSLOT * SLOT_WORDS * 4;
-    L.maskbits_off = o; o += R * 8 * 4;
-    L.candbits_off = o; o += R * 8 * 4;
-    L.misc_off = o; o += 384;
-    L.big_off = o; o += 16 * 4 + 2 * BIG_CAP;
-    L.total = (o + 15) & ~15;
-    return L;
-}
-
-struct Misc {                    // small CTA-wide scalars in shared memory (<= 384 bytes)
-    int32_t nlev[CTA_WARPS];
-    int32_t ovf_count;
-    int32_t ovf_task[32];
-    int32_t cnt_prefix[33];      // candidate count prefix over rotations (R <= 32)
-    int32_t error;
-    int32_t item;
-    int32_t any_mask;
 };
 
 __device__ __forceinline__ int hm_index(int x, int y) { return ((y & 1) * HX + x) * (HY / 2) + (y >> 1); }
@@ -151,17 +120,60 @@ __device__ __forceinline__ int draw_item(const Params& P, int env, int& cursor) 
     return id;
 }
 
-// ---- phase B: one warp scans one rotation -----------------------------------------------------------
-// Writes posz[r][256] and maskbits[r][8] (space.py:98-129).
-__device__ __forceinline__ void scan_rotation(const Params& P, const double* hm_s, double* posz_s,
-                                              uint32_t* maskbits_s, int item, int r, int lane) {
+__host__ __device__ __forceinline__ bool mode_emits_loc(int mode, int K) {
+    return !((mode == MODE_STEP || mode == MODE_RESET) && K > 1);
+}
+
+// ---- level bitmaps of one rotation -------------------------------------------------------------------
+// lv[pass] = level of pose pass*32+lane (or -1).  One 16x16 bitmap (8 words, two rows each) per level
+// present, by warp ballots, written to the scratch; returns the number of levels.
+__device__ __forceinline__ int emit_level_bitmaps(uint32_t* bm_g, int lane, const int (&lv)[8], uint64_t present) {
+    present &= ~(1ull << (LEVEL_OFFSET - 1));        // level -1 is skipped (cvTools.py:84)
+    int k = 0;
+    while (present) {
+        const int b = __ffsll((long long)present) - 1;
+        present &= present - 1;
+        const int L = b - LEVEL_OFFSET;
+        uint32_t mine = 0;
+#pragma unroll
+        for (int pass = 0; pass < 8; ++pass) {
+            const uint32_t bits = __ballot_sync(0xffffffffu, lv[pass] == L);
+            if (lane == pass) mine = bits;
+        }
+        if (lane < 8) bm_g[k * 8 + lane] = mine;
+        ++k;
+    }
+    return k;
+}
+
+__device__ __forceinline__ int level_of(const Params& P, double posz, double inv, uint32_t& pres_lo,
+                                        uint32_t& pres_hi, int& err) {
+    int L = (int)floor_divide_exact(posz, P.resZ, inv);        // cvTools.py:78
+    if (L < -LEVEL_OFFSET || L >= LEVEL_OFFSET) { err = 1; return -1; }
+    if (L != -1) {
+        const int b = L + LEVEL_OFFSET;
+        if (b < 32) pres_lo |= 1u << b; else pres_hi |= 1u << (b - 32);
+    }
+    return L;
+}
+
+// ---- phase B: one warp scans one rotation -------------------------------------------------------------
+// Writes posz[r][256], maskbits[r][8], the level bitmaps and their count (space.py:98-129,
+// cvTools.py:78-85).  Returns true if any pose is feasible.
+__device__ __forceinline__ bool scan_rotation(const Params& P, const double* hm_s, int env, int item, int r,
+                                              int lane, int& err) {
     const ShapeRot* sr = P.srot + (int64_t)item * P.R + r;
     const int w = sr->w, h = sr->h, nX = sr->nX, nY = sr->nY;
     const double ez = sr->ez;
     const double init = sr->any_zero ? 0.0 : -INFINITY;
     const double* __restrict__ B = P.Bs + sr->off;
     const int hpairs = h >> 1;
-#pragma unroll 1
+    const double inv = 1.0 / P.resZ;
+    double* posz_g = P.posz + ((int64_t)env * P.R + r) * NPOSE;
+    uint32_t* mask_g = P.maskbits + ((int64_t)env * P.R + r) * 8;
+    int lv[8];
+    uint32_t pres_lo = 0, pres_hi = 0, any = 0;
+#pragma unroll
     for (int pass = 0; pass < 8; ++pass) {
         const int p = pass * 32 + lane;
         const int X = p >> 4, Y = p & 15;
@@ -172,9 +184,11 @@ __device__ __forceinline__ void scan_rotation(const Params& P, const double* hm_
             acc = init;
             const double* h0 = hm_s + (STEP * X) * (HY / 2) + Y;        // even heightmap columns
             const double* brow = B;
+#pragma unroll 1
             for (int i = 0; i < w; ++i) {
                 const double* h1 = h0 + HX * (HY / 2);                   // odd heightmap columns
                 int jj = 0;
+#pragma unroll 2
                 for (; jj < hpairs; ++jj) {
                     const double v0 = h0[jj] - __ldg(brow + 2 * jj);
                     const double v1 = h1[jj] - __ldg(brow + 2 * jj + 1);
@@ -190,77 +204,27 @@ __device__ __forceinline__ void scan_rotation(const Params& P, const double* hm_
             }
             feas = round6_le0(acc + ez - P.binz);
         }
-        posz_s[r * NPOSE + p] = acc;
+        posz_g[p] = acc;
         const uint32_t mb = __ballot_sync(0xffffffffu, feas);
-        if (lane == 0) maskbits_s[r * 8 + pass] = mb;
-    }
-}
-
-// level quantisation (cvTools.py:78-79): lv[pass] = posZ // resZ for feasible poses, -1 otherwise;
-// `present` gets bit (level + LEVEL_OFFSET) for every level in this rotation
-__device__ __forceinline__ void levels_from_maps(const Params& P, const double* posz_s, const uint32_t* maskbits_s,
-                                                 int r, int lane, int (&lv)[8], uint64_t& present, int& err) {
-    uint32_t pres_lo = 0, pres_hi = 0;
-    const double inv = 1.0 / P.resZ;
-#pragma unroll
-    for (int pass = 0; pass < 8; ++pass) {
-        const int p = pass * 32 + lane;
-        const bool feas = (maskbits_s[r * 8 + pass] >> lane) & 1u;
-        int L = -1;
-        if (feas) {
-            L = (int)floor_divide_exact(posz_s[r * NPOSE + p], P.resZ, inv);
-            if (L < -LEVEL_OFFSET || L >= LEVEL_OFFSET) { err = 1; L = -1; }
-            if (L != -1) {
-                const int b = L + LEVEL_OFFSET;
-                if (b < 32) pres_lo |= 1u << b; else pres_hi |= 1u << (b - 32);
-            }
-        }
-        lv[pass] = L;
+        if (lane == 0) mask_g[pass] = mb;
+        any |= mb;
+        lv[pass] = feas ? level_of(P, acc, inv, pres_lo, pres_hi, err) : -1;
     }
     pres_lo = __reduce_or_sync(0xffffffffu, pres_lo);
     pres_hi = __reduce_or_sync(0xffffffffu, pres_hi);
-    present = ((uint64_t)pres_hi << 32) | pres_lo;
+    const int nl = emit_level_bitmaps(P.bitmaps + ((int64_t)env * P.R + r) * MAX_LEVELS * 8, lane, lv,
+                                      ((uint64_t)pres_hi << 32) | pres_lo);
+    if (lane == 0) P.nlevels[(int64_t)env * P.R + r] = nl;
+    return any != 0;
 }
 
-// up to QUOTA 16x16 bitmaps (8 words, two rows each) for the next levels in `present`, by warp ballots;
-// consumed levels are removed from `present`
-__device__ __forceinline__ int build_level_bitmaps(uint32_t* slots_s, int warp, int lane, const int (&lv)[8],
-                                                   uint64_t& present) {
-    int k = 0;
-    while (present && k < QUOTA) {
-        const int b = __ffsll((long long)present) - 1;
-        present &= present - 1;
-        const int L = b - LEVEL_OFFSET;
-        uint32_t mine = 0;
-#pragma unroll
-        for (int pass = 0; pass < 8; ++pass) {
-            const uint32_t bits = __ballot_sync(0xffffffffu, lv[pass] == L);
-            if (lane == pass) mine = bits;
-        }
-        if (lane < 8) slots_s[(warp * QUOTA + k) * SLOT_WORDS + lane] = mine;
-        ++k;
-    }
-    return k;
-}
-
-// ---- the kernel -------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(CTA_THREADS, 8) irbpp_env_kernel(const Params P) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+// ---- scan kernel ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(CTA_THREADS, 8) irbpp_scan_kernel(const Params P) {
+    __shared__ __align__(16) double hm_s[HX * HY];
+    __shared__ double z_sh;
+    __shared__ int ok_sh, rot_sh, lx_sh, ly_sh, item_sh, err_sh, any_sh;
     const int env = blockIdx.x;
-    const int slot = blockIdx.y;                 // MODE_ALL_OBS only
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const SmemLayout SL = smem_layout(P.R, P.sel);
-    double* hm_s = reinterpret_cast<double*>(smem_raw);                      // region X, phases A-B
-    unsigned char* scratch_s = smem_raw;                                      // region X, phase C
-    float* stage_f = reinterpret_cast<float*>(smem_raw);                      // region X, phase D
-    uint16_t* stage_c = reinterpret_cast<uint16_t*>(smem_raw + P.sel * 5 * 4);
-    double* posz_s = reinterpret_cast<double*>(smem_raw + SL.posz_off);
-    uint32_t* slots_s = reinterpret_cast<uint32_t*>(smem_raw + SL.slots_off);
-    uint32_t* maskbits_s = reinterpret_cast<uint32_t*>(smem_raw + SL.maskbits_off);
-    uint32_t* candbits_s = reinterpret_cast<uint32_t*>(smem_raw + SL.candbits_off);
-    unsigned char* big_s = smem_raw + SL.big_off;
-    Misc* misc = reinterpret_cast<Misc*>(smem_raw + SL.misc_off);
-
     const int mode = P.mode;
     if (mode == MODE_RESET && P.which && !P.which[env]) return;
     long long t_prev = P.phase_cycles ? clock64() : 0;
@@ -283,16 +247,11 @@ __global__ void __launch_bounds__(CTA_THREADS, 8) irbpp_env_kernel(const Params 
             for (int i = tid; i < HX * HY / 2; i += CTA_THREADS) dst[i] = src[i];
         }
     }
-    if (tid == 0) {
-        misc->error = 0; misc->ovf_count = 0; misc->any_mask = 0;
-        if (mode != MODE_ALL_OBS) P.r_error[env] = 0;
-    }
-    for (int i = tid; i < P.R * 8; i += CTA_THREADS) candbits_s[i] = 0u;
+    if (tid == 0) { err_sh = 0; any_sh = 0; }
     __syncthreads();
 
     int32_t* queue_g = P.queue + (int64_t)env * MAX_QUEUE;
-    bool emit_loc = true;        // location observation (scan + candidates) vs order observation
-    bool write_state = true;
+    bool hm_changed = false;
 
     // ---- phase A: bookkeeping / apply action ----
     if (mode == MODE_RESET) {
@@ -303,20 +262,18 @@ __global__ void __launch_bounds__(CTA_THREADS, 8) irbpp_env_kernel(const Params 
             P.cursor[env] = cursor;
             P.packed[env] = 0; P.ep_len[env] = 0; P.vol_sum[env] = 0.0; P.ep_rew[env] = 0.0;
             P.order_act[env] = 0;
-            misc->item = queue_g[0];
+            item_sh = queue_g[0];
         }
-        emit_loc = (P.K <= 1);
+        hm_changed = true;
         __syncthreads();
     } else if (mode == MODE_STEP) {
         // decode the action (warp 0 computes the drop height of that single pose)
-        __shared__ double z_sh;
-        __shared__ int ok_sh, rot_sh, lx_sh, ly_sh, item_sh;
         if (warp == 0) {
             const int64_t a = P.actions[env];
             const int item = P.cur_item[env];
             int rot = 0, lx = 0, ly = 0;
             bool ok = true;
-            if (a < 0 || a >= P.sel) { ok = false; if (lane == 0) misc->error = 2; }
+            if (a < 0 || a >= P.sel) { ok = false; if (lane == 0) err_sh = 2; }
             else {
                 const uint16_t c = P.cand[(int64_t)env * P.sel + a];
                 rot = c >> 8; lx = (c >> 4) & 15; ly = c & 15;
@@ -349,6 +306,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 8) irbpp_env_kernel(const Params 
         __syncthreads();
         const bool ok = ok_sh != 0;
         const int item = item_sh;
+        __syncthreads();                 // item_sh is rewritten below
         if (ok) {
             // heightmap update: hm[win] = max(hm[win], (T + z) * maskT)   (space.py:213)
             const ShapeRot* sr = P.srot + (int64_t)item * P.R + rot_sh;
@@ -390,53 +348,38 @@ __global__ void __launch_bounds__(CTA_THREADS, 8) irbpp_env_kernel(const Params 
                 for (int q = 0; q < nfill; ++q) queue_g[q] = draw_item(P, env, cursor);   // reset(): clear + preview
             }
             P.cursor[env] = cursor;
-            misc->item = queue_g[0];
+            item_sh = queue_g[0];
         }
-        emit_loc = (P.K <= 1);
+        hm_changed = true;
         __syncthreads();
     } else if (mode == MODE_CANDIDATES) {
         if (tid == 0) {
             int64_t oa = P.actions[env];
-            if (oa < 0 || oa >= P.K) { misc->error = 3; oa = 0; }
+            if (oa < 0 || oa >= P.K) { err_sh = 3; oa = 0; }
             P.order_act[env] = (int)oa;
-            misc->item = queue_g[oa];
+            item_sh = queue_g[oa];
         }
         __syncthreads();
     } else if (mode == MODE_ALL_OBS) {
-        if (tid == 0) misc->item = queue_g[slot];
-        write_state = (slot == P.K - 1);
+        if (tid == 0) item_sh = queue_g[P.slot];
         __syncthreads();
-    } else if (mode == MODE_DEBUG_SCAN) {
-        if (tid == 0) misc->item = P.dbg_items[env];
-        write_state = false;
-        __syncthreads();
-    } else {   // MODE_DEBUG_HULLS
-        write_state = false;
-        for (int i = tid; i < P.R * NPOSE; i += CTA_THREADS) {
-            posz_s[i] = P.dbg_in_posz[(int64_t)env * P.R * NPOSE + i];
-        }
-        for (int wd = tid; wd < P.R * 8; wd += CTA_THREADS) {
-            uint32_t bits = 0;
-            for (int b = 0; b < 32; ++b)
-                if (P.dbg_in_mask[(int64_t)env * P.R * NPOSE + wd * 32 + b] != 0.0) bits |= 1u << b;
-            maskbits_s[wd] = bits;
-        }
-        if (tid == 0) misc->item = 0;
+    } else {   // MODE_DEBUG_SCAN
+        if (tid == 0) item_sh = P.dbg_items[env];
         __syncthreads();
     }
-
     phase_mark(0);   // load + phase A
-    float* obs_g = P.obs + (int64_t)env * P.obs_stride + (mode == MODE_ALL_OBS ? slot * P.loc_len : 0);
-    const int item = misc->item;
+
+    const bool emit_loc = mode_emits_loc(mode, P.K);
+    float* obs_g = P.obs + (int64_t)env * P.obs_stride + (mode == MODE_ALL_OBS ? P.slot * P.loc_len : 0);
+    const int item = item_sh;
     const int ncand = P.sel * 5;
 
-    // the heightmap is final for this call: emit its float32 copy and write the state back now, so
-    // region X can be recycled after the scan
+    // the heightmap is final for this call: float32 copy into the observation, state write-back
     {
         const int hm_obs_off = emit_loc ? ncand + 9 : P.K;
         for (int i = tid; i < HX * HY; i += CTA_THREADS)
             obs_g[hm_obs_off + i] = (float)hm_s[hm_index(i >> 5, i & 31)];
-        if (mode == MODE_STEP || mode == MODE_RESET) {
+        if (hm_changed) {
             double2* dst = reinterpret_cast<double2*>(hm_g);
             const double2* src = reinterpret_cast<const double2*>(hm_s);
             for (int i = tid; i < HX * HY / 2; i += CTA_THREADS) dst[i] = src[i];
@@ -445,213 +388,265 @@ __global__ void __launch_bounds__(CTA_THREADS, 8) irbpp_env_kernel(const Params 
     if (!emit_loc) {
         // order observation: [next k item ids | heightmap]  (binPhy.py:229-230)
         for (int i = tid; i < P.K; i += CTA_THREADS) obs_g[i] = (float)queue_g[i];
-        if (tid == 0 && misc->error) P.r_error[env] = (uint8_t)misc->error;
+        if (tid == 0) P.r_error[env] = (uint8_t)err_sh;
         return;
     }
+    if (tid < 9) obs_g[ncand + tid] = (tid == 0) ? (float)item : 0.0f;      // next_item_vec (binPhy.py:191)
 
-    // ---- phase B: drop height + feasibility of every pose, one warp per rotation ----
-    if (mode != MODE_DEBUG_HULLS) {
-        for (int r = warp; r < P.R; r += CTA_WARPS) scan_rotation(P, hm_s, posz_s, maskbits_s, item, r, lane);
-    }
-    __syncthreads();                       // heightmap dead from here on: region X becomes contour scratch
-    phase_mark(1);   // heightmap write-back + scan
-
-    // ---- phase C: candidate extraction, rotations in groups of CTA_WARPS ----
-    const int ngroups = (P.R + CTA_WARPS - 1) / CTA_WARPS;
-    for (int g = 0; g < ngroups; ++g) {
-        const int r = g * CTA_WARPS + warp;
-        int lv[8];
-        uint64_t present = 0;
-        if (r < P.R) {
-            int err = 0;
-            levels_from_maps(P, posz_s, maskbits_s, r, lane, lv, present, err);
-            if (__any_sync(0xffffffffu, err) && lane == 0) misc->error = 4;
-            present &= ~(1ull << (LEVEL_OFFSET - 1));        // level -1 is skipped (cvTools.py:84)
-        }
-        for (;;) {                                           // rounds of at most QUOTA levels per rotation
-            int nl = 0;
-            if (r < P.R) nl = build_level_bitmaps(slots_s, warp, lane, lv, present);
-            if (lane == 0) misc->nlev[warp] = nl;
-            __syncthreads();
-            int pre[CTA_WARPS + 1];
-            pre[0] = 0;
-#pragma unroll
-            for (int q = 0; q < CTA_WARPS; ++q) pre[q + 1] = pre[q] + misc->nlev[q];
-            const int ntask = pre[CTA_WARPS];
-            if (ntask == 0) break;                           // uniform: every warp sees the same counts
-            // one lane per (rotation, level) image; the first TRACE_WARPS warps take the tasks, all their
-            // lanes enter the lock-step routine together
-            if (warp < TRACE_WARPS) {
-                const int li = lane / TRACE_WARPS_DIV;                 // (unused when TRACE_LANES == 32)
-                (void)li;
-                const int t = lane * TRACE_WARPS + warp;
-                const bool has = (lane < TRACE_LANES) && (t < ntask);
-                int wq = 0;
-#pragma unroll
-                for (int q = 1; q < CTA_WARPS; ++q) if (has && t >= pre[q]) wq = q;
-                const int sl = has ? wq * QUOTA + (t - pre[wq]) : 0;
-                const int sidx = warp * TRACE_LANES + (lane < TRACE_LANES ? lane : 0);
-                StridedScratch<NSLOT, FAST_CAP> sc;
-                sc.w = reinterpret_cast<uint32_t*>(scratch_s) + sidx;
-                sc.b = scratch_s + NSLOT * 16 * 4 + sidx;
-                sc.kept = 0;
-                const uint32_t* bm = slots_s + sl * SLOT_WORDS;
-                uint32_t* cb = candbits_s + (g * CTA_WARPS + wq) * 8;
-                const bool okc = process_level_image_lockstep(
-                    sc, bm, has, P.legacy != 0,
-                    [&](int x, int y) { const int b = x * 16 + y; atomicOr(cb + (b >> 5), 1u << (b & 31)); });
-                if (!okc) {
-                    const int k = atomicAdd(&misc->ovf_count, 1);
-                    if (k < 32) misc->ovf_task[k] = (wq << 16) | sl;
-                }
-            }
-            __syncthreads();
-            if (misc->ovf_count > 0) {          // rare: contours longer than FAST_CAP points, serial path
-                if (tid == 0) {
-                    FlatScratch<BIG_CAP> bs;
-                    bs.w = reinterpret_cast<uint32_t*>(big_s);
-                    bs.b = big_s + 16 * 4;
-                    const int n_ovf = misc->ovf_count;
-                    if (n_ovf > 32) misc->error = 5;
-                    for (int k = 0; k < (n_ovf < 32 ? n_ovf : 32); ++k) {
-                        const int wq = misc->ovf_task[k] >> 16, sl = misc->ovf_task[k] & 0xFFFF;
-                        const uint32_t* bm = slots_s + sl * SLOT_WORDS;
-                        uint32_t* cb = candbits_s + (g * CTA_WARPS + wq) * 8;
-                        const bool okc = process_level_image(
-                            bs, bm, P.legacy != 0,
-                            [&](int x, int y) { const int b = x * 16 + y; cb[b >> 5] |= 1u << (b & 31); });
-                        if (!okc) misc->error = 6;
-                    }
-                    misc->ovf_count = 0;
-                }
-                __syncthreads();
-            }
-        }
-        __syncthreads();     // nobody may still be reading misc->nlev when the next group rewrites it
-    }
-
-    phase_mark(2);   // levels, bitmaps, contour tasks
-    // ---- phase D: select / pad, observation assembly ----
-    if (tid < 32) {
-        int c = 0;
-        if (tid < P.R) { for (int q = 0; q < 8; ++q) c += __popc(candbits_s[tid * 8 + q]); }
-        int incl = c;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-        misc->cnt_prefix[tid + 1] = incl;
-        if (tid == 0) misc->cnt_prefix[0] = 0;
-        uint32_t any = 0;
-        for (int q = tid; q < P.R * 8; q += 32) any |= maskbits_s[q];
-        any = __reduce_or_sync(0xffffffffu, any);
-        if (tid == 0) misc->any_mask = any != 0;
+    // ---- phase B ----
+    {
+        int err = 0;
+        bool any = false;
+        for (int r = warp; r < P.R; r += CTA_WARPS) any |= scan_rotation(P, hm_s, env, item, r, lane, err);
+        if (lane == 0 && any) any_sh = 1;
+        if (__any_sync(0xffffffffu, err) && lane == 0) err_sh = 4;
     }
     __syncthreads();
-    const int Ktot = misc->cnt_prefix[P.R];
-    const int sel = P.sel;
-    double* dbg_cand = P.dbg_cand ? P.dbg_cand + (int64_t)env * sel * 5 : nullptr;
-    auto put_row = [&](int row, int rot, int x, int y, double H, double V) {
-        float* d = stage_f + row * 5;
-        d[0] = (float)rot; d[1] = (float)x; d[2] = (float)y; d[3] = (float)H; d[4] = (float)V;
-        stage_c[row] = (uint16_t)((rot << 8) | (x << 4) | y);
-        if (dbg_cand) {
-            double* q = dbg_cand + row * 5;
-            q[0] = rot; q[1] = x; q[2] = y; q[3] = H; q[4] = V;
+    if (tid == 0) {
+        P.r_error[env] = (uint8_t)err_sh;          // the candidates kernel may overwrite with its own code
+        const bool write_state = (mode == MODE_STEP || mode == MODE_RESET || mode == MODE_CANDIDATES ||
+                                  (mode == MODE_ALL_OBS && P.slot == P.K - 1));
+        if (write_state) { P.cur_item[env] = item; P.mask_any[env] = (uint8_t)any_sh; }
+    }
+    phase_mark(1);   // observation heightmap, write-back, scan, level bitmaps
+}
+
+// ---- levels kernel (MODE_DEBUG_HULLS): level bitmaps from caller-supplied posZValid / mask ------------------
+__global__ void __launch_bounds__(CTA_THREADS) irbpp_levels_kernel(const Params P) {
+    __shared__ int err_sh;
+    const int env = blockIdx.x;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double inv = 1.0 / P.resZ;
+    if (threadIdx.x == 0) err_sh = 0;
+    __syncthreads();
+    int err = 0;
+    for (int r = warp; r < P.R; r += CTA_WARPS) {
+        const double* posz_g = P.posz + ((int64_t)env * P.R + r) * NPOSE;
+        const uint32_t* mask_g = P.maskbits + ((int64_t)env * P.R + r) * 8;
+        int lv[8];
+        uint32_t pres_lo = 0, pres_hi = 0;
+#pragma unroll
+        for (int pass = 0; pass < 8; ++pass) {
+            const bool feas = (mask_g[pass] >> lane) & 1u;
+            lv[pass] = feas ? level_of(P, posz_g[pass * 32 + lane], inv, pres_lo, pres_hi, err) : -1;
+        }
+        pres_lo = __reduce_or_sync(0xffffffffu, pres_lo);
+        pres_hi = __reduce_or_sync(0xffffffffu, pres_hi);
+        const int nl = emit_level_bitmaps(P.bitmaps + ((int64_t)env * P.R + r) * MAX_LEVELS * 8, lane, lv,
+                                          ((uint64_t)pres_hi << 32) | pres_lo);
+        if (lane == 0) P.nlevels[(int64_t)env * P.R + r] = nl;
+    }
+    if (err) err_sh = 4;
+    __syncthreads();
+    if (threadIdx.x == 0) P.r_error[env] = (uint8_t)err_sh;
+}
+
+// ---- candidates kernel ----------------------------------------------------------------------------------
+struct CandSmem {
+    uint32_t slots[CTA_THREADS * SLOT_WORDS];              // level image of every lane's task
+    uint32_t marks[16 * CTA_THREADS];                      // per-lane Suzuki labels, element stride CTA_THREADS
+    uint8_t pts[FAST_CAP * CTA_THREADS];                   // per-lane contour points, element stride CTA_THREADS
+    uint32_t candbits[ENVS_PER_CTA * MAX_ROT * 8];         // 256-bit candidate set per (bin, rotation)
+    int32_t pre[ENVS_PER_CTA * MAX_ROT + 1];               // prefix of level counts over (bin, rotation)
+    int32_t ovf_count;
+    int32_t ovf_task[32];
+    int32_t error[ENVS_PER_CTA];
+    uint32_t big_w[16];
+    uint8_t big_b[2 * BIG_CAP];
+};
+
+__global__ void __launch_bounds__(CTA_THREADS) irbpp_candidates_kernel(const Params P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    CandSmem& S = *reinterpret_cast<CandSmem*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int env0 = blockIdx.x * ENVS_PER_CTA;
+    const int nenv = min(ENVS_PER_CTA, P.N - env0);
+    const int R = P.R;
+    const int npairs = nenv * R;                           // (bin, rotation) pairs of this CTA
+    long long t_prev = P.phase_cycles ? clock64() : 0;
+    auto phase_mark = [&](int idx) {
+        if (P.phase_cycles && tid == 0) {
+            const long long now = clock64();
+            atomicAdd(P.phase_cycles + idx, (unsigned long long)(now - t_prev));
+            t_prev = now;
         }
     };
-    auto zero_row = [&](int row) {
-        float* d = stage_f + row * 5;
-        d[0] = d[1] = d[2] = d[3] = d[4] = 0.0f;
-        stage_c[row] = 0;
-        if (dbg_cand) { double* q = dbg_cand + row * 5; q[0] = q[1] = q[2] = q[3] = q[4] = 0.0; }
+
+    for (int i = tid; i < ENVS_PER_CTA * MAX_ROT * 8; i += CTA_THREADS) S.candbits[i] = 0u;
+    if (tid < ENVS_PER_CTA) S.error[tid] = 0;
+    if (tid == 0) {
+        S.ovf_count = 0;
+        int acc = 0;
+        S.pre[0] = 0;
+        for (int q = 0; q < npairs; ++q) {
+            const int e = env0 + q / R;
+            const bool live = !(P.mode == MODE_RESET && P.which && !P.which[e]);
+            acc += live ? P.nlevels[(int64_t)env0 * R + q] : 0;
+            S.pre[q + 1] = acc;
+        }
+    }
+    __syncthreads();
+    const int ntask = S.pre[npairs];
+
+    // ---- phase C: one level image per lane, dense over the bins of this CTA ----
+    for (int base = 0; base < ntask; base += CTA_THREADS) {
+        const int t = base + tid;
+        const bool has = t < ntask;
+        int q = 0;
+        if (has) {                                          // (bin, rotation) pair owning task t
+            int lo = 0, hi = npairs;                        // pre[lo] <= t < pre[hi]
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (S.pre[mid] <= t) lo = mid; else hi = mid; }
+            q = lo;
+        }
+        uint32_t* bm = S.slots + tid * SLOT_WORDS;
+        if (has) {
+            const uint4* src = reinterpret_cast<const uint4*>(
+                P.bitmaps + (((int64_t)env0 * R + q) * MAX_LEVELS + (t - S.pre[q])) * 8);
+            const uint4 a = src[0], b = src[1];
+            bm[0] = a.x; bm[1] = a.y; bm[2] = a.z; bm[3] = a.w; bm[4] = b.x; bm[5] = b.y; bm[6] = b.z; bm[7] = b.w;
+        }
+        StridedScratch<CTA_THREADS, FAST_CAP> sc;
+        sc.w = S.marks + tid;
+        sc.b = S.pts + tid;
+        sc.kept = 0;
+        uint32_t* cb = S.candbits + q * 8;
+        const bool okc = process_level_image_lockstep(
+            sc, bm, has, P.legacy != 0,
+            [&](int x, int y) { const int b = x * 16 + y; atomicOr(cb + (b >> 5), 1u << (b & 31)); });
+        if (!okc) {
+            const int k = atomicAdd(&S.ovf_count, 1);
+            if (k < 32) S.ovf_task[k] = (q << 16) | tid;
+        }
+        __syncthreads();
+        if (S.ovf_count > 0) {          // rare: contours longer than FAST_CAP points, serial path
+            if (tid == 0) {
+                FlatScratch<BIG_CAP> bs;
+                bs.w = S.big_w;
+                bs.b = S.big_b;
+                const int n_ovf = S.ovf_count;
+                if (n_ovf > 32) S.error[0] = 5;
+                for (int k = 0; k < (n_ovf < 32 ? n_ovf : 32); ++k) {
+                    const int qq = S.ovf_task[k] >> 16, lt = S.ovf_task[k] & 0xFFFF;
+                    uint32_t* cb2 = S.candbits + qq * 8;
+                    const bool ok2 = process_level_image(
+                        bs, S.slots + lt * SLOT_WORDS, P.legacy != 0,
+                        [&](int x, int y) { const int b = x * 16 + y; cb2[b >> 5] |= 1u << (b & 31); });
+                    if (!ok2) S.error[qq / R] = 6;
+                }
+                S.ovf_count = 0;
+            }
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    phase_mark(2);   // contour tasks
+
+    // ---- phase D: one warp per bin ----
+    if (warp >= nenv) return;
+    const int env = env0 + warp;
+    if (P.mode == MODE_RESET && P.which && !P.which[env]) return;
+    const int sel = P.sel;
+    const uint32_t* cbits = S.candbits + warp * R * 8;
+    const uint32_t* mask_g = P.maskbits + (int64_t)env * R * 8;
+    const double* posz_g = P.posz + (int64_t)env * R * NPOSE;
+    float* obs_g = P.obs + (int64_t)env * P.obs_stride + (P.mode == MODE_ALL_OBS ? P.slot * P.loc_len : 0);
+    const bool write_state = (P.mode == MODE_STEP || P.mode == MODE_RESET || P.mode == MODE_CANDIDATES ||
+                              (P.mode == MODE_ALL_OBS && P.slot == P.K - 1));
+    uint16_t* cand_g = write_state ? P.cand + (int64_t)env * sel : nullptr;
+    double* dbg_cand = P.dbg_cand ? P.dbg_cand + (int64_t)env * sel * 5 : nullptr;
+
+    // candidate counts per rotation (lane r), exclusive prefix, total
+    int cnt = 0;
+    if (lane < R) { for (int qd = 0; qd < 8; ++qd) cnt += __popc(cbits[lane * 8 + qd]); }
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int tt = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += tt; }
+    const int excl = incl - cnt;
+    const int Ktot = __shfl_sync(0xffffffffu, incl, 31);
+    uint32_t anym = 0;
+    for (int qd = lane; qd < R * 8; qd += 32) anym |= mask_g[qd];
+    anym = __reduce_or_sync(0xffffffffu, anym);
+
+    auto put_row = [&](int row, int rot, int x, int y, double H, double V) {
+        float* d = obs_g + row * 5;
+        d[0] = (float)rot; d[1] = (float)x; d[2] = (float)y; d[3] = (float)H; d[4] = (float)V;
+        if (cand_g) cand_g[row] = (uint16_t)((rot << 8) | (x << 4) | y);
+        if (dbg_cand) { double* qd = dbg_cand + row * 5; qd[0] = rot; qd[1] = x; qd[2] = y; qd[3] = H; qd[4] = V; }
     };
-    // (the staging area is region X: heightmap and contour scratch are dead from here on)
+    auto zero_rows = [&](int first) {
+        for (int i = first * 5 + lane; i < sel * 5; i += 32) obs_g[i] = 0.0f;
+        if (cand_g) for (int i = first + lane; i < sel; i += 32) cand_g[i] = 0;
+        if (dbg_cand) for (int i = first * 5 + lane; i < sel * 5; i += 32) dbg_cand[i] = 0.0;
+    };
+    auto height_of = [&](int cell, bool& m) -> double {     // posZValid at a flat pose index
+        m = (mask_g[cell >> 5] >> (cell & 31)) & 1u;
+        return m ? posz_g[cell] : POSZ_INVALID;
+    };
+
     if (Ktot == 0) {
         // no hull candidate at all (binPhy.py:217-225): the `sel` smallest posZValid, stable order
-        const int total = P.R * NPOSE;
-        if (!misc->any_mask) {
-            for (int i = tid; i < sel; i += CTA_THREADS) {
-                if (i < total) put_row(i, i >> 8, (i >> 4) & 15, i & 15, P.binz, 0.0);
-                else zero_row(i);   // reference would produce a short table; R*256 >= sel is enforced at create
-            }
+        const int total = R * NPOSE;
+        if (!anym) {
+            const int nrow = total < sel ? total : sel;
+            for (int i = lane; i < nrow; i += 32) put_row(i, i >> 8, (i >> 4) & 15, i & 15, P.binz, 0.0);
+            zero_rows(nrow);
         } else {
-            for (int i = tid; i < total; i += CTA_THREADS) {
-                const bool mi = (maskbits_s[i >> 5] >> (i & 31)) & 1u;
-                const double vi = mi ? posz_s[i] : POSZ_INVALID;
+            for (int i = lane; i < total; i += 32) {
+                bool mi; const double vi = height_of(i, mi);
                 int rank = 0;
                 for (int j = 0; j < total; ++j) {
-                    const bool mj = (maskbits_s[j >> 5] >> (j & 31)) & 1u;
-                    const double vj = mj ? posz_s[j] : POSZ_INVALID;
+                    bool mj; const double vj = height_of(j, mj);
                     rank += (vj < vi) || (vj == vi && j < i);
                 }
                 if (rank < sel) put_row(rank, i >> 8, (i >> 4) & 15, i & 15, P.binz, mi ? 1.0 : 0.0);
             }
-            for (int i = total + tid; i < sel; i += CTA_THREADS) zero_row(i);
+            zero_rows(total < sel ? total : sel);
         }
     } else {
         // rows in rotation order, then (col, row) ascending == bit order of the per-rotation sets
-        for (int idx = tid; idx < P.R * NPOSE; idx += CTA_THREADS) {
-            const int r = idx >> 8, b = idx & 255;
-            const uint32_t* cb = candbits_s + r * 8;
-            if (!((cb[b >> 5] >> (b & 31)) & 1u)) continue;
-            int ord = misc->cnt_prefix[r];
-            for (int q = 0; q < (b >> 5); ++q) ord += __popc(cb[q]);
-            ord += __popc(cb[b >> 5] & ((1u << (b & 31)) - 1u));
-            const int col = b >> 4, row = b & 15;
-            const int cell = r * NPOSE + row * 16 + col;
-            const bool m = (maskbits_s[cell >> 5] >> (cell & 31)) & 1u;
-            const double H = m ? posz_s[cell] : POSZ_INVALID;
-            int dest = ord;
-            if (Ktot > sel) {
-                // truncate to the `sel` lowest heights, ties by original order (stable argsort; binPhy.py:209-212)
-                int rank = 0;
-                for (int r2 = 0; r2 < P.R; ++r2) {
-                    const uint32_t* cb2 = candbits_s + r2 * 8;
-                    int ord2 = misc->cnt_prefix[r2];
-                    for (int q = 0; q < 8; ++q) {
-                        uint32_t wbits = cb2[q];
-                        while (wbits) {
-                            const int bb = q * 32 + __ffs((int)wbits) - 1;
-                            wbits &= wbits - 1;
-                            const int cell2 = r2 * NPOSE + (bb & 15) * 16 + (bb >> 4);
-                            const bool m2 = (maskbits_s[cell2 >> 5] >> (cell2 & 31)) & 1u;
-                            const double H2 = m2 ? posz_s[cell2] : POSZ_INVALID;
-                            rank += (H2 < H) || (H2 == H && ord2 < ord);
-                            ++ord2;
+        for (int r = 0; r < R; ++r) {
+            const uint32_t* cb = cbits + r * 8;
+            int ord0 = __shfl_sync(0xffffffffu, excl, r);
+#pragma unroll 1
+            for (int qd = 0; qd < 8; ++qd) {
+                const uint32_t wbits = cb[qd];
+                if ((wbits >> lane) & 1u) {
+                    const int ord = ord0 + __popc(wbits & ((1u << lane) - 1u));
+                    const int b = qd * 32 + lane;
+                    const int col = b >> 4, row = b & 15;
+                    bool m; const double H = height_of(r * NPOSE + row * 16 + col, m);
+                    int dest = ord;
+                    if (Ktot > sel) {
+                        // truncate to the `sel` lowest heights, ties by original order (stable argsort;
+                        // binPhy.py:209-212)
+                        int rank = 0, ord2 = 0;
+                        for (int r2 = 0; r2 < R; ++r2) {
+                            const uint32_t* cb2 = cbits + r2 * 8;
+                            for (int q2 = 0; q2 < 8; ++q2) {
+                                uint32_t w2 = cb2[q2];
+                                while (w2) {
+                                    const int bb = q2 * 32 + __ffs((int)w2) - 1;
+                                    w2 &= w2 - 1;
+                                    bool m2; const double H2 = height_of(r2 * NPOSE + (bb & 15) * 16 + (bb >> 4), m2);
+                                    rank += (H2 < H) || (H2 == H && ord2 < ord);
+                                    ++ord2;
+                                }
+                            }
                         }
+                        dest = rank;
                     }
+                    if (dest < sel) put_row(dest, r, row, col, H, m ? 1.0 : 0.0);
                 }
-                dest = rank;
+                ord0 += __popc(wbits);
             }
-            if (dest < sel) put_row(dest, r, row, col, H, m ? 1.0 : 0.0);
         }
-        for (int i = Ktot + tid; i < sel; i += CTA_THREADS) zero_row(i);
+        if (Ktot < sel) zero_rows(Ktot);
     }
-    __syncthreads();
-
-    phase_mark(3);   // select / pad into the staging area
-    // observation: [candidates sel*5 | next_item_vec 9 | heightmap]  (binPhy.py:196-227)
-    for (int i = tid; i < ncand; i += CTA_THREADS) obs_g[i] = stage_f[i];
-    if (tid < 9) obs_g[ncand + tid] = (tid == 0) ? (float)item : 0.0f;
-
-    if (write_state) {
-        uint16_t* cg = P.cand + (int64_t)env * sel;
-        for (int i = tid; i < sel; i += CTA_THREADS) cg[i] = stage_c[i];
-        if (tid == 0) { P.cur_item[env] = item; P.mask_any[env] = (uint8_t)misc->any_mask; }
+    if (lane == 0) {
+        if (S.error[warp]) P.r_error[env] = (uint8_t)S.error[warp];
+        if (P.dbg_nhull) P.dbg_nhull[env] = Ktot;
     }
-    if (tid == 0 && misc->error) P.r_error[env] = (uint8_t)misc->error;
-
-    // float64 parity views
-    if (P.dbg_posz) {
-        const int64_t base = (int64_t)env * P.R * NPOSE;
-        for (int i = tid; i < P.R * NPOSE; i += CTA_THREADS) {
-            const bool m = (maskbits_s[i >> 5] >> (i & 31)) & 1u;
-            P.dbg_posz[base + i] = posz_s[i];
-            P.dbg_poszv[base + i] = m ? posz_s[i] : POSZ_INVALID;
-            P.dbg_mask[base + i] = m ? 1.0 : 0.0;
-        }
-    }
-    if (P.dbg_nhull && tid == 0) P.dbg_nhull[env] = Ktot;
-    phase_mark(4);   // observation / state stores
+    phase_mark(3);   // select / pad, candidate rows of the observation
 }
 
 }  // namespace irbpp

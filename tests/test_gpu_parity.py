@@ -286,5 +286,5 @@ def test_full_size_properties():
         prev_hm = hm
         total_done += int(da.sum())
     assert total_done > 0
-    assert a.launch_count() == 31
+    assert a.launch_count() == 62          # scan + candidates kernel per reset / step
     a.close(); b.close()
