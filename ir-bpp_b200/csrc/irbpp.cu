@@ -17,12 +17,16 @@
 
 using namespace irbpp;
 
+#ifndef IRBPP_DEFAULT_CHUNKS
+#define IRBPP_DEFAULT_CHUNKS 1
+#endif
+
 static std::string g_create_error;
 
 struct irbpp_env {
     irbpp_config cfg;
     Params P;                      // device pointers + configuration (mode/inputs filled per launch)
-    int cand_smem = 0;
+    int cand_smem = 0, scan_smem = 0;
     std::string err;
     bool shapes_loaded = false, sequences_set = false, was_reset = false, waiting_step = false;
     cudaStream_t pending_stream = nullptr;
@@ -39,6 +43,10 @@ struct irbpp_env {
     ShapeRot* srot_dev = nullptr; double* Bs_dev = nullptr; double* Ts_dev = nullptr;
     double* vol_dev = nullptr; double* rew_dev = nullptr; int32_t* seq_dev = nullptr;
     unsigned long long* phase_dev = nullptr;
+    // chunked pipeline
+    int nchunks = 1;
+    cudaStream_t chunk_stream[8] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[8] = {};
 };
 
 static int fail(irbpp_env* h, int code, const char* fmt, ...) {
@@ -125,7 +133,7 @@ int irbpp_create(const irbpp_config* cfg, irbpp_handle* out) {
     P.binz = cfg->bin_dimension[2];
     P.resZ = cfg->resolution_z;
     P.binvol = (cfg->bin_dimension[0] * cfg->bin_dimension[1]) * cfg->bin_dimension[2];   // np.prod
-    h->cand_smem = (int)sizeof(CandSmem);
+    h->cand_smem = (int)sizeof(WarpSmem) * ENVS_PER_CTA;
 
 #define TRY_ALLOC(expr)                                                                          \
     do { cudaError_t e2_ = (expr); if (e2_ != cudaSuccess) {                                      \
@@ -162,6 +170,17 @@ int irbpp_create(const irbpp_config* cfg, irbpp_handle* out) {
         P.r_error = reinterpret_cast<uint8_t*>(b);
     }
     TRY_ALLOC(cudaFuncSetAttribute(irbpp_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->cand_smem));
+    {
+        const char* envc = getenv("IRBPP_CHUNKS");
+        int nc = envc ? atoi(envc) : IRBPP_DEFAULT_CHUNKS;
+        if (nc < 1) nc = 1; if (nc > 8) nc = 8;
+        h->nchunks = nc;
+        TRY_ALLOC(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        for (int c = 0; c < nc; ++c) {
+            TRY_ALLOC(cudaStreamCreateWithFlags(&h->chunk_stream[c], cudaStreamNonBlocking));
+            TRY_ALLOC(cudaEventCreateWithFlags(&h->ev_join[c], cudaEventDisableTiming));
+        }
+    }
 #undef TRY_ALLOC
     *out = h;
     return IRBPP_OK;
@@ -172,6 +191,8 @@ int irbpp_destroy(irbpp_handle h) {
     cudaSetDevice(h->cfg.device);
     cudaDeviceSynchronize();
     for (void* p : h->dev_allocs) cudaFree(p);
+    for (int c = 0; c < 8; ++c) { if (h->chunk_stream[c]) cudaStreamDestroy(h->chunk_stream[c]); if (h->ev_join[c]) cudaEventDestroy(h->ev_join[c]); }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->results_dev) cudaFree(h->results_dev);
     if (h->results_host) cudaFreeHost(h->results_host);
     if (h->actions_pinned) cudaFreeHost(h->actions_pinned);
@@ -196,6 +217,7 @@ int irbpp_load_shapes(irbpp_handle h, int32_t S, int32_t R, const int32_t* dims,
     std::vector<ShapeRot> srot((size_t)S * R);
     std::vector<double> Bs, Ts;
     std::vector<double> rew(S);
+    int maxwh = 1;
     for (int s = 0; s < S; ++s) {
         rew[s] = (vol[s] / h->P.binvol) * 10;                        // binPhy.py:155-156,321-322
         for (int r = 0; r < R; ++r) {
@@ -210,6 +232,7 @@ int irbpp_load_shapes(irbpp_handle h, int32_t S, int32_t R, const int32_t* dims,
                             "(the reference fails on this table)", s, r, w, hh, wA, hA);
             const int64_t off = offsets[(size_t)s * R + r];
             const int64_t n = (int64_t)w * hh;
+            if ((int)n > maxwh) maxwh = (int)n;
             if (off < 0 || off + 4 * n > maps_len) return fail(h, IRBPP_EINVAL, "shape %d rot %d: table out of range", s, r);
             ShapeRot& q = srot[(size_t)s * R + r];
             q.w = w; q.h = hh;
@@ -254,6 +277,9 @@ int irbpp_load_shapes(irbpp_handle h, int32_t S, int32_t R, const int32_t* dims,
     CUDA_TRY(h, cudaMemcpy(h->rew_dev, rew.data(), (size_t)S * 8, cudaMemcpyHostToDevice));
     h->P.S = S; h->P.srot = h->srot_dev; h->P.Bs = h->Bs_dev; h->P.Ts = h->Ts_dev;
     h->P.vol = h->vol_dev; h->P.reward_tab = h->rew_dev;
+    h->P.maxwh = (maxwh + 1) & ~1;
+    h->scan_smem = CTA_WARPS * h->P.maxwh * (int)sizeof(double);
+    CUDA_TRY(h, cudaFuncSetAttribute(irbpp_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->scan_smem));
     h->shapes_loaded = true;
     return IRBPP_OK;
 }
@@ -273,21 +299,39 @@ int irbpp_set_sequences(irbpp_handle h, const int32_t* ids, int32_t length) {
     return IRBPP_OK;
 }
 
-// one pass of the pipeline: scan kernel (or the levels kernel for caller-supplied maps), then the
-// candidates kernel when the observation carries candidate rows
+// One pass of the pipeline: scan kernel (or the levels kernel for caller-supplied maps), then the
+// candidates kernel when the observation carries candidate rows.  The bins are cut into `nchunks`
+// ranges that run on internal streams: the scan kernel is issue-bound and the candidates kernel is a
+// latency-bound serial chain per lane, so letting chunk i's candidates kernel share the SMs with chunk
+// i+1's scan kernel fills issue slots that either kernel alone leaves idle.  The caller's stream
+// order is preserved with events (fork after everything already enqueued on `s`, join before return).
 static int launch(irbpp_env* h, Params& P, cudaStream_t s) {
-    if (P.mode == MODE_DEBUG_HULLS) irbpp_levels_kernel<<<P.N, CTA_THREADS, 0, s>>>(P);
-    else irbpp_scan_kernel<<<P.N, CTA_THREADS, 0, s>>>(P);
-    h->launches += 1;
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) return fail(h, IRBPP_ECUDA, "scan kernel launch: %s", cudaGetErrorString(e));
-    if (mode_emits_loc(P.mode, P.K)) {
-        const int grid = (P.N + ENVS_PER_CTA - 1) / ENVS_PER_CTA;
-        irbpp_candidates_kernel<<<grid, CTA_THREADS, h->cand_smem, s>>>(P);
-        h->launches += 1;
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return fail(h, IRBPP_ECUDA, "candidates kernel launch: %s", cudaGetErrorString(e));
+    const int nch = (h->nchunks > 1 && P.N >= 64 * h->nchunks) ? h->nchunks : 1;
+    const bool cand = mode_emits_loc(P.mode, P.K);
+    if (nch > 1) {
+        cudaError_t e = cudaEventRecord(h->ev_fork, s);
+        if (e != cudaSuccess) return fail(h, IRBPP_ECUDA, "event record: %s", cudaGetErrorString(e));
     }
+    for (int c = 0; c < nch; ++c) {
+        cudaStream_t cs = (nch > 1) ? h->chunk_stream[c] : s;
+        if (nch > 1) cudaStreamWaitEvent(cs, h->ev_fork, 0);
+        P.env_lo = (int)((int64_t)P.N * c / nch);
+        P.env_hi = (int)((int64_t)P.N * (c + 1) / nch);
+        const int n = P.env_hi - P.env_lo;
+        if (P.mode == MODE_DEBUG_HULLS) irbpp_levels_kernel<<<n, CTA_THREADS, 0, cs>>>(P);
+        else irbpp_scan_kernel<<<n, CTA_THREADS, h->scan_smem, cs>>>(P);
+        h->launches += 1;
+        if (cand) {
+            irbpp_candidates_kernel<<<(n + ENVS_PER_CTA - 1) / ENVS_PER_CTA, CAND_THREADS, h->cand_smem, cs>>>(P);
+            h->launches += 1;
+        }
+        if (nch > 1) {
+            cudaEventRecord(h->ev_join[c], cs);
+            cudaStreamWaitEvent(s, h->ev_join[c], 0);
+        }
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(h, IRBPP_ECUDA, "kernel launch: %s", cudaGetErrorString(e));
     return IRBPP_OK;
 }
 

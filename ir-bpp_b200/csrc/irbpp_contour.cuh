@@ -86,15 +86,26 @@ struct FlatScratch {
 };
 
 // ---- border following (Suzuki-Abe, CHAIN_APPROX_SIMPLE) -----------------------------------------
-// (x0, y0) unpadded.  Marks every visited border pixel; stores the emitted points as (x<<4 | y).
-// Returns the number of points, or -1 if it exceeded S::CAP (marks are still complete in that case).
+// (x0, y0) unpadded.  Marks every visited border pixel; when `store` is set the emitted points are kept
+// as (x<<4 | y).  Returns the number of points, or -1 if it exceeded S::CAP (marks are still complete in
+// that case).  The three image rows around the current pixel are cached in registers (padded by one
+// zero column) and reloaded only on vertical moves.
+__device__ __forceinline__ uint32_t ring_from_rows(uint32_t rm, uint32_t r0, uint32_t rp, int x) {
+    const uint32_t wm = (rm >> x) & 7u;   // bit0 = col x-1, bit1 = col x, bit2 = col x+1
+    const uint32_t w0 = (r0 >> x) & 7u;
+    const uint32_t wp = (rp >> x) & 7u;
+    const uint32_t rev = ((wm & 1u) << 2) | (wm & 2u) | (wm >> 2);   // NE, N, NW in direction order
+    return (w0 >> 2) | (rev << 1) | ((w0 & 1u) << 4) | (wp << 5);
+}
+
 template <class S>
-__device__ int follow_border(S& sc, const uint32_t* bm, int x0, int y0, bool hole) {
+__device__ int follow_border(S& sc, const uint32_t* bm, int x0, int y0, bool hole, bool store) {
     const int s_start = hole ? 0 : 4;
-    uint32_t ring = neighbour_ring(bm, x0, y0);
+    uint32_t rm = row16(bm, y0 - 1) << 1, r0 = row16(bm, y0) << 1, rp = row16(bm, y0 + 1) << 1;
+    uint32_t ring = ring_from_rows(rm, r0, rp, x0);
     if (!ring) {  // isolated pixel
         sc.set_mk(y0, sc.mk(y0) | (0x10000u << x0));
-        sc.set_pt(0, (x0 << 4) | y0);
+        if (store) sc.set_pt(0, (x0 << 4) | y0);
         return 1;
     }
     // clockwise search from s_start-1 down to s_start: highest set bit of the ring rotated by s_start
@@ -114,12 +125,62 @@ __device__ int follow_border(S& sc, const uint32_t* bm, int x0, int y0, bool hol
         // counter-clockwise search starting at s_end+1: lowest set bit of the ring rotated by s_end+1
         const uint32_t rot = ((ring | (ring << 8)) >> ((s_end + 1) & 7)) & 0xFFu;
         s = (s_end + __ffs((int)rot)) & 7;        // (s_end + 1 + (ffs-1)) & 7
-        const int x4 = x3 + ddx(s), y4 = y3 + ddy(s);
+        const int dy = ddy(s);
+        const int x4 = x3 + ddx(s), y4 = y3 + dy;
         {
             const uint32_t m = sc.mk(y3);
             if ((unsigned)(s - 1) < (unsigned)s_end) sc.set_mk(y3, m | (0x10000u << x3));
             else if (!((m | (m >> 16)) & (1u << x3))) sc.set_mk(y3, m | (1u << x3));
         }
+        if (s != prev_s) {
+            if (store) {
+                if (n < S::CAP) sc.set_pt(n, (x3 << 4) | y3);
+                else ovf = true;
+            }
+            ++n;
+        }
+        prev_s = s;
+        if (x4 == x0 && y4 == y0 && x3 == x1 && y3 == y1) break;
+        if (dy > 0) { rm = r0; r0 = rp; rp = row16(bm, y4 + 1) << 1; }
+        else if (dy < 0) { rp = r0; r0 = rm; rm = row16(bm, y4 - 1) << 1; }
+        x3 = x4; y3 = y4;
+        s = (s + 4) & 7;
+        ring = ring_from_rows(rm, r0, rp, x3);
+    }
+    return ovf ? -1 : n;
+}
+
+// Outer-rule border follower used by the component-first formulation below: starts at (x0, y0) whose
+// W, NW, N, NE neighbours are background, follows the border with the outer start rule, sets the
+// "visited" bit of every pixel it passes, stores the CHAIN_APPROX_SIMPLE points and accumulates twice
+// the signed area of the closed path (<= 0: the path is an outer border; > 0: it ran around a hole).
+template <class S>
+__device__ int follow_outer(S& sc, const uint32_t* bm, int x0, int y0, int& area2) {
+    uint32_t rm = row16(bm, y0 - 1) << 1, r0 = row16(bm, y0) << 1, rp = row16(bm, y0 + 1) << 1;
+    uint32_t ring = ring_from_rows(rm, r0, rp, x0);
+    area2 = 0;
+    sc.set_mk(y0, sc.mk(y0) | (1u << x0));
+    if (!ring) {  // isolated pixel
+        sc.set_pt(0, (x0 << 4) | y0);
+        return 1;
+    }
+    int s;
+    {   // clockwise search from direction 3 down to 4: highest set bit of the ring rotated by 4
+        const uint32_t r2 = ((ring | (ring << 8)) >> 4) & 0xFFu;
+        s = (4 + (31 - __clz((int)r2))) & 7;
+    }
+    const int x1 = x0 + ddx(s), y1 = y0 + ddy(s);
+    int x3 = x0, y3 = y0;
+    int prev_s = s ^ 4;
+    int n = 0, a2 = 0;
+    bool ovf = false;
+    for (;;) {
+        const int s_end = s;
+        const uint32_t rot = ((ring | (ring << 8)) >> ((s_end + 1) & 7)) & 0xFFu;
+        s = (s_end + __ffs((int)rot)) & 7;
+        const int dy = ddy(s);
+        const int x4 = x3 + ddx(s), y4 = y3 + dy;
+        a2 += x3 * y4 - x4 * y3;
         if (s != prev_s) {
             if (n < S::CAP) sc.set_pt(n, (x3 << 4) | y3);
             else ovf = true;
@@ -127,10 +188,14 @@ __device__ int follow_border(S& sc, const uint32_t* bm, int x0, int y0, bool hol
         }
         prev_s = s;
         if (x4 == x0 && y4 == y0 && x3 == x1 && y3 == y1) break;
+        if (dy > 0) { rm = r0; r0 = rp; rp = row16(bm, y4 + 1) << 1; }
+        else if (dy < 0) { rp = r0; r0 = rm; rm = row16(bm, y4 - 1) << 1; }
         x3 = x4; y3 = y4;
+        sc.set_mk(y3, sc.mk(y3) | (1u << x3));
         s = (s + 4) & 7;
-        ring = neighbour_ring(bm, x3, y3);
+        ring = ring_from_rows(rm, r0, rp, x3);
     }
+    area2 = a2;
     return ovf ? -1 : n;
 }
 
@@ -140,6 +205,19 @@ template <class S, class Emit>
 __device__ void approx_and_emit(S& sc, int n, bool legacy, Emit emit) {
     auto PX = [&](int i) { return sc.pt(i) >> 4; };
     auto PY = [&](int i) { return sc.pt(i) & 15; };
+    if (n == 4) {
+        // Filled axis-aligned rectangle with both sides >= 2 (the common level-set component): the
+        // border is (x0,y0),(x0,y1),(x1,y1),(x1,y0).  Every corner is at squared distance
+        // a^2 b^2 / (a^2 + b^2) >= 2 > eps^2 from the diagonal, the clean-up test 2 a^2 b^2 <= a^2 + b^2
+        // fails, and all four turns have the same sign, so approxPolyDP + find_convex_vetex return
+        // exactly the four corners.
+        const int p0 = sc.pt(0), p1 = sc.pt(1), p2 = sc.pt(2), p3 = sc.pt(3);
+        if ((p0 >> 4) == (p1 >> 4) && (p1 & 15) == (p2 & 15) && (p2 >> 4) == (p3 >> 4) && (p3 & 15) == (p0 & 15) &&
+            (p1 & 15) - (p0 & 15) >= 2 && (p2 >> 4) - (p1 >> 4) >= 2) {
+            emit(p0 >> 4, p0 & 15); emit(p1 >> 4, p1 & 15); emit(p2 >> 4, p2 & 15); emit(p3 >> 4, p3 & 15);
+            return;
+        }
+    }
     // 1. seed: three rounds of "farthest point from the current one"
     int pos = 0, far = 0, maxd = 0;
     for (int it = 0; it < 3; ++it) {
@@ -312,7 +390,7 @@ __device__ bool process_level_image(S& sc, const uint32_t* bm, bool legacy, Emit
             if (!c) break;
             const int x = __ffs((int)c) - 1;
             const bool is_hole = !((outer >> x) & 1u);
-            const int n = follow_border(sc, bm, x, y, is_hole);
+            const int n = follow_border(sc, bm, x, y, is_hole, !is_hole);
             if (!is_hole) {
                 if (n < 0) ok = false;
                 else approx_and_emit(sc, n, legacy, emit);
@@ -365,10 +443,75 @@ __device__ bool process_level_image_lockstep(S& sc, const uint32_t* bm, bool has
         if (!__any_sync(0xffffffffu, active)) break;
         int n = 0;
         if (active) {
-            n = follow_border(sc, bm, x, y, is_hole);
+            n = follow_border(sc, bm, x, y, is_hole, !is_hole);
             window = 0xFFFFu & ~((2u << x) - 1u);
         }
         if (active && !is_hole) {
+            if (n < 0) ok = false;
+            else approx_and_emit(sc, n, legacy, emit);
+        }
+    }
+    return ok;
+}
+
+// ---- component-first formulation ------------------------------------------------------------------------
+// cv2.findContours(RETR_TREE) + find_out_contour keep exactly one contour per 8-connected foreground
+// component (nested islands included): its outer border, followed from the component's raster-first
+// pixel.  That pixel has background at W, NW, N and NE.  Instead of following every hole border just to
+// maintain Suzuki's labels, every unvisited pixel with that local property is tried as a start: if it is
+// a component's first pixel the path is the outer border (signed area <= 0); the only other
+// possibility is a pixel on a hole border of an already followed component, whose path runs the other
+// way round (signed area > 0) and is dropped.  Plain holes (e.g. rectangular footprints inside a level
+// set) contain no such pixel and are never followed at all.
+__device__ __forceinline__ uint32_t start_candidates(const uint32_t* bm, int y, uint32_t visited) {
+    const uint32_t f = row16(bm, y);
+    const uint32_t up = row16(bm, y - 1);
+    return f & ~(f << 1) & ~(up | (up << 1) | (up >> 1)) & ~visited & 0xFFFFu;
+}
+
+template <class S, class Emit>
+__device__ bool process_level_image_cf(S& sc, const uint32_t* bm, bool legacy, Emit emit) {
+    for (int y = 0; y < 16; ++y) sc.set_mk(y, 0u);
+    bool ok = true;
+    for (int y = 0; y < 16; ++y) {
+        for (;;) {
+            const uint32_t c = start_candidates(bm, y, sc.mk(y));
+            if (!c) break;
+            const int x = __ffs((int)c) - 1;
+            int area2;
+            const int n = follow_outer(sc, bm, x, y, area2);
+            if (area2 <= 0) {
+                if (n < 0) ok = false;
+                else approx_and_emit(sc, n, legacy, emit);
+            }
+        }
+    }
+    return ok;
+}
+
+// Warp lock-step variant (all 32 lanes call it; has_task = false for idle lanes): every lane finds its
+// next start, then all lanes follow their borders together, then all approximate together.
+template <class S, class Emit>
+__device__ bool process_level_image_cf_lockstep(S& sc, const uint32_t* bm, bool has_task, bool legacy, Emit emit) {
+    bool active = has_task;
+    bool ok = true;
+    int y = 0;
+    if (active) { for (int q = 0; q < 16; ++q) sc.set_mk(q, 0u); }
+    for (;;) {
+        int x = 0;
+        if (active) {
+            bool found = false;
+            while (y < 16) {
+                const uint32_t c = start_candidates(bm, y, sc.mk(y));
+                if (c) { x = __ffs((int)c) - 1; found = true; break; }
+                ++y;
+            }
+            active = found;
+        }
+        if (!__any_sync(0xffffffffu, active)) break;
+        int n = 0, area2 = 1;
+        if (active) n = follow_outer(sc, bm, x, y, area2);
+        if (active && area2 <= 0) {
             if (n < 0) ok = false;
             else approx_and_emit(sc, n, legacy, emit);
         }

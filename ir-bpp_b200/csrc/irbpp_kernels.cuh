@@ -42,7 +42,8 @@ constexpr int STEP = 2;                  // stepSize = resolutionAct / resolutio
 constexpr int NPOSE = AX * AY;           // 256 poses per rotation
 constexpr int CTA_THREADS = 128;
 constexpr int CTA_WARPS = CTA_THREADS / 32;
-constexpr int ENVS_PER_CTA = 4;          // bins per CTA of the candidates kernel (one warp each in phase D)
+constexpr int ENVS_PER_CTA = 1;          // bins (= warps) per CTA of the candidates kernel
+constexpr int CAND_THREADS = 32 * ENVS_PER_CTA;
 constexpr int MAX_LEVELS = 64;           // level-image slots per (bin, rotation) in the scratch
 constexpr int SLOT_WORDS = 9;            // 8 bitmap words + 1 pad (bank spread) in shared memory
 constexpr int FAST_CAP = 64;             // contour points on the fast path
@@ -79,6 +80,7 @@ struct Params {
     double binz, resZ, binvol;
     // shapes
     int32_t S;
+    int32_t maxwh;                       // largest w*h of the library (size of a warp's table buffer)
     const ShapeRot* srot;                // [S*R]
     const double* Bs;                    // bottom tables, +inf where maskB == 0
     const double* Ts;                    // top tables, -inf where maskT == 0
@@ -103,6 +105,7 @@ struct Params {
     const uint8_t* which;                // MODE_RESET (NULL = all)
     const int32_t* dbg_items;            // MODE_DEBUG_SCAN
     int32_t slot;                        // MODE_ALL_OBS: queue slot of this pass
+    int32_t env_lo, env_hi;              // bins [env_lo, env_hi) handled by this launch (chunked pipeline)
     // outputs
     float* obs;                          // [N][obs_stride] (+ slot offset in MODE_ALL_OBS)
     float* r_reward; uint8_t* r_done; uint8_t* r_valid; uint8_t* r_error;
@@ -160,55 +163,76 @@ __device__ __forceinline__ int level_of(const Params& P, double posz, double inv
 // ---- phase B: one warp scans one rotation -------------------------------------------------------------
 // Writes posz[r][256], maskbits[r][8], the level bitmaps and their count (space.py:98-129,
 // cvTools.py:78-85).  Returns true if any pose is feasible.
-__device__ __forceinline__ bool scan_rotation(const Params& P, const double* hm_s, int env, int item, int r,
-                                              int lane, int& err) {
+// The bottom table is staged in this warp's shared-memory buffer (every lane reads the same element:
+// a broadcast); each lane carries two poses, (X, Y) and (X + 8, Y), so one table element serves two
+// window cells.
+__device__ __forceinline__ bool scan_rotation(const Params& P, const double* hm_s, double* bs, int env, int item,
+                                              int r, int lane, int& err) {
     const ShapeRot* sr = P.srot + (int64_t)item * P.R + r;
     const int w = sr->w, h = sr->h, nX = sr->nX, nY = sr->nY;
     const double ez = sr->ez;
     const double init = sr->any_zero ? 0.0 : -INFINITY;
-    const double* __restrict__ B = P.Bs + sr->off;
+    {
+        const double* __restrict__ B = P.Bs + sr->off;
+        __syncwarp();                                   // previous rotation's readers are done
+        for (int c = lane; c < w * h; c += 32) bs[c] = __ldg(B + c);
+        __syncwarp();
+    }
     const int hpairs = h >> 1;
     const double inv = 1.0 / P.resZ;
     double* posz_g = P.posz + ((int64_t)env * P.R + r) * NPOSE;
     uint32_t* mask_g = P.maskbits + ((int64_t)env * P.R + r) * 8;
     int lv[8];
     uint32_t pres_lo = 0, pres_hi = 0, any = 0;
+    const int Y = lane & 15;
 #pragma unroll
-    for (int pass = 0; pass < 8; ++pass) {
-        const int p = pass * 32 + lane;
-        const int X = p >> 4, Y = p & 15;
-        const bool valid = (X < nX) && (Y < nY);
-        double acc = POSZ_INVALID;
-        bool feas = false;
-        if (valid) {
-            acc = init;
-            const double* h0 = hm_s + (STEP * X) * (HY / 2) + Y;        // even heightmap columns
-            const double* brow = B;
+    for (int pass = 0; pass < 4; ++pass) {
+        const int pA = pass * 32 + lane;
+        const int X = pA >> 4;
+        const bool validA = (X < nX) && (Y < nY);
+        const bool validB = (X + 8 < nX) && (Y < nY);
+        double accA = POSZ_INVALID, accB = POSZ_INVALID;
+        bool feasA = false, feasB = false;
+        if (validA) {
+            accA = init; accB = init;
+            const double* a0 = hm_s + (STEP * X) * (HY / 2) + Y;                   // even heightmap columns
+            const double* b0 = validB ? a0 + STEP * 8 * (HY / 2) : a0;             // pose (X + 8, Y)
+            const double* brow = bs;
 #pragma unroll 1
             for (int i = 0; i < w; ++i) {
-                const double* h1 = h0 + HX * (HY / 2);                   // odd heightmap columns
+                const double* a1 = a0 + HX * (HY / 2);                              // odd heightmap columns
+                const double* b1 = b0 + HX * (HY / 2);
                 int jj = 0;
 #pragma unroll 2
                 for (; jj < hpairs; ++jj) {
-                    const double v0 = h0[jj] - __ldg(brow + 2 * jj);
-                    const double v1 = h1[jj] - __ldg(brow + 2 * jj + 1);
-                    acc = (v0 > acc) ? v0 : acc;
-                    acc = (v1 > acc) ? v1 : acc;
+                    const double t0 = brow[2 * jj], t1 = brow[2 * jj + 1];
+                    const double u0 = a0[jj] - t0, u1 = a1[jj] - t1;
+                    const double v0 = b0[jj] - t0, v1 = b1[jj] - t1;
+                    accA = (u0 > accA) ? u0 : accA;
+                    accB = (v0 > accB) ? v0 : accB;
+                    accA = (u1 > accA) ? u1 : accA;
+                    accB = (v1 > accB) ? v1 : accB;
                 }
                 if (h & 1) {
-                    const double v0 = h0[jj] - __ldg(brow + 2 * jj);
-                    acc = (v0 > acc) ? v0 : acc;
+                    const double t0 = brow[2 * jj];
+                    const double u0 = a0[jj] - t0, v0 = b0[jj] - t0;
+                    accA = (u0 > accA) ? u0 : accA;
+                    accB = (v0 > accB) ? v0 : accB;
                 }
-                h0 += HY / 2;
+                a0 += HY / 2; b0 += HY / 2;
                 brow += h;
             }
-            feas = round6_le0(acc + ez - P.binz);
+            feasA = round6_le0(accA + ez - P.binz);
+            if (validB) feasB = round6_le0(accB + ez - P.binz); else accB = POSZ_INVALID;
         }
-        posz_g[p] = acc;
-        const uint32_t mb = __ballot_sync(0xffffffffu, feas);
-        if (lane == 0) mask_g[pass] = mb;
-        any |= mb;
-        lv[pass] = feas ? level_of(P, acc, inv, pres_lo, pres_hi, err) : -1;
+        posz_g[pA] = accA;
+        posz_g[pA + 128] = accB;
+        const uint32_t mbA = __ballot_sync(0xffffffffu, feasA);
+        const uint32_t mbB = __ballot_sync(0xffffffffu, feasB);
+        if (lane == 0) { mask_g[pass] = mbA; mask_g[pass + 4] = mbB; }
+        any |= mbA | mbB;
+        lv[pass] = feasA ? level_of(P, accA, inv, pres_lo, pres_hi, err) : -1;
+        lv[pass + 4] = feasB ? level_of(P, accB, inv, pres_lo, pres_hi, err) : -1;
     }
     pres_lo = __reduce_or_sync(0xffffffffu, pres_lo);
     pres_hi = __reduce_or_sync(0xffffffffu, pres_hi);
@@ -221,9 +245,10 @@ __device__ __forceinline__ bool scan_rotation(const Params& P, const double* hm_
 // ---- scan kernel ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(CTA_THREADS, 8) irbpp_scan_kernel(const Params P) {
     __shared__ __align__(16) double hm_s[HX * HY];
+    extern __shared__ __align__(16) double bstage[];     // CTA_WARPS x P.maxwh: bottom table of each warp's rotation
     __shared__ double z_sh;
     __shared__ int ok_sh, rot_sh, lx_sh, ly_sh, item_sh, err_sh, any_sh;
-    const int env = blockIdx.x;
+    const int env = P.env_lo + blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int mode = P.mode;
     if (mode == MODE_RESET && P.which && !P.which[env]) return;
@@ -397,7 +422,8 @@ __global__ void __launch_bounds__(CTA_THREADS, 8) irbpp_scan_kernel(const Params
     {
         int err = 0;
         bool any = false;
-        for (int r = warp; r < P.R; r += CTA_WARPS) any |= scan_rotation(P, hm_s, env, item, r, lane, err);
+        for (int r = warp; r < P.R; r += CTA_WARPS)
+            any |= scan_rotation(P, hm_s, bstage + warp * P.maxwh, env, item, r, lane, err);
         if (lane == 0 && any) any_sh = 1;
         if (__any_sync(0xffffffffu, err) && lane == 0) err_sh = 4;
     }
@@ -414,7 +440,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 8) irbpp_scan_kernel(const Params
 // ---- levels kernel (MODE_DEBUG_HULLS): level bitmaps from caller-supplied posZValid / mask ------------------
 __global__ void __launch_bounds__(CTA_THREADS) irbpp_levels_kernel(const Params P) {
     __shared__ int err_sh;
-    const int env = blockIdx.x;
+    const int env = P.env_lo + blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double inv = 1.0 / P.resZ;
     if (threadIdx.x == 0) err_sh = 0;
@@ -442,111 +468,96 @@ __global__ void __launch_bounds__(CTA_THREADS) irbpp_levels_kernel(const Params 
 }
 
 // ---- candidates kernel ----------------------------------------------------------------------------------
-struct CandSmem {
-    uint32_t slots[CTA_THREADS * SLOT_WORDS];              // level image of every lane's task
-    uint32_t marks[16 * CTA_THREADS];                      // per-lane Suzuki labels, element stride CTA_THREADS
-    uint8_t pts[FAST_CAP * CTA_THREADS];                   // per-lane contour points, element stride CTA_THREADS
-    uint32_t candbits[ENVS_PER_CTA * MAX_ROT * 8];         // 256-bit candidate set per (bin, rotation)
-    int32_t pre[ENVS_PER_CTA * MAX_ROT + 1];               // prefix of level counts over (bin, rotation)
-    int32_t ovf_count;
-    int32_t ovf_task[32];
-    int32_t error[ENVS_PER_CTA];
-    uint32_t big_w[16];
-    uint8_t big_b[2 * BIG_CAP];
+// One WARP per bin, no block-level synchronisation: lanes = the bin's (rotation, level) images, 32 per round.
+struct WarpSmem {
+    uint32_t slots[32 * SLOT_WORDS];          // level image of every lane's task
+    uint32_t marks[16 * 32];                  // per-lane Suzuki labels, element stride 32   } reused as the
+    uint8_t pts[FAST_CAP * 32];               // per-lane contour points, element stride 32  } overflow buffers
+    uint32_t candbits[MAX_ROT * 8];           // 256-bit candidate set per rotation
+    int32_t pre[MAX_ROT + 1];                 // prefix of level counts over rotations
 };
+static_assert(16 * 32 * 4 + FAST_CAP * 32 >= 16 * 4 + 2 * BIG_CAP, "overflow buffers must fit the lane scratch");
 
-__global__ void __launch_bounds__(CTA_THREADS) irbpp_candidates_kernel(const Params P) {
+__global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Params P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    CandSmem& S = *reinterpret_cast<CandSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int env0 = blockIdx.x * ENVS_PER_CTA;
-    const int nenv = min(ENVS_PER_CTA, P.N - env0);
+    WarpSmem& S = reinterpret_cast<WarpSmem*>(smem_raw)[warp];
+    const int env = P.env_lo + blockIdx.x * ENVS_PER_CTA + warp;
     const int R = P.R;
-    const int npairs = nenv * R;                           // (bin, rotation) pairs of this CTA
     long long t_prev = P.phase_cycles ? clock64() : 0;
     auto phase_mark = [&](int idx) {
-        if (P.phase_cycles && tid == 0) {
+        if (P.phase_cycles && lane == 0) {
             const long long now = clock64();
             atomicAdd(P.phase_cycles + idx, (unsigned long long)(now - t_prev));
             t_prev = now;
         }
     };
+    if (env >= P.env_hi) return;
+    if (P.mode == MODE_RESET && P.which && !P.which[env]) return;
 
-    for (int i = tid; i < ENVS_PER_CTA * MAX_ROT * 8; i += CTA_THREADS) S.candbits[i] = 0u;
-    if (tid < ENVS_PER_CTA) S.error[tid] = 0;
-    if (tid == 0) {
-        S.ovf_count = 0;
-        int acc = 0;
-        S.pre[0] = 0;
-        for (int q = 0; q < npairs; ++q) {
-            const int e = env0 + q / R;
-            const bool live = !(P.mode == MODE_RESET && P.which && !P.which[e]);
-            acc += live ? P.nlevels[(int64_t)env0 * R + q] : 0;
-            S.pre[q + 1] = acc;
-        }
+    for (int i = lane; i < R * 8; i += 32) S.candbits[i] = 0u;
+    {   // prefix of the level counts (R <= 32: one lane per rotation)
+        int c = (lane < R) ? P.nlevels[(int64_t)env * R + lane] : 0;
+        int incl = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int tt = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += tt; }
+        if (lane < R) S.pre[lane + 1] = incl;
+        if (lane == 0) S.pre[0] = 0;
     }
-    __syncthreads();
-    const int ntask = S.pre[npairs];
+    __syncwarp();
+    const int ntask = S.pre[R];
+    int dev_err = 0;
 
-    // ---- phase C: one level image per lane, dense over the bins of this CTA ----
-    for (int base = 0; base < ntask; base += CTA_THREADS) {
-        const int t = base + tid;
+    // ---- phase C: one level image per lane ----
+    for (int base = 0; base < ntask; base += 32) {
+        const int t = base + lane;
         const bool has = t < ntask;
         int q = 0;
-        if (has) {                                          // (bin, rotation) pair owning task t
-            int lo = 0, hi = npairs;                        // pre[lo] <= t < pre[hi]
+        if (has) {                                          // rotation owning task t: pre[q] <= t < pre[q+1]
+            int lo = 0, hi = R;
             while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (S.pre[mid] <= t) lo = mid; else hi = mid; }
             q = lo;
         }
-        uint32_t* bm = S.slots + tid * SLOT_WORDS;
+        uint32_t* bm = S.slots + lane * SLOT_WORDS;
         if (has) {
             const uint4* src = reinterpret_cast<const uint4*>(
-                P.bitmaps + (((int64_t)env0 * R + q) * MAX_LEVELS + (t - S.pre[q])) * 8);
+                P.bitmaps + (((int64_t)env * R + q) * MAX_LEVELS + (t - S.pre[q])) * 8);
             const uint4 a = src[0], b = src[1];
             bm[0] = a.x; bm[1] = a.y; bm[2] = a.z; bm[3] = a.w; bm[4] = b.x; bm[5] = b.y; bm[6] = b.z; bm[7] = b.w;
         }
-        StridedScratch<CTA_THREADS, FAST_CAP> sc;
-        sc.w = S.marks + tid;
-        sc.b = S.pts + tid;
+        StridedScratch<32, FAST_CAP> sc;
+        sc.w = S.marks + lane;
+        sc.b = S.pts + lane;
         sc.kept = 0;
         uint32_t* cb = S.candbits + q * 8;
-        const bool okc = process_level_image_lockstep(
+        const bool okc = process_level_image_cf_lockstep(
             sc, bm, has, P.legacy != 0,
             [&](int x, int y) { const int b = x * 16 + y; atomicOr(cb + (b >> 5), 1u << (b & 31)); });
-        if (!okc) {
-            const int k = atomicAdd(&S.ovf_count, 1);
-            if (k < 32) S.ovf_task[k] = (q << 16) | tid;
-        }
-        __syncthreads();
-        if (S.ovf_count > 0) {          // rare: contours longer than FAST_CAP points, serial path
-            if (tid == 0) {
+        __syncwarp();
+        // rare: a contour longer than FAST_CAP points; the lanes concerned redo their image one at a time
+        // with 1024-point buffers laid over the (now idle) lane scratch of this warp
+        uint32_t ovf = __ballot_sync(0xffffffffu, !okc);
+        while (ovf) {
+            const int src_lane = __ffs((int)ovf) - 1;
+            ovf &= ovf - 1;
+            if (lane == src_lane) {
                 FlatScratch<BIG_CAP> bs;
-                bs.w = S.big_w;
-                bs.b = S.big_b;
-                const int n_ovf = S.ovf_count;
-                if (n_ovf > 32) S.error[0] = 5;
-                for (int k = 0; k < (n_ovf < 32 ? n_ovf : 32); ++k) {
-                    const int qq = S.ovf_task[k] >> 16, lt = S.ovf_task[k] & 0xFFFF;
-                    uint32_t* cb2 = S.candbits + qq * 8;
-                    const bool ok2 = process_level_image(
-                        bs, S.slots + lt * SLOT_WORDS, P.legacy != 0,
-                        [&](int x, int y) { const int b = x * 16 + y; cb2[b >> 5] |= 1u << (b & 31); });
-                    if (!ok2) S.error[qq / R] = 6;
-                }
-                S.ovf_count = 0;
+                bs.w = S.marks;
+                bs.b = reinterpret_cast<uint8_t*>(S.marks + 16);
+                const bool ok2 = process_level_image_cf(
+                    bs, bm, P.legacy != 0,
+                    [&](int x, int y) { const int b = x * 16 + y; cb[b >> 5] |= 1u << (b & 31); });
+                if (!ok2) dev_err = 6;
             }
-            __syncthreads();
+            __syncwarp();
         }
     }
-    __syncthreads();
+    __syncwarp();
     phase_mark(2);   // contour tasks
 
-    // ---- phase D: one warp per bin ----
-    if (warp >= nenv) return;
-    const int env = env0 + warp;
-    if (P.mode == MODE_RESET && P.which && !P.which[env]) return;
+    // ---- phase D ----
     const int sel = P.sel;
-    const uint32_t* cbits = S.candbits + warp * R * 8;
+    const uint32_t* cbits = S.candbits;
     const uint32_t* mask_g = P.maskbits + (int64_t)env * R * 8;
     const double* posz_g = P.posz + (int64_t)env * R * NPOSE;
     float* obs_g = P.obs + (int64_t)env * P.obs_stride + (P.mode == MODE_ALL_OBS ? P.slot * P.loc_len : 0);
@@ -603,23 +614,55 @@ __global__ void __launch_bounds__(CTA_THREADS) irbpp_candidates_kernel(const Par
             zero_rows(total < sel ? total : sel);
         }
     } else {
-        // rows in rotation order, then (col, row) ascending == bit order of the per-rotation sets
-        for (int r = 0; r < R; ++r) {
-            const uint32_t* cb = cbits + r * 8;
-            int ord0 = __shfl_sync(0xffffffffu, excl, r);
+        // rows in rotation order, then (col, row) ascending == bit order of the per-rotation sets.
+        // Pass 1 compacts the set bits into a list (no memory loads); pass 2 gives every lane one
+        // candidate, so the height gathers of 32 candidates are in flight together.
+        uint16_t* list = reinterpret_cast<uint16_t*>(S.slots);        // lane scratch is idle now
+        constexpr int LIST_CAP = (int)((sizeof(S.slots) + sizeof(S.marks) + sizeof(S.pts)) / 2);
+        auto cell_of = [](int e) { const int b = e & 255; return (e >> 8) * NPOSE + (b & 15) * 16 + (b >> 4); };
+        if (Ktot <= LIST_CAP) {
+            for (int r = 0; r < R; ++r) {
+                const uint32_t* cb = cbits + r * 8;
+                int ord0 = __shfl_sync(0xffffffffu, excl, r);
+#pragma unroll
+                for (int qd = 0; qd < 8; ++qd) {
+                    const uint32_t wbits = cb[qd];
+                    if ((wbits >> lane) & 1u)
+                        list[ord0 + __popc(wbits & ((1u << lane) - 1u))] = (uint16_t)((r << 8) | (qd * 32 + lane));
+                    ord0 += __popc(wbits);
+                }
+            }
+            __syncwarp();
+            for (int i = lane; i < Ktot; i += 32) {
+                const int e = list[i];
+                const int r = e >> 8, b = e & 255;
+                bool m; const double H = height_of(cell_of(e), m);
+                int dest = i;
+                if (Ktot > sel) {
+                    // truncate to the `sel` lowest heights, ties by original order (stable argsort;
+                    // binPhy.py:209-212)
+                    int rank = 0;
+                    for (int j = 0; j < Ktot; ++j) {
+                        bool m2; const double H2 = height_of(cell_of(list[j]), m2);
+                        rank += (H2 < H) || (H2 == H && j < i);
+                    }
+                    dest = rank;
+                }
+                if (dest < sel) put_row(dest, r, b & 15, b >> 4, H, m ? 1.0 : 0.0);
+            }
+        } else {
+            for (int r = 0; r < R; ++r) {
+                const uint32_t* cb = cbits + r * 8;
+                int ord0 = __shfl_sync(0xffffffffu, excl, r);
 #pragma unroll 1
-            for (int qd = 0; qd < 8; ++qd) {
-                const uint32_t wbits = cb[qd];
-                if ((wbits >> lane) & 1u) {
-                    const int ord = ord0 + __popc(wbits & ((1u << lane) - 1u));
-                    const int b = qd * 32 + lane;
-                    const int col = b >> 4, row = b & 15;
-                    bool m; const double H = height_of(r * NPOSE + row * 16 + col, m);
-                    int dest = ord;
-                    if (Ktot > sel) {
-                        // truncate to the `sel` lowest heights, ties by original order (stable argsort;
-                        // binPhy.py:209-212)
-                        int rank = 0, ord2 = 0;
+                for (int qd = 0; qd < 8; ++qd) {
+                    const uint32_t wbits = cb[qd];
+                    if ((wbits >> lane) & 1u) {
+                        const int ord = ord0 + __popc(wbits & ((1u << lane) - 1u));
+                        const int b = qd * 32 + lane;
+                        const int col = b >> 4, row = b & 15;
+                        bool m; const double H = height_of(r * NPOSE + row * 16 + col, m);
+                        int rank = 0, ord2 = 0;                   // Ktot > LIST_CAP >= sel: always truncating
                         for (int r2 = 0; r2 < R; ++r2) {
                             const uint32_t* cb2 = cbits + r2 * 8;
                             for (int q2 = 0; q2 < 8; ++q2) {
@@ -633,17 +676,17 @@ __global__ void __launch_bounds__(CTA_THREADS) irbpp_candidates_kernel(const Par
                                 }
                             }
                         }
-                        dest = rank;
+                        if (rank < sel) put_row(rank, r, row, col, H, m ? 1.0 : 0.0);
                     }
-                    if (dest < sel) put_row(dest, r, row, col, H, m ? 1.0 : 0.0);
+                    ord0 += __popc(wbits);
                 }
-                ord0 += __popc(wbits);
             }
         }
         if (Ktot < sel) zero_rows(Ktot);
     }
+    dev_err = __reduce_max_sync(0xffffffffu, dev_err);
     if (lane == 0) {
-        if (S.error[warp]) P.r_error[env] = (uint8_t)S.error[warp];
+        if (dev_err) P.r_error[env] = (uint8_t)dev_err;
         if (P.dbg_nhull) P.dbg_nhull[env] = Ktot;
     }
     phase_mark(3);   // select / pad, candidate rows of the observation

@@ -20,6 +20,16 @@ extern "C" int hull_bits(const uint16_t* rows, int legacy, int use_big, uint32_t
     uint32_t bm[8];
     for (int i = 0; i < 8; ++i) bm[i] = (uint32_t)rows[2 * i] | ((uint32_t)rows[2 * i + 1] << 16);
     auto emit = [&](int x, int y) { const int b = x * 16 + y; out_bits[b >> 5] |= 1u << (b & 31); };
+    if (use_big == 3) {   // component-first, serial, long buffers
+        static uint32_t w[16]; static uint8_t b[2 * 1024];
+        irbpp::FlatScratch<1024> sc; sc.w = w; sc.b = b;
+        return irbpp::process_level_image_cf(sc, bm, legacy != 0, emit) ? 0 : 1;
+    }
+    if (use_big == 4) {   // component-first, lock-step routine with one lane
+        static uint32_t w[16]; static uint8_t b[64];
+        irbpp::StridedScratch<1, 64> sc; sc.w = w; sc.b = b; sc.kept = 0;
+        return irbpp::process_level_image_cf_lockstep(sc, bm, true, legacy != 0, emit) ? 0 : 1;
+    }
     if (use_big == 1) {
         static uint32_t w[16]; static uint8_t b[2 * 1024];
         irbpp::FlatScratch<1024> sc; sc.w = w; sc.b = b;

@@ -100,6 +100,13 @@ def test_device_contour_routines_match_oracle(contour_harness):
             for _ in range(int(rng.integers(1, 9))):
                 x0, y0 = rng.integers(0, 15, 2); w, h = rng.integers(1, 5, 2)
                 img[x0:x0 + w, y0:y0 + h] = 0
+        elif it % 8 == 7:   # nested rings and islands, noise
+            img = np.zeros((16, 16), np.uint8)
+            a = int(rng.integers(0, 3)); img[a:16 - a, a:16 - a] = 1
+            b = a + int(rng.integers(1, 3)); img[b:16 - b, b:16 - b] = 0
+            c = b + int(rng.integers(1, 3)); img[c:16 - c, c:16 - c] = 1
+            d = c + 1; img[d:16 - d, d:16 - d] = 0
+            img ^= (rng.random((16, 16)) < 0.06).astype(np.uint8)
         else:
             img = ((np.add.outer(np.arange(16), np.arange(16)) % 2) == 0).astype(np.uint8)
             img &= (rng.random((16, 16)) < 0.9).astype(np.uint8)
@@ -111,6 +118,12 @@ def test_device_contour_routines_match_oracle(contour_harness):
             rc_fast, got_fast = _dev_bits(contour_harness, img, legacy, 0)
             rc_big, got_big = _dev_bits(contour_harness, img, legacy, 1)
             assert rc_big == 0 and got_big == want
+            # component-first formulation (what the kernels run): serial long-buffer and lock-step variants
+            rc_cf, got_cf = _dev_bits(contour_harness, img, legacy, 3)
+            assert rc_cf == 0 and got_cf == want
+            rc_cfl, got_cfl = _dev_bits(contour_harness, img, legacy, 4)
+            if rc_cfl == 0:
+                assert got_cfl == want
             assert (rc_fast == 1) == (maxlen > 64)          # fast path reports overflow exactly when it must
             if rc_fast == 0:
                 assert got_fast == want
