@@ -133,7 +133,7 @@ int irbpp_create(const irbpp_config* cfg, irbpp_handle* out) {
     P.binz = cfg->bin_dimension[2];
     P.resZ = cfg->resolution_z;
     P.binvol = (cfg->bin_dimension[0] * cfg->bin_dimension[1]) * cfg->bin_dimension[2];   // np.prod
-    h->cand_smem = (int)sizeof(WarpSmem) * ENVS_PER_CTA;
+    h->cand_smem = (int)sizeof(CandSmem);
 
 #define TRY_ALLOC(expr)                                                                          \
     do { cudaError_t e2_ = (expr); if (e2_ != cudaSuccess) {                                      \

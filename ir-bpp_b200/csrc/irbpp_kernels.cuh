@@ -42,7 +42,10 @@ constexpr int STEP = 2;                  // stepSize = resolutionAct / resolutio
 constexpr int NPOSE = AX * AY;           // 256 poses per rotation
 constexpr int CTA_THREADS = 128;
 constexpr int CTA_WARPS = CTA_THREADS / 32;
-constexpr int ENVS_PER_CTA = 1;          // bins (= warps) per CTA of the candidates kernel
+#ifndef IRBPP_ENVS_PER_CTA
+#define IRBPP_ENVS_PER_CTA 4
+#endif
+constexpr int ENVS_PER_CTA = IRBPP_ENVS_PER_CTA;   // bins (= warps) per CTA of the candidates kernel
 constexpr int CAND_THREADS = 32 * ENVS_PER_CTA;
 constexpr int MAX_LEVELS = 64;           // level-image slots per (bin, rotation) in the scratch
 constexpr int SLOT_WORDS = 9;            // 8 bitmap words + 1 pad (bank spread) in shared memory
@@ -468,66 +471,123 @@ __global__ void __launch_bounds__(CTA_THREADS) irbpp_levels_kernel(const Params 
 }
 
 // ---- candidates kernel ----------------------------------------------------------------------------------
-// One WARP per bin, no block-level synchronisation: lanes = the bin's (rotation, level) images, 32 per round.
-struct WarpSmem {
-    uint32_t slots[32 * SLOT_WORDS];          // level image of every lane's task
-    uint32_t marks[16 * 32];                  // per-lane Suzuki labels, element stride 32   } reused as the
-    uint8_t pts[FAST_CAP * 32];               // per-lane contour points, element stride 32  } overflow buffers
-    uint32_t candbits[MAX_ROT * 8];           // 256-bit candidate set per rotation
-    int32_t pre[MAX_ROT + 1];                 // prefix of level counts over rotations
+// One CTA per ENVS_PER_CTA bins, one warp per bin in phase D.  In phase C every (bin, rotation, level)
+// image of the CTA is one lane's task; the tasks are ordered by a cost key (number of border pixels) so
+// that the lanes of a warp carry images of similar size -- the lanes run in lock step and a warp costs
+// what its heaviest lane costs (the floor-level image of each rotation is an order of magnitude
+// heavier than the small plateaus above it).
+struct WarpScratch {
+    uint32_t marks[16 * 32];                  // per-lane visited bits, element stride 32   } reused as the overflow
+    uint8_t pts[FAST_CAP * 32];               // per-lane contour points, element stride 32 } buffers and the row list
 };
-static_assert(16 * 32 * 4 + FAST_CAP * 32 >= 16 * 4 + 2 * BIG_CAP, "overflow buffers must fit the lane scratch");
+static_assert(sizeof(WarpScratch) >= 16 * 4 + 2 * BIG_CAP, "overflow buffers must fit the lane scratch");
+
+struct CandSmem {
+    uint32_t slots[CAND_THREADS * SLOT_WORDS];            // level image of task t (CTA-wide task index)
+    WarpScratch ws[ENVS_PER_CTA];
+    uint32_t candbits[ENVS_PER_CTA * MAX_ROT * 8];        // 256-bit candidate set per (bin, rotation)
+    int32_t pre[ENVS_PER_CTA * MAX_ROT + 1];              // prefix of level counts over (bin, rotation)
+    uint16_t order[CAND_THREADS];                         // task index by decreasing cost
+    uint16_t pair_of[CAND_THREADS];                       // (bin, rotation) pair of task t
+    int32_t hist[64], base[64];
+    int32_t error[ENVS_PER_CTA];
+};
 
 __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Params P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    CandSmem& S = *reinterpret_cast<CandSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    WarpSmem& S = reinterpret_cast<WarpSmem*>(smem_raw)[warp];
-    const int env = P.env_lo + blockIdx.x * ENVS_PER_CTA + warp;
+    const int env0 = P.env_lo + blockIdx.x * ENVS_PER_CTA;
+    const int nenv = min(ENVS_PER_CTA, P.env_hi - env0);
     const int R = P.R;
+    const int npairs = nenv * R;
     long long t_prev = P.phase_cycles ? clock64() : 0;
     auto phase_mark = [&](int idx) {
-        if (P.phase_cycles && lane == 0) {
+        if (P.phase_cycles && tid == 0) {
             const long long now = clock64();
             atomicAdd(P.phase_cycles + idx, (unsigned long long)(now - t_prev));
             t_prev = now;
         }
     };
-    if (env >= P.env_hi) return;
-    if (P.mode == MODE_RESET && P.which && !P.which[env]) return;
+    auto env_live = [&](int e) { return !(P.mode == MODE_RESET && P.which && !P.which[e]); };
 
-    for (int i = lane; i < R * 8; i += 32) S.candbits[i] = 0u;
-    {   // prefix of the level counts (R <= 32: one lane per rotation)
-        int c = (lane < R) ? P.nlevels[(int64_t)env * R + lane] : 0;
-        int incl = c;
+    for (int i = tid; i < ENVS_PER_CTA * R * 8; i += CAND_THREADS) S.candbits[i] = 0u;
+    if (tid < ENVS_PER_CTA) S.error[tid] = 0;
+    if (warp == 0) {   // prefix of the level counts over the (bin, rotation) pairs, 32 pairs per step
+        int carry = 0;
+        for (int b = 0; b < npairs; b += 32) {
+            const int q = b + lane;
+            int c = 0;
+            if (q < npairs && env_live(env0 + q / R)) c = P.nlevels[(int64_t)env0 * R + q];
+            int incl = c;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int tt = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += tt; }
-        if (lane < R) S.pre[lane + 1] = incl;
+            for (int o = 1; o < 32; o <<= 1) { const int tt = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += tt; }
+            if (q < npairs) S.pre[q + 1] = carry + incl;
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
         if (lane == 0) S.pre[0] = 0;
     }
-    __syncwarp();
-    const int ntask = S.pre[R];
+    __syncthreads();
+    const int ntask = S.pre[npairs];
     int dev_err = 0;
 
-    // ---- phase C: one level image per lane ----
-    for (int base = 0; base < ntask; base += 32) {
-        const int t = base + lane;
-        const bool has = t < ntask;
-        int q = 0;
-        if (has) {                                          // rotation owning task t: pre[q] <= t < pre[q+1]
-            int lo = 0, hi = R;
+    // ---- phase C ----
+    for (int base = 0; base < ntask; base += CAND_THREADS) {
+        const int nround = min(CAND_THREADS, ntask - base);
+        // 1. load this thread's task image, compute its cost key, histogram
+        if (tid < 64) S.hist[tid] = 0;
+        __syncthreads();
+        int my_bucket = 0, my_off = 0;
+        if (tid < nround) {
+            const int t = base + tid;
+            int lo = 0, hi = npairs;                        // pre[lo] <= t < pre[hi]
             while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (S.pre[mid] <= t) lo = mid; else hi = mid; }
-            q = lo;
-        }
-        uint32_t* bm = S.slots + lane * SLOT_WORDS;
-        if (has) {
             const uint4* src = reinterpret_cast<const uint4*>(
-                P.bitmaps + (((int64_t)env * R + q) * MAX_LEVELS + (t - S.pre[q])) * 8);
+                P.bitmaps + (((int64_t)env0 * R + lo) * MAX_LEVELS + (t - S.pre[lo])) * 8);
             const uint4 a = src[0], b = src[1];
+            uint32_t* bm = S.slots + tid * SLOT_WORDS;
             bm[0] = a.x; bm[1] = a.y; bm[2] = a.z; bm[3] = a.w; bm[4] = b.x; bm[5] = b.y; bm[6] = b.z; bm[7] = b.w;
+            S.pair_of[tid] = (uint16_t)lo;
+            // cost key: horizontal + vertical foreground/background transitions (~ border length)
+            const uint32_t wv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            int key = 0;
+            uint32_t prev_row = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t r0 = wv[k] & 0xFFFFu, r1 = wv[k] >> 16;
+                key += __popc(r0 ^ (r0 << 1)) + __popc(r1 ^ (r1 << 1)) + __popc(r0 ^ prev_row) + __popc(r1 ^ r0);
+                prev_row = r1;
+            }
+            key += __popc(prev_row);
+            my_bucket = 63 - min(63, key >> 2);             // bucket 0 = heaviest
+            my_off = atomicAdd(&S.hist[my_bucket], 1);
         }
+        __syncthreads();
+        if (warp == 0) {   // exclusive prefix over the 64 buckets
+            const int h0 = S.hist[lane], h1 = S.hist[32 + lane];
+            int i0 = h0, i1 = h1;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t0 = __shfl_up_sync(0xffffffffu, i0, o), t1 = __shfl_up_sync(0xffffffffu, i1, o);
+                if (lane >= o) { i0 += t0; i1 += t1; }
+            }
+            const int tot0 = __shfl_sync(0xffffffffu, i0, 31);
+            S.base[lane] = i0 - h0;
+            S.base[32 + lane] = tot0 + i1 - h1;
+        }
+        __syncthreads();
+        if (tid < nround) S.order[S.base[my_bucket] + my_off] = (uint16_t)tid;
+        __syncthreads();
+
+        // 2. lane i of the CTA takes the i-th heaviest task
+        const bool has = tid < nround;
+        const int slot = has ? S.order[tid] : 0;
+        const int q = has ? S.pair_of[slot] : 0;
+        const uint32_t* bm = S.slots + slot * SLOT_WORDS;
+        WarpScratch& W = S.ws[warp];
         StridedScratch<32, FAST_CAP> sc;
-        sc.w = S.marks + lane;
-        sc.b = S.pts + lane;
+        sc.w = W.marks + lane;
+        sc.b = W.pts + lane;
         sc.kept = 0;
         uint32_t* cb = S.candbits + q * 8;
         const bool okc = process_level_image_cf_lockstep(
@@ -542,22 +602,29 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
             ovf &= ovf - 1;
             if (lane == src_lane) {
                 FlatScratch<BIG_CAP> bs;
-                bs.w = S.marks;
-                bs.b = reinterpret_cast<uint8_t*>(S.marks + 16);
+                bs.w = W.marks;
+                bs.b = reinterpret_cast<uint8_t*>(W.marks + 16);
                 const bool ok2 = process_level_image_cf(
                     bs, bm, P.legacy != 0,
-                    [&](int x, int y) { const int b = x * 16 + y; cb[b >> 5] |= 1u << (b & 31); });
-                if (!ok2) dev_err = 6;
+                    [&](int x, int y) { const int b = x * 16 + y; atomicOr(cb + (b >> 5), 1u << (b & 31)); });
+                if (!ok2) atomicMax(&S.error[q / R], 6);
             }
             __syncwarp();
         }
+        __syncthreads();
     }
-    __syncwarp();
+    __syncthreads();
     phase_mark(2);   // contour tasks
 
+    // ---- phase D: warp w serves bin env0 + w ----
+    if (warp >= nenv) return;
+    const int env = env0 + warp;
+    if (!env_live(env)) return;
+    dev_err = S.error[warp];
+    WarpScratch& WS = S.ws[warp];
     // ---- phase D ----
     const int sel = P.sel;
-    const uint32_t* cbits = S.candbits;
+    const uint32_t* cbits = S.candbits + warp * R * 8;
     const uint32_t* mask_g = P.maskbits + (int64_t)env * R * 8;
     const double* posz_g = P.posz + (int64_t)env * R * NPOSE;
     float* obs_g = P.obs + (int64_t)env * P.obs_stride + (P.mode == MODE_ALL_OBS ? P.slot * P.loc_len : 0);
@@ -617,8 +684,8 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
         // rows in rotation order, then (col, row) ascending == bit order of the per-rotation sets.
         // Pass 1 compacts the set bits into a list (no memory loads); pass 2 gives every lane one
         // candidate, so the height gathers of 32 candidates are in flight together.
-        uint16_t* list = reinterpret_cast<uint16_t*>(S.slots);        // lane scratch is idle now
-        constexpr int LIST_CAP = (int)((sizeof(S.slots) + sizeof(S.marks) + sizeof(S.pts)) / 2);
+        uint16_t* list = reinterpret_cast<uint16_t*>(&WS);            // lane scratch is idle now
+        constexpr int LIST_CAP = (int)(sizeof(WarpScratch) / 2);
         auto cell_of = [](int e) { const int b = e & 255; return (e >> 8) * NPOSE + (b & 15) * 16 + (b >> 4); };
         if (Ktot <= LIST_CAP) {
             for (int r = 0; r < R; ++r) {
@@ -684,7 +751,6 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
         }
         if (Ktot < sel) zero_rows(Ktot);
     }
-    dev_err = __reduce_max_sync(0xffffffffu, dev_err);
     if (lane == 0) {
         if (dev_err) P.r_error[env] = (uint8_t)dev_err;
         if (P.dbg_nhull) P.dbg_nhull[env] = Ktot;
