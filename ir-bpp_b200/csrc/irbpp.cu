@@ -140,11 +140,7 @@ int irbpp_create(const irbpp_config* cfg, irbpp_handle* out) {
         fail(nullptr, IRBPP_ECUDA, "%s: %s", #expr, cudaGetErrorString(e2_)); irbpp_destroy(h); return IRBPP_ECUDA; } } while (0)
     TRY_ALLOC(dev_alloc(h, &P.hm, (size_t)N * HX * HY));
     TRY_ALLOC(dev_alloc(h, &P.cand, (size_t)N * P.sel));
-    TRY_ALLOC(dev_alloc(h, &P.queue, (size_t)N * MAX_QUEUE));
-    TRY_ALLOC(dev_alloc(h, &P.cursor, N)); TRY_ALLOC(dev_alloc(h, &P.cur_item, N));
-    TRY_ALLOC(dev_alloc(h, &P.order_act, N)); TRY_ALLOC(dev_alloc(h, &P.packed, N));
-    TRY_ALLOC(dev_alloc(h, &P.ep_len, N)); TRY_ALLOC(dev_alloc(h, &P.vol_sum, N));
-    TRY_ALLOC(dev_alloc(h, &P.ep_rew, N)); TRY_ALLOC(dev_alloc(h, &P.mask_any, N));
+    TRY_ALLOC(dev_alloc(h, &P.state, (size_t)N));
     TRY_ALLOC(dev_alloc(h, &h->actions_dev, N)); TRY_ALLOC(dev_alloc(h, &h->which_dev, N));
     // scan -> candidates hand-over scratch
     TRY_ALLOC(dev_alloc(h, &P.posz, (size_t)N * P.R * NPOSE));
@@ -293,7 +289,8 @@ int irbpp_set_sequences(irbpp_handle h, const int32_t* ids, int32_t length) {
     cudaSetDevice(h->cfg.device);
     CUDA_TRY(h, dev_alloc(h, &h->seq_dev, n, false));
     CUDA_TRY(h, cudaMemcpy(h->seq_dev, ids, n * 4, cudaMemcpyHostToDevice));
-    CUDA_TRY(h, cudaMemset(h->P.cursor, 0, (size_t)h->P.N * 4));
+    CUDA_TRY(h, cudaMemset(h->P.state, 0, (size_t)h->P.N * sizeof(EnvState)));   // cursors restart
+    h->was_reset = false;
     h->P.seq = h->seq_dev; h->P.L = length;
     h->sequences_set = true;
     return IRBPP_OK;
@@ -466,14 +463,16 @@ int irbpp_debug_state(irbpp_handle h, double* heightmap, int32_t* queue, int32_t
                     heightmap[((size_t)e * HX + x) * HY + y] =
                         raw[(size_t)e * HX * HY + ((y & 1) * HX + x) * (HY / 2) + (y >> 1)];
     }
-    if (queue) {
-        std::vector<int32_t> q((size_t)N * MAX_QUEUE);
-        CUDA_TRY(h, cudaMemcpy(q.data(), h->P.queue, q.size() * 4, cudaMemcpyDeviceToHost));
+    if (queue || cursor || packed_count) {
+        std::vector<EnvState> st((size_t)N);
+        CUDA_TRY(h, cudaMemcpy(st.data(), h->P.state, st.size() * sizeof(EnvState), cudaMemcpyDeviceToHost));
         const int k = h->P.K > 1 ? h->P.K : 1;
-        for (int e = 0; e < N; ++e) for (int i = 0; i < k; ++i) queue[(size_t)e * k + i] = q[(size_t)e * MAX_QUEUE + i];
+        for (int e = 0; e < N; ++e) {
+            if (queue) for (int i = 0; i < k; ++i) queue[(size_t)e * k + i] = st[e].queue[i];
+            if (cursor) cursor[e] = st[e].cursor;
+            if (packed_count) packed_count[e] = st[e].packed;
+        }
     }
-    if (cursor) CUDA_TRY(h, cudaMemcpy(cursor, h->P.cursor, (size_t)N * 4, cudaMemcpyDeviceToHost));
-    if (packed_count) CUDA_TRY(h, cudaMemcpy(packed_count, h->P.packed, (size_t)N * 4, cudaMemcpyDeviceToHost));
     return IRBPP_OK;
 }
 

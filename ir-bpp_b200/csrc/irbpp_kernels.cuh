@@ -75,6 +75,21 @@ struct ShapeRot {          // one (shape, rotation) entry, device resident
     int64_t off;           // offset of Bs / Ts of this entry in the pools (doubles)
 };
 
+// Scalar state of one bin, 128 bytes so that one warp loads / stores it with one coalesced access.
+struct EnvState {
+    int32_t cursor;            // position in the item-id sequence (persists across episodes)
+    int32_t cur_item;          // item the current candidate table refers to (binPhy.py: next_item_ID)
+    int32_t order_act;         // binPhy.py: orderAction
+    int32_t packed;            // items packed in this episode (item_idx)
+    int32_t ep_len;            // steps in this episode
+    int32_t mask_any;          // sum(naiveMask) != 0 of the last scan (prejudge, binPhy.py:243)
+    double vol_sum;            // packed volume (get_ratio, binPhy.py:149-153)
+    double ep_rew;             // sum of episode rewards (monitor.py:60)
+    int32_t queue[MAX_QUEUE];  // item FIFO (IRcreator.py:6-24)
+    int32_t pad[6];
+};
+static_assert(sizeof(EnvState) == 128, "EnvState must be 128 bytes");
+
 struct Params {
     // configuration
     int32_t N, R, sel, K;                // K = buffer_size (1 = online)
@@ -94,10 +109,7 @@ struct Params {
     // per-env state
     double* hm;                          // [N][2][32][16] column-parity planes
     uint16_t* cand;                      // [N][sel] rot<<8 | x<<4 | y
-    int32_t* queue;                      // [N][MAX_QUEUE]
-    int32_t* cursor; int32_t* cur_item; int32_t* order_act; int32_t* packed; int32_t* ep_len;
-    double* vol_sum; double* ep_rew;
-    uint8_t* mask_any;
+    EnvState* state;                     // [N]
     // scan -> candidates hand-over (global scratch, L2 resident)
     double* posz;                        // [N][R][256] drop heights (posZmap)
     uint32_t* maskbits;                  // [N][R][8]   feasibility bits (naiveMask)
@@ -249,6 +261,7 @@ __device__ __forceinline__ bool scan_rotation(const Params& P, const double* hm_
 __global__ void __launch_bounds__(CTA_THREADS, 8) irbpp_scan_kernel(const Params P) {
     __shared__ __align__(16) double hm_s[HX * HY];
     extern __shared__ __align__(16) double bstage[];     // CTA_WARPS x P.maxwh: bottom table of each warp's rotation
+    __shared__ __align__(16) EnvState st_s;              // this bin's scalar state (loaded / stored by warp 0)
     __shared__ double z_sh;
     __shared__ int ok_sh, rot_sh, lx_sh, ly_sh, item_sh, err_sh, any_sh;
     const int env = P.env_lo + blockIdx.x;
@@ -276,29 +289,31 @@ __global__ void __launch_bounds__(CTA_THREADS, 8) irbpp_scan_kernel(const Params
         }
     }
     if (tid == 0) { err_sh = 0; any_sh = 0; }
+    if (warp == 0) reinterpret_cast<uint32_t*>(&st_s)[lane] = reinterpret_cast<const uint32_t*>(P.state + env)[lane];
     __syncthreads();
 
-    int32_t* queue_g = P.queue + (int64_t)env * MAX_QUEUE;
+    int32_t* queue_g = st_s.queue;
     bool hm_changed = false;
+    bool st_dirty = false;
 
     // ---- phase A: bookkeeping / apply action ----
     if (mode == MODE_RESET) {
         if (tid == 0) {
-            int cursor = P.cursor[env];
+            int cursor = st_s.cursor;
             const int nfill = P.K > 1 ? P.K : 1;
             for (int q = 0; q < nfill; ++q) queue_g[q] = draw_item(P, env, cursor);
-            P.cursor[env] = cursor;
-            P.packed[env] = 0; P.ep_len[env] = 0; P.vol_sum[env] = 0.0; P.ep_rew[env] = 0.0;
-            P.order_act[env] = 0;
+            st_s.cursor = cursor;
+            st_s.packed = 0; st_s.ep_len = 0; st_s.vol_sum = 0.0; st_s.ep_rew = 0.0;
+            st_s.order_act = 0;
             item_sh = queue_g[0];
         }
-        hm_changed = true;
+        hm_changed = true; st_dirty = true;
         __syncthreads();
     } else if (mode == MODE_STEP) {
         // decode the action (warp 0 computes the drop height of that single pose)
         if (warp == 0) {
             const int64_t a = P.actions[env];
-            const int item = P.cur_item[env];
+            const int item = st_s.cur_item;
             int rot = 0, lx = 0, ly = 0;
             bool ok = true;
             if (a < 0 || a >= P.sel) { ok = false; if (lane == 0) err_sh = 2; }
@@ -309,7 +324,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 8) irbpp_scan_kernel(const Params
             const ShapeRot* sr = P.srot + (int64_t)item * P.R + rot;
             // prejudge (binPhy.py:238-245)
             if (!((sr->okx >> lx) & 1u) || !((sr->oky >> ly) & 1u)) ok = false;
-            if (!P.mask_any[env]) ok = false;
+            if (!st_s.mask_any) ok = false;
             double z = POSZ_INVALID;     // posZmap keeps 1e3 outside the scanned range (space.py:101)
             if (lx < sr->nX && ly < sr->nY) {
                 const int w = sr->w, h = sr->h;
@@ -352,41 +367,42 @@ __global__ void __launch_bounds__(CTA_THREADS, 8) irbpp_scan_kernel(const Params
             for (int i = tid; i < HX * HY; i += CTA_THREADS) hm_s[i] = 0.0;    // auto-reset
         }
         if (tid == 0) {
-            int cursor = P.cursor[env];
+            int cursor = st_s.cursor;
             const int nfill = P.K > 1 ? P.K : 1;
             if (ok) {
                 const double rew = P.reward_tab[item];
                 P.r_reward[env] = (float)rew; P.r_done[env] = 0; P.r_valid[env] = 1;
                 P.r_counter[env] = -1; P.r_eplen[env] = 0; P.r_ratio[env] = -1.0; P.r_eprew[env] = 0.0;
-                P.packed[env] += 1; P.ep_len[env] += 1;
-                P.vol_sum[env] += P.vol[item];
-                P.ep_rew[env] += rew;
+                st_s.packed += 1; st_s.ep_len += 1;
+                st_s.vol_sum += P.vol[item];
+                st_s.ep_rew += rew;
                 // item_creator.update_item_queue(orderAction); generate_item()  (binPhy.py:324-325)
-                const int oa = P.order_act[env];
+                const int oa = st_s.order_act;
                 for (int q = oa; q + 1 < nfill; ++q) queue_g[q] = queue_g[q + 1];
                 queue_g[nfill - 1] = draw_item(P, env, cursor);
             } else {
                 P.r_reward[env] = 0.0f; P.r_done[env] = 1; P.r_valid[env] = 1;
-                P.r_counter[env] = P.packed[env];
-                P.r_ratio[env] = P.vol_sum[env] / P.binvol;
-                P.r_eplen[env] = P.ep_len[env] + 1;
-                P.r_eprew[env] = P.ep_rew[env] + 0.0;
-                P.packed[env] = 0; P.ep_len[env] = 0; P.vol_sum[env] = 0.0; P.ep_rew[env] = 0.0;
-                P.order_act[env] = 0;
+                P.r_counter[env] = st_s.packed;
+                P.r_ratio[env] = st_s.vol_sum / P.binvol;
+                P.r_eplen[env] = st_s.ep_len + 1;
+                P.r_eprew[env] = st_s.ep_rew + 0.0;
+                st_s.packed = 0; st_s.ep_len = 0; st_s.vol_sum = 0.0; st_s.ep_rew = 0.0;
+                st_s.order_act = 0;
                 for (int q = 0; q < nfill; ++q) queue_g[q] = draw_item(P, env, cursor);   // reset(): clear + preview
             }
-            P.cursor[env] = cursor;
+            st_s.cursor = cursor;
             item_sh = queue_g[0];
         }
-        hm_changed = true;
+        hm_changed = true; st_dirty = true;
         __syncthreads();
     } else if (mode == MODE_CANDIDATES) {
         if (tid == 0) {
             int64_t oa = P.actions[env];
             if (oa < 0 || oa >= P.K) { err_sh = 3; oa = 0; }
-            P.order_act[env] = (int)oa;
+            st_s.order_act = (int)oa;
             item_sh = queue_g[oa];
         }
+        st_dirty = true;
         __syncthreads();
     } else if (mode == MODE_ALL_OBS) {
         if (tid == 0) item_sh = queue_g[P.slot];
@@ -417,6 +433,7 @@ __global__ void __launch_bounds__(CTA_THREADS, 8) irbpp_scan_kernel(const Params
         // order observation: [next k item ids | heightmap]  (binPhy.py:229-230)
         for (int i = tid; i < P.K; i += CTA_THREADS) obs_g[i] = (float)queue_g[i];
         if (tid == 0) P.r_error[env] = (uint8_t)err_sh;
+        if (st_dirty && warp == 0) reinterpret_cast<uint32_t*>(P.state + env)[lane] = reinterpret_cast<const uint32_t*>(&st_s)[lane];
         return;
     }
     if (tid < 9) obs_g[ncand + tid] = (tid == 0) ? (float)item : 0.0f;      // next_item_vec (binPhy.py:191)
@@ -435,7 +452,15 @@ __global__ void __launch_bounds__(CTA_THREADS, 8) irbpp_scan_kernel(const Params
         P.r_error[env] = (uint8_t)err_sh;          // the candidates kernel may overwrite with its own code
         const bool write_state = (mode == MODE_STEP || mode == MODE_RESET || mode == MODE_CANDIDATES ||
                                   (mode == MODE_ALL_OBS && P.slot == P.K - 1));
-        if (write_state) { P.cur_item[env] = item; P.mask_any[env] = (uint8_t)any_sh; }
+        if (write_state) { st_s.cur_item = item; st_s.mask_any = any_sh; }
+    }
+    {
+        const bool write_state = (mode == MODE_STEP || mode == MODE_RESET || mode == MODE_CANDIDATES ||
+                                  (mode == MODE_ALL_OBS && P.slot == P.K - 1));
+        if (st_dirty || write_state) {
+            __syncthreads();
+            if (warp == 0) reinterpret_cast<uint32_t*>(P.state + env)[lane] = reinterpret_cast<const uint32_t*>(&st_s)[lane];
+        }
     }
     phase_mark(1);   // observation heightmap, write-back, scan, level bitmaps
 }
