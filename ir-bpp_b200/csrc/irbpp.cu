@@ -9,6 +9,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+#include <cmath>
 #include <string>
 #include <vector>
 
@@ -42,6 +44,7 @@ struct irbpp_env {
     // shape pools
     ShapeRot* srot_dev = nullptr; double* Bs_dev = nullptr; double* Ts_dev = nullptr;
     double* vol_dev = nullptr; double* rew_dev = nullptr; int32_t* seq_dev = nullptr;
+    TileEntry* tiles_dev = nullptr;
     unsigned long long* phase_dev = nullptr;
     // chunked pipeline
     int nchunks = 1;
@@ -212,6 +215,7 @@ int irbpp_load_shapes(irbpp_handle h, int32_t S, int32_t R, const int32_t* dims,
     const irbpp_config& c = h->cfg;
     std::vector<ShapeRot> srot((size_t)S * R);
     std::vector<double> Bs, Ts;
+    std::vector<TileEntry> tiles;
     std::vector<double> rew(S);
     int maxwh = 1;
     for (int s = 0; s < S; ++s) {
@@ -235,7 +239,6 @@ int irbpp_load_shapes(irbpp_handle h, int32_t S, int32_t R, const int32_t* dims,
             q.nX = AX - wA + 1; q.nY = AY - hA + 1;                  // range(rangeX_A - rangeX_OA + 1)
             if (q.nX < 0) q.nX = 0; if (q.nY < 0) q.nY = 0;
             q.ez = np_round6(e[2]);
-            q.pad = 0;
             // prejudge (binPhy.py:236,240-241): round(round(l*resA, 6) + extent - bin, 6) > 0 fails
             q.okx = 0; q.oky = 0;
             for (int l = 0; l < AX; ++l) {
@@ -258,6 +261,40 @@ int irbpp_load_shapes(irbpp_handle h, int32_t S, int32_t R, const int32_t* dims,
                 Ts.push_back(mT[i] != 0.0 ? T[i] : -INFINITY);
             }
             q.any_zero = any_zero;
+            q.tile = 1; q.tile_off = 0; q.ntiles = 0;
+        }
+        // block structure of the bottom tables of shape s (all rotations must agree on the block size)
+        for (int t = 4; t >= 2; t >>= 1) {
+            bool ok = true;
+            std::vector<std::vector<TileEntry>> found(R);
+            for (int r = 0; r < R && ok; ++r) {
+                const ShapeRot& q = srot[(size_t)s * R + r];
+                const double* Bq = Bs.data() + q.off;            // +inf where masked
+                for (int bi = 0; bi * t < q.w && ok; ++bi)
+                    for (int bj = 0; bj * t < q.h && ok; ++bj) {
+                        const int i1 = std::min(bi * t + t, q.w), j1 = std::min(bj * t + t, q.h);
+                        bool any_open = false, any_masked = false, same = true;
+                        double b0 = 0.0; bool have = false;
+                        for (int i = bi * t; i < i1; ++i)
+                            for (int j = bj * t; j < j1; ++j) {
+                                const double b = Bq[(size_t)i * q.h + j];
+                                if (std::isinf(b)) any_masked = true;
+                                else { any_open = true; if (!have) { b0 = b; have = true; } else if (b != b0) same = false; }
+                            }
+                        if (!any_open) continue;                  // fully masked block contributes nothing
+                        if (any_masked || !same || i1 - bi * t != t || j1 - bj * t != t) { ok = false; break; }
+                        TileEntry e; e.du = (int16_t)(bi * t / 2); e.dv = (int16_t)(bj * t / 2); e.pad = 0; e.b = b0;
+                        found[r].push_back(e);
+                    }
+            }
+            if (ok) {
+                for (int r = 0; r < R; ++r) {
+                    ShapeRot& q = srot[(size_t)s * R + r];
+                    q.tile = t; q.tile_off = (int32_t)tiles.size(); q.ntiles = (int32_t)found[r].size();
+                    tiles.insert(tiles.end(), found[r].begin(), found[r].end());
+                }
+                break;
+            }
         }
     }
     cudaSetDevice(c.device);
@@ -266,6 +303,9 @@ int irbpp_load_shapes(irbpp_handle h, int32_t S, int32_t R, const int32_t* dims,
     CUDA_TRY(h, dev_alloc(h, &h->Ts_dev, Ts.size() + 1, false));
     CUDA_TRY(h, dev_alloc(h, &h->vol_dev, (size_t)S, false));
     CUDA_TRY(h, dev_alloc(h, &h->rew_dev, (size_t)S, false));
+    CUDA_TRY(h, dev_alloc(h, &h->tiles_dev, tiles.size() + 1, false));
+    if (!tiles.empty()) CUDA_TRY(h, cudaMemcpy(h->tiles_dev, tiles.data(), tiles.size() * sizeof(TileEntry), cudaMemcpyHostToDevice));
+    h->P.tiles = h->tiles_dev;
     CUDA_TRY(h, cudaMemcpy(h->srot_dev, srot.data(), srot.size() * sizeof(ShapeRot), cudaMemcpyHostToDevice));
     CUDA_TRY(h, cudaMemcpy(h->Bs_dev, Bs.data(), Bs.size() * 8, cudaMemcpyHostToDevice));
     CUDA_TRY(h, cudaMemcpy(h->Ts_dev, Ts.data(), Ts.size() * 8, cudaMemcpyHostToDevice));
