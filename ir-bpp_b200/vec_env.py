@@ -260,19 +260,33 @@ class GpuVecEnv(VecEnv):
         self._obs_pending = None
         res = self._result
         self._check(self._lib.irbpp_step_wait(self._h, ctypes.byref(res)))
-        n = self.num_envs
-
-        def view(ptr, ctype, dtype):
-            return np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctype)), shape=(n,)).astype(dtype, copy=True)
-
-        reward = view(res.reward, ctypes.c_float, np.float32)
-        done = view(res.done, ctypes.c_uint8, np.bool_)
-        valid = view(res.valid, ctypes.c_uint8, np.bool_)
-        infos = LazyInfos(valid, done, view(res.counter, ctypes.c_int32, np.int32),
-                          view(res.ratio, ctypes.c_double, np.float64),
-                          view(res.ep_reward, ctypes.c_double, np.float64),
-                          view(res.ep_len, ctypes.c_int32, np.int32), round(time.time() - self._tstart, 6))
+        v = self._host_views(res)
+        reward = v["reward"].copy()
+        done = v["done"].copy()
+        infos = LazyInfos(v["valid"].copy(), done, v["counter"].copy(), v["ratio"].copy(), v["ep_reward"].copy(),
+                          v["ep_len"].copy(), round(time.time() - self._tstart, 6))
         return obs, torch.from_numpy(reward).unsqueeze(dim=1), done, infos
+
+    def _host_views(self, res):
+        """NumPy views of the library's pinned result block (fixed addresses for the life of the handle;
+        built once -- constructing them per step costs more than the kernels' launch)."""
+        key = (res.reward, res.done)
+        if getattr(self, "_views_key", None) != key:
+            n = self.num_envs
+
+            def view(ptr, ctype, dtype):
+                buf = (ctype * n).from_address(ptr)
+                return np.frombuffer(buf, dtype=dtype, count=n)
+
+            self._views = {"reward": view(res.reward, ctypes.c_float, np.float32),
+                           "done": view(res.done, ctypes.c_uint8, np.bool_),
+                           "valid": view(res.valid, ctypes.c_uint8, np.bool_),
+                           "counter": view(res.counter, ctypes.c_int32, np.int32),
+                           "ep_len": view(res.ep_len, ctypes.c_int32, np.int32),
+                           "ratio": view(res.ratio, ctypes.c_double, np.float64),
+                           "ep_reward": view(res.ep_reward, ctypes.c_double, np.float64)}
+            self._views_key = key
+        return self._views
 
     def step_device(self, actions):
         """Device-resident loop: ``actions`` is a CUDA int64 tensor; nothing is copied to the host and
