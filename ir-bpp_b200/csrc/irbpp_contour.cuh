@@ -17,6 +17,7 @@
 // point contours, kept-set in a 64-bit register) and the overflow path (one thread, long buffers).
 #pragma once
 #include <stdint.h>
+#include <type_traits>
 
 namespace irbpp {
 
@@ -49,20 +50,30 @@ __device__ __forceinline__ uint32_t neighbour_ring(const uint32_t* bm, int x, in
 template <int STRIDE, int CAP_>
 struct StridedScratch {
     static constexpr int CAP = CAP_;
+    static_assert(CAP_ <= 64, "kept-set is one register pair at most");
     uint32_t* w;   // 16 mark rows, element stride STRIDE
     uint8_t* b;    // CAP contour points, element stride STRIDE
-    uint64_t kept;
+    typename std::conditional<(CAP_ <= 32), uint32_t, uint64_t>::type kept;
     __device__ __forceinline__ uint32_t mk(int y) const { return w[y * STRIDE]; }
     __device__ __forceinline__ void set_mk(int y, uint32_t v) { w[y * STRIDE] = v; }
     __device__ __forceinline__ int pt(int i) const { return b[i * STRIDE]; }
     __device__ __forceinline__ void set_pt(int i, int v) { b[i * STRIDE] = (uint8_t)v; }
-    __device__ __forceinline__ void kept_clear(int) { kept = 0ull; }
-    __device__ __forceinline__ void kept_set(int i) { kept |= (1ull << i); }
-    __device__ __forceinline__ int kept_count(int) const { return __popcll(kept); }
+    __device__ __forceinline__ void kept_clear(int) { kept = 0; }
+    __device__ __forceinline__ void kept_set(int i) { kept |= (decltype(kept))1 << i; }
+    __device__ __forceinline__ int kept_count(int) const {
+        if constexpr (CAP_ <= 32) return __popc((uint32_t)kept); else return __popcll((uint64_t)kept);
+    }
     // next kept index strictly after i, cyclically
     __device__ __forceinline__ int kept_next(int i, int) const {
-        const uint64_t hi = (i >= 63) ? 0ull : (kept & ~((2ull << i) - 1ull));
-        return hi ? (__ffsll((long long)hi) - 1) : (__ffsll((long long)kept) - 1);
+        if constexpr (CAP_ <= 32) {
+            const uint32_t k32 = (uint32_t)kept;
+            const uint32_t hi = (i >= 31) ? 0u : (k32 & ~((2u << i) - 1u));
+            return hi ? (__ffs((int)hi) - 1) : (__ffs((int)k32) - 1);
+        } else {
+            const uint64_t k64 = (uint64_t)kept;
+            const uint64_t hi = (i >= 63) ? 0ull : (k64 & ~((2ull << i) - 1ull));
+            return hi ? (__ffsll((long long)hi) - 1) : (__ffsll((long long)k64) - 1);
+        }
     }
 };
 
@@ -260,17 +271,16 @@ __device__ void approx_and_emit(S& sc, int n, bool legacy, Emit emit) {
                 k = (k + 1 == n) ? 0 : k + 1;
                 const int p = sc.pt(k);
                 const int vx = (p >> 4) - sx, vy = (p & 15) - sy;
-                int num;
-                if (legacy) {
-                    const int cr = vy * dx - vx * dy;
-                    num = cr < 0 ? -cr : cr;                 // |cross| (common factor 1/|seg|)
-                } else {
-                    const int dot = vx * dx + vy * dy;
-                    if (seg2 == 0) num = vx * vx + vy * vy;  // degenerate segment: plain distance^2
-                    else if (dot <= 0) num = (vx * vx + vy * vy) * seg2;
-                    else if (dot >= seg2) { const int wx = vx - dx, wy = vy - dy; num = (wx * wx + wy * wy) * seg2; }
-                    else { const int cr = vy * dx - vx * dy; num = cr * cr; }   // dist^2 * seg2
-                }
+                // dist^2 to the segment times seg2 (4.13 rule) or |cross| (legacy line rule), select form
+                const int cr = vy * dx - vx * dy;
+                const int d2 = vx * vx + vy * vy;
+                const int dot = vx * dx + vy * dy;
+                const int wx = vx - dx, wy = vy - dy;
+                int num = cr * cr;                                            // projection inside the segment
+                num = (dot >= seg2) ? (wx * wx + wy * wy) * seg2 : num;      // beyond the end point
+                num = (dot <= 0) ? d2 * seg2 : num;                          // before the start point
+                num = (seg2 == 0) ? d2 : num;                                // degenerate segment
+                num = legacy ? (cr < 0 ? -cr : cr) : num;
                 if (num > best) { best = num; bi = k; }
             }
             bool le;

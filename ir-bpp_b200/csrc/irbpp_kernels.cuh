@@ -49,7 +49,7 @@ constexpr int ENVS_PER_CTA = IRBPP_ENVS_PER_CTA;   // bins (= warps) per CTA of 
 constexpr int CAND_THREADS = 32 * ENVS_PER_CTA;
 constexpr int MAX_LEVELS = 64;           // level-image slots per (bin, rotation) in the scratch
 constexpr int SLOT_WORDS = 9;            // 8 bitmap words + 1 pad (bank spread) in shared memory
-constexpr int FAST_CAP = 64;             // contour points on the fast path
+constexpr int FAST_CAP = 64;             // contour points on the fast path (32 was measured slower: every overflow redo stalls a warp)
 constexpr int BIG_CAP = 1024;            // contour points on the overflow path
 constexpr int LEVEL_OFFSET = 32;         // levels in [-32, 31] -> presence bit (level + 32)
 constexpr int MAX_QUEUE = 16;            // buffer_size limit

@@ -10,6 +10,7 @@
 static inline int __ffs(int x) { return __builtin_ffs(x); }
 static inline int __ffsll(long long x) { return __builtin_ffsll(x); }
 static inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
+static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
 static inline int __any_sync(unsigned, int p) { return p; }   // one "lane": the lock-step variant degenerates to serial
 #include "../../ir-bpp_b200/csrc/irbpp_contour.cuh"
@@ -27,7 +28,7 @@ extern "C" int hull_bits(const uint16_t* rows, int legacy, int use_big, uint32_t
     }
     if (use_big == 4) {   // component-first, lock-step routine with one lane
         static uint32_t w[16]; static uint8_t b[64];
-        irbpp::StridedScratch<1, 64> sc; sc.w = w; sc.b = b; sc.kept = 0;
+        irbpp::StridedScratch<1, 32> sc; sc.w = w; sc.b = b; sc.kept = 0;
         return irbpp::process_level_image_cf_lockstep(sc, bm, true, legacy != 0, emit) ? 0 : 1;
     }
     if (use_big == 1) {

@@ -290,3 +290,45 @@ def test_full_size_properties():
     chunks = int(os.environ.get("IRBPP_CHUNKS", "1"))
     assert a.launch_count() == 62 * chunks  # (scan + candidates kernel) per chunk per reset / step
     a.close(); b.close()
+
+
+def test_full_size_subset_matches_oracle():
+    """4096 bins on the GPU, a random subset of 40 of them replayed by the oracle with the same actions:
+    bins are independent, so this is a value-exact check at the benchmark's batch size."""
+    import torch
+    from irbpp_b200 import shapes
+    from oracle.oracle_env import OracleConfig, OracleEnv
+    n = 4096
+    lib = shapes.make_blockout_library(32, seed=1)
+    seqs = shapes.make_sequences(n, 128, lib.num_shapes, seed=0)
+    env = _env(lib, seqs)
+    rng = np.random.default_rng(11)
+    subset = np.sort(rng.choice(n, size=40, replace=False))
+    cfg = OracleConfig(ZRotNum=4)
+    oracles = [OracleEnv(cfg, lib, seqs[i]) for i in subset]
+    obs = env.reset()
+    want = np.stack([o.reset() for o in oracles])
+    assert np.array_equal(obs[subset].cpu().numpy(), want.astype(np.float32))
+    gen = torch.Generator(device="cuda:0"); gen.manual_seed(3)
+    ep_r = [[] for _ in subset]
+    n_done = 0
+    for t in range(45):
+        mask = obs[:, :2500].view(n, 500, 5)[:, :, 4] == 1
+        acts = torch.argmax(torch.rand((n, 500), device="cuda:0", generator=gen) + mask.float(), dim=1)
+        obs, rew, done, infos = env.step(acts)
+        a = acts.cpu().numpy()
+        for k, i in enumerate(subset):
+            o, r, d, info = oracles[k].step(int(a[i]))
+            ep_r[k].append(r)
+            if d:
+                gi = infos[int(i)]
+                assert gi["counter"] == info["counter"] and gi["ratio"] == info["ratio"]
+                assert gi["episode"]["r"] == round(sum(ep_r[k]), 6) and gi["episode"]["l"] == len(ep_r[k])
+                ep_r[k] = []
+                o = oracles[k].reset()
+                n_done += 1
+            want[k] = o
+            assert np.float32(r) == rew[int(i), 0].item() and bool(d) == bool(done[i])
+        assert np.array_equal(obs[subset].cpu().numpy(), want.astype(np.float32)), t
+    assert n_done > 0
+    env.close()
