@@ -315,7 +315,13 @@ int irbpp_load_shapes(irbpp_handle h, int32_t S, int32_t R, const int32_t* dims,
     h->P.vol = h->vol_dev; h->P.reward_tab = h->rew_dev;
     h->P.maxwh = (maxwh + 1) & ~1;
     h->scan_smem = CTA_WARPS * h->P.maxwh * (int)sizeof(double);
-    CUDA_TRY(h, cudaFuncSetAttribute(irbpp_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->scan_smem));
+    {   // the attribute is per function, not per handle: only ever raise it (several handles may coexist)
+        static int scan_attr = 0;
+        if (h->scan_smem > scan_attr) {
+            CUDA_TRY(h, cudaFuncSetAttribute(irbpp_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->scan_smem));
+            scan_attr = h->scan_smem;
+        }
+    }
     h->shapes_loaded = true;
     return IRBPP_OK;
 }

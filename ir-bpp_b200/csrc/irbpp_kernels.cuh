@@ -47,6 +47,11 @@ constexpr int CTA_WARPS = CTA_THREADS / 32;
 #endif
 constexpr int ENVS_PER_CTA = IRBPP_ENVS_PER_CTA;   // bins (= warps) per CTA of the candidates kernel
 constexpr int CAND_THREADS = 32 * ENVS_PER_CTA;
+#ifndef IRBPP_TASK_LANES
+#define IRBPP_TASK_LANES 32
+#endif
+constexpr int TASK_LANES = IRBPP_TASK_LANES;          // lanes of a warp that carry a level image in phase C
+constexpr int ROUND_TASKS = ENVS_PER_CTA * TASK_LANES; // level images a CTA processes per round
 constexpr int MAX_LEVELS = 64;           // level-image slots per (bin, rotation) in the scratch
 constexpr int SLOT_WORDS = 9;            // 8 bitmap words + 1 pad (bank spread) in shared memory
 constexpr int FAST_CAP = 64;             // contour points on the fast path (32 was measured slower: every overflow redo stalls a warp)
@@ -326,7 +331,10 @@ __device__ __forceinline__ bool scan_rotation_tiles(const Params& P, const doubl
 }
 
 // ---- scan kernel ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(CTA_THREADS, 8) irbpp_scan_kernel(const Params P) {
+#ifndef IRBPP_SCAN_MIN_CTAS
+#define IRBPP_SCAN_MIN_CTAS 8
+#endif
+__global__ void __launch_bounds__(CTA_THREADS, IRBPP_SCAN_MIN_CTAS) irbpp_scan_kernel(const Params P) {
     __shared__ __align__(16) double hm_s[HX * HY];
     extern __shared__ __align__(16) double bstage[];     // CTA_WARPS x P.maxwh: bottom table of each warp's rotation
     __shared__ __align__(16) EnvState st_s;              // this bin's scalar state (loaded / stored by warp 0)
@@ -647,8 +655,8 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
     int dev_err = 0;
 
     // ---- phase C ----
-    for (int base = 0; base < ntask; base += CAND_THREADS) {
-        const int nround = min(CAND_THREADS, ntask - base);
+    for (int base = 0; base < ntask; base += ROUND_TASKS) {
+        const int nround = min(ROUND_TASKS, ntask - base);
         // 1. load this thread's task image, compute its cost key, histogram
         if (tid < 64) S.hist[tid] = 0;
         __syncthreads();
@@ -694,9 +702,11 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
         if (tid < nround) S.order[S.base[my_bucket] + my_off] = (uint16_t)tid;
         __syncthreads();
 
-        // 2. lane i of the CTA takes the i-th heaviest task
-        const bool has = tid < nround;
-        const int slot = has ? S.order[tid] : 0;
+        // 2. the first TASK_LANES lanes of every warp take tasks, heaviest first: fewer lanes per lock-step
+        //    group means less divergence inflation on the serial chain, and all warps of the CTA get work
+        const int ti = warp * TASK_LANES + lane;
+        const bool has = (lane < TASK_LANES) && (ti < nround);
+        const int slot = has ? S.order[ti] : 0;
         const int q = has ? S.pair_of[slot] : 0;
         const uint32_t* bm = S.slots + slot * SLOT_WORDS;
         WarpScratch& W = S.ws[warp];

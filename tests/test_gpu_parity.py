@@ -332,3 +332,78 @@ def test_full_size_subset_matches_oracle():
         assert np.array_equal(obs[subset].cpu().numpy(), want.astype(np.float32)), t
     assert n_done > 0
     env.close()
+
+
+def test_c_abi_error_behaviour():
+    """Error codes of the C ABI (include/irbpp.h): call order, argument validation, table validation."""
+    import ctypes
+    from irbpp_b200 import _lib, shapes
+    lib = _lib.load()
+    cfg = _lib.IrbppConfig()
+    cfg.num_envs, cfg.num_rotations, cfg.selected_action, cfg.buffer_size = 4, 4, 500, 1
+    cfg.bin_dimension[0], cfg.bin_dimension[1], cfg.bin_dimension[2] = 0.32, 0.32, 0.30
+    cfg.resolution_act, cfg.resolution_h, cfg.resolution_z = 0.02, 0.01, 0.01
+    cfg.device = 0
+    h = ctypes.c_void_p()
+    assert lib.irbpp_create(ctypes.byref(cfg), ctypes.byref(h)) == _lib.IRBPP_OK
+    import torch
+    obs = torch.empty((4, 3533), dtype=torch.float32, device="cuda:0")
+    acts = np.zeros(4, dtype=np.int64)
+    # nothing loaded yet
+    assert lib.irbpp_reset(h, None, obs.data_ptr(), None) == _lib.IRBPP_ESTATE
+    sl = shapes.make_blockout_library(6, seed=3)
+    dims, ext, vol, maps, offsets = sl.flat()
+    # rotation count mismatch, out-of-range table, non-0/1 mask
+    assert lib.irbpp_load_shapes(h, 6, 2, dims.ctypes.data, ext.ctypes.data, vol.ctypes.data, maps.ctypes.data,
+                                 offsets.ctypes.data, maps.size) == _lib.IRBPP_EINVAL
+    assert lib.irbpp_load_shapes(h, 6, 4, dims.ctypes.data, ext.ctypes.data, vol.ctypes.data, maps.ctypes.data,
+                                 offsets.ctypes.data, maps.size - 8) == _lib.IRBPP_EINVAL
+    bad = maps.copy(); n0 = int(dims[0, 0, 0] * dims[0, 0, 1]); bad[int(offsets[0, 0]) + 3 * n0] = 0.5
+    assert lib.irbpp_load_shapes(h, 6, 4, dims.ctypes.data, ext.ctypes.data, vol.ctypes.data, bad.ctypes.data,
+                                 offsets.ctypes.data, maps.size) == _lib.IRBPP_EINVAL
+    assert b"masks must be 0/1" in lib.irbpp_last_error(h)
+    # a window wider than its action footprint: the reference's slice would run off the heightmap
+    d2 = dims.copy(); d2[0, 0, 2] = 1
+    assert lib.irbpp_load_shapes(h, 6, 4, d2.ctypes.data, ext.ctypes.data, vol.ctypes.data, maps.ctypes.data,
+                                 offsets.ctypes.data, maps.size) == _lib.IRBPP_EINVAL
+    assert lib.irbpp_load_shapes(h, 6, 4, dims.ctypes.data, ext.ctypes.data, vol.ctypes.data, maps.ctypes.data,
+                                 offsets.ctypes.data, maps.size) == _lib.IRBPP_OK
+    ids = np.zeros((4, 8), dtype=np.int32); ids[2, 3] = 6
+    assert lib.irbpp_set_sequences(h, ids.ctypes.data, 8) == _lib.IRBPP_EINVAL            # id out of range
+    ids[2, 3] = 5
+    assert lib.irbpp_set_sequences(h, ids.ctypes.data, 8) == _lib.IRBPP_OK
+    # call order: step before reset, wait without step, double step_async, buffered-only calls
+    assert lib.irbpp_step_async(h, acts.ctypes.data, 0, obs.data_ptr(), None) == _lib.IRBPP_ESTATE
+    assert lib.irbpp_step_wait(h, None) == _lib.IRBPP_ESTATE
+    assert lib.irbpp_reset(h, None, obs.data_ptr(), None) == _lib.IRBPP_OK
+    assert lib.irbpp_step_async(h, acts.ctypes.data, 0, obs.data_ptr(), None) == _lib.IRBPP_OK
+    assert lib.irbpp_step_async(h, acts.ctypes.data, 0, obs.data_ptr(), None) == _lib.IRBPP_ESTATE
+    assert b"already running" in lib.irbpp_last_error(h)
+    assert lib.irbpp_step_wait(h, None) == _lib.IRBPP_OK
+    assert lib.irbpp_get_action_candidates(h, acts.ctypes.data, 0, obs.data_ptr(), None) == _lib.IRBPP_ESTATE
+    assert lib.irbpp_get_all_possible_observation(h, obs.data_ptr(), None) == _lib.IRBPP_ESTATE
+    assert lib.irbpp_step_async(h, None, 0, obs.data_ptr(), None) == _lib.IRBPP_EINVAL
+    assert lib.irbpp_launch_count(h) == 4
+    assert lib.irbpp_destroy(h) == _lib.IRBPP_OK
+
+
+def test_two_handles_with_different_libraries_coexist():
+    """Per-function CUDA attributes are shared by all handles of the process: a small-table handle created
+    after a large-table one must not break the first."""
+    from irbpp_b200 import shapes
+    from oracle.oracle_env import OracleConfig, OracleVecEnv
+    big = shapes.make_irregular_library(8, seed=5)
+    small = shapes.make_cube_library(seed=6, num_shapes=6)
+    sa = shapes.make_sequences(6, 16, big.num_shapes, seed=1)
+    sb = shapes.make_sequences(6, 16, small.num_shapes, seed=2)
+    a = _env(big, sa)
+    b = _env(small, sb)
+    oa = OracleVecEnv(OracleConfig(ZRotNum=8), big, sa)
+    ob = OracleVecEnv(OracleConfig(ZRotNum=2), small, sb)
+    assert np.array_equal(a.reset().cpu().numpy(), oa.reset().astype(np.float32))
+    assert np.array_equal(b.reset().cpu().numpy(), ob.reset().astype(np.float32))
+    for t in range(6):
+        acts = np.zeros(6, dtype=np.int64)
+        assert np.array_equal(a.step(acts)[0].cpu().numpy(), oa.step(acts)[0].astype(np.float32))
+        assert np.array_equal(b.step(acts)[0].cpu().numpy(), ob.step(acts)[0].astype(np.float32))
+    a.close(); b.close()
