@@ -19,10 +19,6 @@
 
 using namespace irbpp;
 
-#ifndef IRBPP_DEFAULT_CHUNKS
-#define IRBPP_DEFAULT_CHUNKS 1
-#endif
-
 static std::string g_create_error;
 
 struct irbpp_env {
@@ -46,10 +42,6 @@ struct irbpp_env {
     double* vol_dev = nullptr; double* rew_dev = nullptr; int32_t* seq_dev = nullptr;
     TileEntry* tiles_dev = nullptr;
     unsigned long long* phase_dev = nullptr;
-    // chunked pipeline
-    int nchunks = 1;
-    cudaStream_t chunk_stream[8] = {};
-    cudaEvent_t ev_fork = nullptr, ev_join[8] = {};
 };
 
 static int fail(irbpp_env* h, int code, const char* fmt, ...) {
@@ -169,17 +161,6 @@ int irbpp_create(const irbpp_config* cfg, irbpp_handle* out) {
         P.r_error = reinterpret_cast<uint8_t*>(b);
     }
     TRY_ALLOC(cudaFuncSetAttribute(irbpp_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->cand_smem));
-    {
-        const char* envc = getenv("IRBPP_CHUNKS");
-        int nc = envc ? atoi(envc) : IRBPP_DEFAULT_CHUNKS;
-        if (nc < 1) nc = 1; if (nc > 8) nc = 8;
-        h->nchunks = nc;
-        TRY_ALLOC(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-        for (int c = 0; c < nc; ++c) {
-            TRY_ALLOC(cudaStreamCreateWithFlags(&h->chunk_stream[c], cudaStreamNonBlocking));
-            TRY_ALLOC(cudaEventCreateWithFlags(&h->ev_join[c], cudaEventDisableTiming));
-        }
-    }
 #undef TRY_ALLOC
     *out = h;
     return IRBPP_OK;
@@ -190,8 +171,6 @@ int irbpp_destroy(irbpp_handle h) {
     cudaSetDevice(h->cfg.device);
     cudaDeviceSynchronize();
     for (void* p : h->dev_allocs) cudaFree(p);
-    for (int c = 0; c < 8; ++c) { if (h->chunk_stream[c]) cudaStreamDestroy(h->chunk_stream[c]); if (h->ev_join[c]) cudaEventDestroy(h->ev_join[c]); }
-    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->results_dev) cudaFree(h->results_dev);
     if (h->results_host) cudaFreeHost(h->results_host);
     if (h->actions_pinned) cudaFreeHost(h->actions_pinned);
@@ -343,35 +322,18 @@ int irbpp_set_sequences(irbpp_handle h, const int32_t* ids, int32_t length) {
 }
 
 // One pass of the pipeline: scan kernel (or the levels kernel for caller-supplied maps), then the
-// candidates kernel when the observation carries candidate rows.  The bins are cut into `nchunks`
-// ranges that run on internal streams: the scan kernel is issue-bound and the candidates kernel is a
-// latency-bound serial chain per lane, so letting chunk i's candidates kernel share the SMs with chunk
-// i+1's scan kernel fills issue slots that either kernel alone leaves idle.  The caller's stream
-// order is preserved with events (fork after everything already enqueued on `s`, join before return).
+// candidates kernel when the observation carries candidate rows.  (Running bin ranges on separate
+// streams so that one range's candidates kernel overlaps the next range's scan kernel was measured:
+// no gain -- the scan kernel owns the whole register file, the two cannot co-reside.)
 static int launch(irbpp_env* h, Params& P, cudaStream_t s) {
-    const int nch = (h->nchunks > 1 && P.N >= 64 * h->nchunks) ? h->nchunks : 1;
-    const bool cand = mode_emits_loc(P.mode, P.K);
-    if (nch > 1) {
-        cudaError_t e = cudaEventRecord(h->ev_fork, s);
-        if (e != cudaSuccess) return fail(h, IRBPP_ECUDA, "event record: %s", cudaGetErrorString(e));
-    }
-    for (int c = 0; c < nch; ++c) {
-        cudaStream_t cs = (nch > 1) ? h->chunk_stream[c] : s;
-        if (nch > 1) cudaStreamWaitEvent(cs, h->ev_fork, 0);
-        P.env_lo = (int)((int64_t)P.N * c / nch);
-        P.env_hi = (int)((int64_t)P.N * (c + 1) / nch);
-        const int n = P.env_hi - P.env_lo;
-        if (P.mode == MODE_DEBUG_HULLS) irbpp_levels_kernel<<<n, CTA_THREADS, 0, cs>>>(P);
-        else irbpp_scan_kernel<<<n, CTA_THREADS, h->scan_smem, cs>>>(P);
+    P.env_lo = 0;
+    P.env_hi = P.N;
+    if (P.mode == MODE_DEBUG_HULLS) irbpp_levels_kernel<<<P.N, CTA_THREADS, 0, s>>>(P);
+    else irbpp_scan_kernel<<<P.N, CTA_THREADS, h->scan_smem, s>>>(P);
+    h->launches += 1;
+    if (mode_emits_loc(P.mode, P.K)) {
+        irbpp_candidates_kernel<<<(P.N + ENVS_PER_CTA - 1) / ENVS_PER_CTA, CAND_THREADS, h->cand_smem, s>>>(P);
         h->launches += 1;
-        if (cand) {
-            irbpp_candidates_kernel<<<(n + ENVS_PER_CTA - 1) / ENVS_PER_CTA, CAND_THREADS, h->cand_smem, cs>>>(P);
-            h->launches += 1;
-        }
-        if (nch > 1) {
-            cudaEventRecord(h->ev_join[c], cs);
-            cudaStreamWaitEvent(s, h->ev_join[c], 0);
-        }
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(h, IRBPP_ECUDA, "kernel launch: %s", cudaGetErrorString(e));

@@ -4,11 +4,12 @@
 //   cvTools.py:86  cv2.findContours(check, RETR_TREE, CHAIN_APPROX_SIMPLE)  + find_out_contour (:7-38)
 //   cvTools.py:91  cv2.approxPolyDP(contour, 1, True)
 //   cvTools.py:92  find_convex_vetex (:40-59)
-// (paths relative to the reference root).  Algorithms: Suzuki-Abe border following with the
-// CHAIN_APPROX_SIMPLE emission rule; Douglas-Peucker with OpenCV's closed-curve seeding and
-// clean-up pass.  All arithmetic is integer (coordinates are 0..15), so there is nothing to round:
-// the float comparisons OpenCV performs are between exactly representable values and are restated
-// as integer cross-multiplications.
+// (paths relative to the reference root).  Algorithms: border following with the outer start rule of
+// Suzuki-Abe and the CHAIN_APPROX_SIMPLE emission rule, in a component-first formulation that never
+// follows hole borders (see below); Douglas-Peucker with OpenCV's closed-curve seeding and clean-up
+// pass.  All arithmetic is integer (coordinates are 0..15), so there is nothing to round: the float
+// comparisons OpenCV performs are between exactly representable values and are restated as integer
+// cross-multiplications.
 //
 // The level image is 8 words, two 16-bit rows per word (row y = bits (y&1)*16.. of word y>>1, bit x =
 // column x).  Border following works on the 8-neighbourhood ring of the current pixel (one byte built
@@ -36,17 +37,8 @@ __device__ __forceinline__ uint32_t row16(const uint32_t* bm, int y) {
     return ((unsigned)y < 16u) ? ((bm[y >> 1] >> ((y & 1) * 16)) & 0xFFFFu) : 0u;
 }
 
-// 8-neighbourhood of (x, y) as a byte: bit s set <=> the neighbour in direction s is foreground
-__device__ __forceinline__ uint32_t neighbour_ring(const uint32_t* bm, int x, int y) {
-    const uint32_t wm = ((row16(bm, y - 1) << 1) >> x) & 7u;   // bit0 = col x-1, bit1 = col x, bit2 = col x+1
-    const uint32_t w0 = ((row16(bm, y) << 1) >> x) & 7u;
-    const uint32_t wp = ((row16(bm, y + 1) << 1) >> x) & 7u;
-    const uint32_t rev = ((wm & 1u) << 2) | (wm & 2u) | (wm >> 2);   // NE, N, NW in direction order
-    return (w0 >> 2) | (rev << 1) | ((w0 & 1u) << 4) | (wp << 5);
-}
-
 // ---- scratch accessors -------------------------------------------------------------------------
-// marks: one word per image row; low half = "positive" Suzuki label per column, high half = "negative".
+// marks: one word per image row, bit x = pixel (x, y) has been visited by a followed border.
 template <int STRIDE, int CAP_>
 struct StridedScratch {
     static constexpr int CAP = CAP_;
@@ -96,69 +88,14 @@ struct FlatScratch {
     }
 };
 
-// ---- border following (Suzuki-Abe, CHAIN_APPROX_SIMPLE) -----------------------------------------
-// (x0, y0) unpadded.  Marks every visited border pixel; when `store` is set the emitted points are kept
-// as (x<<4 | y).  Returns the number of points, or -1 if it exceeded S::CAP (marks are still complete in
-// that case).  The three image rows around the current pixel are cached in registers (padded by one
-// zero column) and reloaded only on vertical moves.
+// ---- border following ------------------------------------------------------------------------------------
+// 8-neighbourhood ring of a pixel from the three (padded) image rows around it
 __device__ __forceinline__ uint32_t ring_from_rows(uint32_t rm, uint32_t r0, uint32_t rp, int x) {
     const uint32_t wm = (rm >> x) & 7u;   // bit0 = col x-1, bit1 = col x, bit2 = col x+1
     const uint32_t w0 = (r0 >> x) & 7u;
     const uint32_t wp = (rp >> x) & 7u;
     const uint32_t rev = ((wm & 1u) << 2) | (wm & 2u) | (wm >> 2);   // NE, N, NW in direction order
     return (w0 >> 2) | (rev << 1) | ((w0 & 1u) << 4) | (wp << 5);
-}
-
-template <class S>
-__device__ int follow_border(S& sc, const uint32_t* bm, int x0, int y0, bool hole, bool store) {
-    const int s_start = hole ? 0 : 4;
-    uint32_t rm = row16(bm, y0 - 1) << 1, r0 = row16(bm, y0) << 1, rp = row16(bm, y0 + 1) << 1;
-    uint32_t ring = ring_from_rows(rm, r0, rp, x0);
-    if (!ring) {  // isolated pixel
-        sc.set_mk(y0, sc.mk(y0) | (0x10000u << x0));
-        if (store) sc.set_pt(0, (x0 << 4) | y0);
-        return 1;
-    }
-    // clockwise search from s_start-1 down to s_start: highest set bit of the ring rotated by s_start
-    int s;
-    {
-        const uint32_t r2 = ((ring | (ring << 8)) >> s_start) & 0xFFu;
-        const int j = 31 - __clz((int)r2);
-        s = (s_start + j) & 7;
-    }
-    const int x1 = x0 + ddx(s), y1 = y0 + ddy(s);
-    int x3 = x0, y3 = y0;
-    int prev_s = s ^ 4;
-    int n = 0;
-    bool ovf = false;
-    for (;;) {
-        const int s_end = s;
-        // counter-clockwise search starting at s_end+1: lowest set bit of the ring rotated by s_end+1
-        const uint32_t rot = ((ring | (ring << 8)) >> ((s_end + 1) & 7)) & 0xFFu;
-        s = (s_end + __ffs((int)rot)) & 7;        // (s_end + 1 + (ffs-1)) & 7
-        const int dy = ddy(s);
-        const int x4 = x3 + ddx(s), y4 = y3 + dy;
-        {
-            const uint32_t m = sc.mk(y3);
-            if ((unsigned)(s - 1) < (unsigned)s_end) sc.set_mk(y3, m | (0x10000u << x3));
-            else if (!((m | (m >> 16)) & (1u << x3))) sc.set_mk(y3, m | (1u << x3));
-        }
-        if (s != prev_s) {
-            if (store) {
-                if (n < S::CAP) sc.set_pt(n, (x3 << 4) | y3);
-                else ovf = true;
-            }
-            ++n;
-        }
-        prev_s = s;
-        if (x4 == x0 && y4 == y0 && x3 == x1 && y3 == y1) break;
-        if (dy > 0) { rm = r0; r0 = rp; rp = row16(bm, y4 + 1) << 1; }
-        else if (dy < 0) { rp = r0; r0 = rm; rm = row16(bm, y4 - 1) << 1; }
-        x3 = x4; y3 = y4;
-        s = (s + 4) & 7;
-        ring = ring_from_rows(rm, r0, rp, x3);
-    }
-    return ovf ? -1 : n;
 }
 
 // Outer-rule border follower used by the component-first formulation below: starts at (x0, y0) whose
@@ -380,90 +317,6 @@ __device__ void approx_and_emit(S& sc, int n, bool legacy, Emit emit) {
     }
 }
 
-// ---- one level image: raster scan for border starts, follow, approximate, emit --------------------
-// Returns false if some outer contour overflowed S::CAP points (the caller re-runs the task on the
-// overflow path; emitting the other contours twice is harmless because emission is a set union).
-template <class S, class Emit>
-__device__ bool process_level_image(S& sc, const uint32_t* bm, bool legacy, Emit emit) {
-    for (int y = 0; y < 16; ++y) sc.set_mk(y, 0u);
-    bool ok = true;
-    for (int y = 0; y < 16; ++y) {
-        const uint32_t f = row16(bm, y);
-        if (!f) continue;
-        uint32_t window = 0xFFFFu;                          // columns still to visit in this row
-        for (;;) {
-            const uint32_t m = sc.mk(y);
-            const uint32_t posm = m & 0xFFFFu, negm = m >> 16;
-            const uint32_t outer = (f & ~posm & ~negm) & ~(f << 1);   // label 1 and left neighbour 0
-            const uint32_t hole = (f & ~negm) & ~(f >> 1);            // label >= 1 and right neighbour 0
-            const uint32_t c = (outer | hole) & window;
-            if (!c) break;
-            const int x = __ffs((int)c) - 1;
-            const bool is_hole = !((outer >> x) & 1u);
-            const int n = follow_border(sc, bm, x, y, is_hole, !is_hole);
-            if (!is_hole) {
-                if (n < 0) ok = false;
-                else approx_and_emit(sc, n, legacy, emit);
-            }
-            window = 0xFFFFu & ~((2u << x) - 1u);
-        }
-    }
-    return ok;
-}
-
-// ---- warp-lockstep variant --------------------------------------------------------------------------
-// Called by ALL 32 lanes of a warp (lanes without a task pass has_task = false).  Lane-private work is
-// the same as process_level_image, but the lanes advance contour by contour together: every lane
-// first finds ITS next border start, then all lanes with one follow their borders at the same time,
-// then the lanes holding an outer border approximate it at the same time.  This keeps the lanes of a
-// warp inside the same loops (SIMT efficiency = how similar the trip counts are) instead of
-// serialising on where in the raster scan each image happens to have a contour.
-template <class S, class Emit>
-__device__ bool process_level_image_lockstep(S& sc, const uint32_t* bm, bool has_task, bool legacy, Emit emit) {
-    bool active = has_task;
-    bool ok = true;
-    int y = 0;
-    uint32_t window = 0xFFFFu;
-    if (active) { for (int q = 0; q < 16; ++q) sc.set_mk(q, 0u); }
-    for (;;) {
-        int x = 0;
-        bool is_hole = false;
-        if (active) {
-            bool found = false;
-            while (y < 16) {
-                const uint32_t f = row16(bm, y);
-                if (f) {
-                    const uint32_t m = sc.mk(y);
-                    const uint32_t posm = m & 0xFFFFu, negm = m >> 16;
-                    const uint32_t outer = (f & ~posm & ~negm) & ~(f << 1);   // label 1 and left neighbour 0
-                    const uint32_t hole = (f & ~negm) & ~(f >> 1);            // label >= 1 and right neighbour 0
-                    const uint32_t c = (outer | hole) & window;
-                    if (c) {
-                        x = __ffs((int)c) - 1;
-                        is_hole = !((outer >> x) & 1u);
-                        found = true;
-                        break;
-                    }
-                }
-                ++y;
-                window = 0xFFFFu;
-            }
-            active = found;
-        }
-        if (!__any_sync(0xffffffffu, active)) break;
-        int n = 0;
-        if (active) {
-            n = follow_border(sc, bm, x, y, is_hole, !is_hole);
-            window = 0xFFFFu & ~((2u << x) - 1u);
-        }
-        if (active && !is_hole) {
-            if (n < 0) ok = false;
-            else approx_and_emit(sc, n, legacy, emit);
-        }
-    }
-    return ok;
-}
-
 // ---- component-first formulation ------------------------------------------------------------------------
 // cv2.findContours(RETR_TREE) + find_out_contour keep exactly one contour per 8-connected foreground
 // component (nested islands included): its outer border, followed from the component's raster-first
@@ -502,12 +355,15 @@ __device__ bool process_level_image_cf(S& sc, const uint32_t* bm, bool legacy, E
 // Warp lock-step variant (all 32 lanes call it; has_task = false for idle lanes): every lane finds its
 // next start, then all lanes follow their borders together, then all approximate together.
 template <class S, class Emit>
-__device__ bool process_level_image_cf_lockstep(S& sc, const uint32_t* bm, bool has_task, bool legacy, Emit emit) {
+__device__ bool process_level_image_cf_lockstep(S& sc, const uint32_t* bm, bool has_task, bool legacy, Emit emit,
+                                                long long* tm = nullptr) {
     bool active = has_task;
     bool ok = true;
     int y = 0;
     if (active) { for (int q = 0; q < 16; ++q) sc.set_mk(q, 0u); }
     for (;;) {
+        long long t0 = 0;
+        if (tm) t0 = clock64();
         int x = 0;
         if (active) {
             bool found = false;
@@ -519,12 +375,17 @@ __device__ bool process_level_image_cf_lockstep(S& sc, const uint32_t* bm, bool 
             active = found;
         }
         if (!__any_sync(0xffffffffu, active)) break;
+        long long t1 = 0;
+        if (tm) { t1 = clock64(); tm[0] += t1 - t0; }
         int n = 0, area2 = 1;
         if (active) n = follow_outer(sc, bm, x, y, area2);
+        long long t2 = 0;
+        if (tm) { __syncwarp(); t2 = clock64(); tm[1] += t2 - t1; }
         if (active && area2 <= 0) {
             if (n < 0) ok = false;
             else approx_and_emit(sc, n, legacy, emit);
         }
+        if (tm) { __syncwarp(); tm[2] += clock64() - t2; }
     }
     return ok;
 }

@@ -9,10 +9,12 @@
 //     B  scan every (rotation, X, Y) pose for the next item: drop height + feasibility
 //        (space.py:98-129), one warp per rotation, lanes = poses; level quantisation with NumPy
 //        floor_divide semantics (cvTools.py:78-79); one 16x16 bitmap per (rotation, level) by warp
-//        ballots -> global scratch (L2 resident)
+//        ballots -> global scratch (L2 resident).  Tables that are constant on square blocks of cells
+//        (voxel shapes) are scanned from block maxima of the heightmap (scan_rotation_tiles)
 //   irbpp_candidates_kernel  one CTA (128 threads) per 4 bins
-//     C  candidate extraction (cvTools.py:61-103): the level images of the 4 bins are dealt densely to
-//        the lanes (one image per lane, warps in lock step contour by contour): border following +
+//     C  candidate extraction (cvTools.py:61-103): every (bin, rotation, level) image of the CTA is one
+//        lane's task; tasks are ordered by a cost key so that the lanes of a warp carry images of
+//        similar size, and each warp advances in lock step, contour by contour: border following +
 //        approxPolyDP + convex filter (irbpp_contour.cuh), results OR-ed into a 256-bit set per
 //        (bin, rotation) in shared memory (np.unique == sorted set)
 //     D  select / pad (binPhy.py:205-225): one warp per bin ranks the set bits and writes the
@@ -20,11 +22,11 @@
 //        table the next step decodes its action from
 // (paths relative to the reference root)
 //
-// Why two kernels: phase C is one serial task per lane with ~25 tasks per bin; inside a one-bin CTA it
+// Why two kernels: phase C is one serial task per lane with ~16 tasks per bin; inside a one-bin CTA it
 // ran at ~3 active lanes per instruction and left the other warps waiting at a barrier (profiles/).
-// Splitting lets phase C pack tasks of several bins into full warps and lets phase B run at full
-// occupancy with 8 KB of shared memory.  The hand-over (float64 drop heights, masks, level bitmaps:
-// ~9 KB per bin) is written and re-read within microseconds and stays in the 126 MB L2.
+// Splitting lets phase C pack tasks of several bins into full warps and lets phase B run with 12 KB of
+// shared memory per CTA.  The hand-over (float64 drop heights, masks, level bitmaps: ~9 KB per bin) is
+// written and re-read within microseconds and stays in the 126 MB L2.
 //
 // Arithmetic is IEEE float64 exactly as NumPy performs it (compile with -fmad=false); masks are
 // folded into the tables as +/-inf sentinels at load time, which changes no comparison result.
@@ -715,10 +717,17 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
         sc.b = W.pts + lane;
         sc.kept = 0;
         uint32_t* cb = S.candbits + q * 8;
+        long long tm[3] = {0, 0, 0};
         const bool okc = process_level_image_cf_lockstep(
             sc, bm, has, P.legacy != 0,
-            [&](int x, int y) { const int b = x * 16 + y; atomicOr(cb + (b >> 5), 1u << (b & 31)); });
+            [&](int x, int y) { const int b = x * 16 + y; atomicOr(cb + (b >> 5), 1u << (b & 31)); },
+            P.phase_cycles ? tm : nullptr);
         __syncwarp();
+        if (P.phase_cycles && lane == 0 && warp == 0) {     // heaviest warp of the CTA: where its cycles go
+            atomicAdd(P.phase_cycles + 4, (unsigned long long)tm[0]);
+            atomicAdd(P.phase_cycles + 5, (unsigned long long)tm[1]);
+            atomicAdd(P.phase_cycles + 6, (unsigned long long)tm[2]);
+        }
         // rare: a contour longer than FAST_CAP points; the lanes concerned redo their image one at a time
         // with 1024-point buffers laid over the (now idle) lane scratch of this warp
         uint32_t ovf = __ballot_sync(0xffffffffu, !okc);

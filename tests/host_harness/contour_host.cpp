@@ -13,6 +13,8 @@ static inline int __popcll(unsigned long long x) { return __builtin_popcountll(x
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
 static inline int __any_sync(unsigned, int p) { return p; }   // one "lane": the lock-step variant degenerates to serial
+static inline long long clock64() { return 0; }
+static inline void __syncwarp() {}
 #include "../../ir-bpp_b200/csrc/irbpp_contour.cuh"
 #include "../../ir-bpp_b200/csrc/irbpp_math.cuh"
 
@@ -31,15 +33,7 @@ extern "C" int hull_bits(const uint16_t* rows, int legacy, int use_big, uint32_t
         irbpp::StridedScratch<1, 32> sc; sc.w = w; sc.b = b; sc.kept = 0;
         return irbpp::process_level_image_cf_lockstep(sc, bm, true, legacy != 0, emit) ? 0 : 1;
     }
-    if (use_big == 1) {
-        static uint32_t w[16]; static uint8_t b[2 * 1024];
-        irbpp::FlatScratch<1024> sc; sc.w = w; sc.b = b;
-        return irbpp::process_level_image(sc, bm, legacy != 0, emit) ? 0 : 1;
-    }
-    static uint32_t w[16]; static uint8_t b[64];
-    irbpp::StridedScratch<1, 64> sc; sc.w = w; sc.b = b; sc.kept = 0;
-    if (use_big == 0) return irbpp::process_level_image_lockstep(sc, bm, true, legacy != 0, emit) ? 0 : 1;
-    return irbpp::process_level_image(sc, bm, legacy != 0, emit) ? 0 : 1;
+    return -1;   // modes 3 (serial, long buffers) and 4 (lock-step routine, one lane) only
 }
 
 extern "C" void floor_div_many(const double* a, double b, int n, double* out) {

@@ -286,9 +286,7 @@ def test_full_size_properties():
         prev_hm = hm
         total_done += int(da.sum())
     assert total_done > 0
-    import os
-    chunks = int(os.environ.get("IRBPP_CHUNKS", "1"))
-    assert a.launch_count() == 62 * chunks  # (scan + candidates kernel) per chunk per reset / step
+    assert a.launch_count() == 62          # (scan + candidates kernel) per reset / step
     a.close(); b.close()
 
 

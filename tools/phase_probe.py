@@ -18,5 +18,5 @@ n = 20
 for _ in range(n):
     obs, _ = env.step_device(bench.device_policy(torch, obs, gen))
 c = env.debug_phase_cycles(False).astype(np.float64) / (n * bench.N_ENVS)
-names = ["scan:load+apply", "scan:obs+scan+bitmaps", "cand:contours(per 4 bins)", "cand:select/pad(per 4 bins)", "-"]
-print(json.dumps({"lib": os.environ.get("IRBPP_LIB", "default"), "cycles_per_cta": dict(zip(names, [round(float(v)) for v in c[:5]])), "total": round(float(c[:5].sum()))}))
+names = ["scan:load+apply", "scan:obs+scan+bitmaps", "cand:contours(per 4 bins)", "cand:select/pad(per 4 bins)", "warp0:find-start(per 4 bins)", "warp0:follow(per 4 bins)", "warp0:approx(per 4 bins)"]
+print(json.dumps({"lib": os.environ.get("IRBPP_LIB", "default"), "cycles_per_cta": dict(zip(names, [round(float(v)) for v in c[:7]])), "note": "candidates-kernel counters are summed over N/4 CTAs but divided by N: multiply by 4 for cycles per CTA"}))
