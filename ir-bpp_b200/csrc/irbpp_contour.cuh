@@ -390,4 +390,83 @@ __device__ bool process_level_image_cf_lockstep(S& sc, const uint32_t* bm, bool 
     return ok;
 }
 
+// ---- micro-task formulation -------------------------------------------------------------------------------
+// One step further than the component-first form: the visited bits are not needed either.  A start
+// candidate (background at W, NW, N, NE) is the raster-first pixel of the border it lies on iff following
+// that border never reaches a pixel that precedes it in raster order; such a path is abandoned on the
+// spot.  So every candidate pixel of an image can be processed independently -- one (image, candidate)
+// pair per lane: follow, test the signed area, approximate, emit.  The serial chain of a lane is one
+// contour instead of all contours of an image.
+// Returns the number of stored points (>= 1), -1 if the contour exceeded S::CAP, or -2 if the path
+// was abandoned (not a raster-first start) -- in which case nothing must be emitted.
+template <class S>
+__device__ int follow_outer_from(S& sc, const uint32_t* bm, int x0, int y0, int& area2) {
+    uint32_t rm = row16(bm, y0 - 1) << 1, r0 = row16(bm, y0) << 1, rp = row16(bm, y0 + 1) << 1;
+    uint32_t ring = ring_from_rows(rm, r0, rp, x0);
+    area2 = 0;
+    if (!ring) {  // isolated pixel
+        sc.set_pt(0, (x0 << 4) | y0);
+        return 1;
+    }
+    int s;
+    {   // clockwise search from direction 3 down to 4: highest set bit of the ring rotated by 4
+        const uint32_t r2 = ((ring | (ring << 8)) >> 4) & 0xFFu;
+        s = (4 + (31 - __clz((int)r2))) & 7;
+    }
+    const int x1 = x0 + ddx(s), y1 = y0 + ddy(s);
+    int x3 = x0, y3 = y0;
+    int prev_s = s ^ 4;
+    int n = 0, a2 = 0;
+    bool ovf = false;
+    for (;;) {
+        const int s_end = s;
+        const uint32_t rot = ((ring | (ring << 8)) >> ((s_end + 1) & 7)) & 0xFFu;
+        s = (s_end + __ffs((int)rot)) & 7;
+        const int dy = ddy(s);
+        const int x4 = x3 + ddx(s), y4 = y3 + dy;
+        if (y4 < y0 || (y4 == y0 && x4 < x0)) return -2;      // a pixel of this border precedes the start
+        a2 += x3 * y4 - x4 * y3;
+        if (s != prev_s) {
+            if (n < S::CAP) sc.set_pt(n, (x3 << 4) | y3);
+            else ovf = true;
+            ++n;
+        }
+        prev_s = s;
+        if (x4 == x0 && y4 == y0 && x3 == x1 && y3 == y1) break;
+        if (dy > 0) { rm = r0; r0 = rp; rp = row16(bm, y4 + 1) << 1; }
+        else if (dy < 0) { rp = r0; r0 = rm; rm = row16(bm, y4 - 1) << 1; }
+        x3 = x4; y3 = y4;
+        s = (s + 4) & 7;
+        ring = ring_from_rows(rm, r0, rp, x3);
+    }
+    area2 = a2;
+    return ovf ? -1 : n;
+}
+
+// one micro-task: returns false only when the contour overflowed S::CAP points
+template <class S, class Emit>
+__device__ bool process_start_candidate(S& sc, const uint32_t* bm, int x, int y, bool legacy, Emit emit) {
+    int area2;
+    const int n = follow_outer_from(sc, bm, x, y, area2);
+    if (n == -2 || area2 > 0) return true;       // not a raster-first start, or a hole border
+    if (n < 0) return false;
+    approx_and_emit(sc, n, legacy, emit);
+    return true;
+}
+
+// whole image, serially (overflow path and host validation)
+template <class S, class Emit>
+__device__ bool process_level_image_mt(S& sc, const uint32_t* bm, bool legacy, Emit emit) {
+    bool ok = true;
+    for (int y = 0; y < 16; ++y) {
+        uint32_t c = start_candidates(bm, y, 0u);
+        while (c) {
+            const int x = __ffs((int)c) - 1;
+            c &= c - 1;
+            ok &= process_start_candidate(sc, bm, x, y, legacy, emit);
+        }
+    }
+    return ok;
+}
+
 }  // namespace irbpp

@@ -602,19 +602,19 @@ __global__ void __launch_bounds__(CTA_THREADS) irbpp_levels_kernel(const Params 
 // what its heaviest lane costs (the floor-level image of each rotation is an order of magnitude
 // heavier than the small plateaus above it).
 struct WarpScratch {
-    uint32_t marks[16 * 32];                  // per-lane visited bits, element stride 32   } reused as the overflow
-    uint8_t pts[FAST_CAP * 32];               // per-lane contour points, element stride 32 } buffers and the row list
+    uint8_t pts[FAST_CAP * 32];               // per-lane contour points, element stride 32 (also the overflow buffers)
+    uint8_t spare[4096 - FAST_CAP * 32];      // together: the row list of phase D
 };
-static_assert(sizeof(WarpScratch) >= 16 * 4 + 2 * BIG_CAP, "overflow buffers must fit the lane scratch");
+static_assert(sizeof(WarpScratch) >= 2 * BIG_CAP, "overflow buffers must fit the lane scratch");
 
 struct CandSmem {
-    uint32_t slots[CAND_THREADS * SLOT_WORDS];            // level image of task t (CTA-wide task index)
+    uint32_t slots[CAND_THREADS * SLOT_WORDS];            // level images of this round (one per thread)
     WarpScratch ws[ENVS_PER_CTA];
     uint32_t candbits[ENVS_PER_CTA * MAX_ROT * 8];        // 256-bit candidate set per (bin, rotation)
     int32_t pre[ENVS_PER_CTA * MAX_ROT + 1];              // prefix of level counts over (bin, rotation)
-    uint16_t order[CAND_THREADS];                         // task index by decreasing cost
-    uint16_t pair_of[CAND_THREADS];                       // (bin, rotation) pair of task t
-    int32_t hist[64], base[64];
+    int32_t cand_off[CAND_THREADS + 1];                   // prefix of start-candidate counts over the images
+    uint16_t pair_of[CAND_THREADS];                       // (bin, rotation) pair of image t
+    int32_t warp_tot[ENVS_PER_CTA];
     int32_t error[ENVS_PER_CTA];
 };
 
@@ -653,16 +653,14 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
         if (lane == 0) S.pre[0] = 0;
     }
     __syncthreads();
-    const int ntask = S.pre[npairs];
-    int dev_err = 0;
+    const int nimg = S.pre[npairs];
+    WarpScratch& W = S.ws[warp];
 
-    // ---- phase C ----
-    for (int base = 0; base < ntask; base += ROUND_TASKS) {
-        const int nround = min(ROUND_TASKS, ntask - base);
-        // 1. load this thread's task image, compute its cost key, histogram
-        if (tid < 64) S.hist[tid] = 0;
-        __syncthreads();
-        int my_bucket = 0, my_off = 0;
+    // ---- phase C: rounds of CAND_THREADS level images; inside a round one (image, start pixel) per lane ----
+    for (int base = 0; base < nimg; base += CAND_THREADS) {
+        const int nround = min(CAND_THREADS, nimg - base);
+        // 1. thread t loads image t and counts its start candidates (background at W, NW, N, NE)
+        int cnt = 0;
         if (tid < nround) {
             const int t = base + tid;
             int lo = 0, hi = npairs;                        // pre[lo] <= t < pre[hi]
@@ -673,77 +671,75 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
             uint32_t* bm = S.slots + tid * SLOT_WORDS;
             bm[0] = a.x; bm[1] = a.y; bm[2] = a.z; bm[3] = a.w; bm[4] = b.x; bm[5] = b.y; bm[6] = b.z; bm[7] = b.w;
             S.pair_of[tid] = (uint16_t)lo;
-            // cost key: horizontal + vertical foreground/background transitions (~ border length)
             const uint32_t wv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-            int key = 0;
-            uint32_t prev_row = 0;
+            uint32_t up = 0;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const uint32_t r0 = wv[k] & 0xFFFFu, r1 = wv[k] >> 16;
-                key += __popc(r0 ^ (r0 << 1)) + __popc(r1 ^ (r1 << 1)) + __popc(r0 ^ prev_row) + __popc(r1 ^ r0);
-                prev_row = r1;
+                cnt += __popc(r0 & ~(r0 << 1) & ~(up | (up << 1) | (up >> 1)) & 0xFFFFu);
+                cnt += __popc(r1 & ~(r1 << 1) & ~(r0 | (r0 << 1) | (r0 >> 1)) & 0xFFFFu);
+                up = r1;
             }
-            key += __popc(prev_row);
-            my_bucket = 63 - min(63, key >> 2);             // bucket 0 = heaviest
-            my_off = atomicAdd(&S.hist[my_bucket], 1);
         }
-        __syncthreads();
-        if (warp == 0) {   // exclusive prefix over the 64 buckets
-            const int h0 = S.hist[lane], h1 = S.hist[32 + lane];
-            int i0 = h0, i1 = h1;
+        {   // CTA-wide exclusive prefix of cnt -> cand_off
+            int incl = cnt;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t0 = __shfl_up_sync(0xffffffffu, i0, o), t1 = __shfl_up_sync(0xffffffffu, i1, o);
-                if (lane >= o) { i0 += t0; i1 += t1; }
-            }
-            const int tot0 = __shfl_sync(0xffffffffu, i0, 31);
-            S.base[lane] = i0 - h0;
-            S.base[32 + lane] = tot0 + i1 - h1;
+            for (int o = 1; o < 32; o <<= 1) { const int tt = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += tt; }
+            if (lane == 31) S.warp_tot[warp] = incl;
+            __syncthreads();
+            int wbase = 0;
+            for (int w2 = 0; w2 < warp; ++w2) wbase += S.warp_tot[w2];
+            S.cand_off[tid + 1] = wbase + incl;
+            if (tid == 0) S.cand_off[0] = 0;
         }
         __syncthreads();
-        if (tid < nround) S.order[S.base[my_bucket] + my_off] = (uint16_t)tid;
-        __syncthreads();
+        const int ntask = S.cand_off[CAND_THREADS];
 
-        // 2. the first TASK_LANES lanes of every warp take tasks, heaviest first: fewer lanes per lock-step
-        //    group means less divergence inflation on the serial chain, and all warps of the CTA get work
-        const int ti = warp * TASK_LANES + lane;
-        const bool has = (lane < TASK_LANES) && (ti < nround);
-        const int slot = has ? S.order[ti] : 0;
-        const int q = has ? S.pair_of[slot] : 0;
-        const uint32_t* bm = S.slots + slot * SLOT_WORDS;
-        WarpScratch& W = S.ws[warp];
-        StridedScratch<32, FAST_CAP> sc;
-        sc.w = W.marks + lane;
-        sc.b = W.pts + lane;
-        sc.kept = 0;
-        uint32_t* cb = S.candbits + q * 8;
-        long long tm[3] = {0, 0, 0};
-        const bool okc = process_level_image_cf_lockstep(
-            sc, bm, has, P.legacy != 0,
-            [&](int x, int y) { const int b = x * 16 + y; atomicOr(cb + (b >> 5), 1u << (b & 31)); },
-            P.phase_cycles ? tm : nullptr);
-        __syncwarp();
-        if (P.phase_cycles && lane == 0 && warp == 0) {     // heaviest warp of the CTA: where its cycles go
-            atomicAdd(P.phase_cycles + 4, (unsigned long long)tm[0]);
-            atomicAdd(P.phase_cycles + 5, (unsigned long long)tm[1]);
-            atomicAdd(P.phase_cycles + 6, (unsigned long long)tm[2]);
-        }
-        // rare: a contour longer than FAST_CAP points; the lanes concerned redo their image one at a time
-        // with 1024-point buffers laid over the (now idle) lane scratch of this warp
-        uint32_t ovf = __ballot_sync(0xffffffffu, !okc);
-        while (ovf) {
-            const int src_lane = __ffs((int)ovf) - 1;
-            ovf &= ovf - 1;
-            if (lane == src_lane) {
-                FlatScratch<BIG_CAP> bs;
-                bs.w = W.marks;
-                bs.b = reinterpret_cast<uint8_t*>(W.marks + 16);
-                const bool ok2 = process_level_image_cf(
-                    bs, bm, P.legacy != 0,
-                    [&](int x, int y) { const int b = x * 16 + y; atomicOr(cb + (b >> 5), 1u << (b & 31)); });
-                if (!ok2) atomicMax(&S.error[q / R], 6);
+        // 2. one (image, start pixel) micro-task per lane
+        for (int mb = 0; mb < ntask; mb += CAND_THREADS) {
+            const int m = mb + tid;
+            const bool has = m < ntask;
+            int slot = 0, x = 0, y = 0;
+            if (has) {
+                int lo = 0, hi = CAND_THREADS;              // cand_off[lo] <= m < cand_off[hi]
+                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (S.cand_off[mid] <= m) lo = mid; else hi = mid; }
+                slot = lo;
+                int k = m - S.cand_off[lo];
+                const uint32_t* bmi = S.slots + slot * SLOT_WORDS;
+                for (y = 0; y < 16; ++y) {
+                    const uint32_t c = start_candidates(bmi, y, 0u);
+                    const int pc = __popc(c);
+                    if (k < pc) { x = (int)__fns(c, 0u, k + 1); break; }
+                    k -= pc;
+                }
+            }
+            const uint32_t* bm = S.slots + slot * SLOT_WORDS;
+            const int q = S.pair_of[slot];
+            uint32_t* cb = S.candbits + q * 8;
+            auto emit = [&](int ex, int ey) { const int b = ex * 16 + ey; atomicOr(cb + (b >> 5), 1u << (b & 31)); };
+            bool okc = true;
+            if (has) {
+                StridedScratch<32, FAST_CAP> sc;
+                sc.w = nullptr;
+                sc.b = W.pts + lane;
+                sc.kept = 0;
+                okc = process_start_candidate(sc, bm, x, y, P.legacy != 0, emit);
             }
             __syncwarp();
+            // rare: a contour longer than FAST_CAP points; the lanes concerned redo it one at a time with
+            // 1024-point buffers laid over the (now idle) lane scratch of this warp
+            uint32_t ovf = __ballot_sync(0xffffffffu, !okc);
+            while (ovf) {
+                const int src_lane = __ffs((int)ovf) - 1;
+                ovf &= ovf - 1;
+                if (lane == src_lane) {
+                    FlatScratch<BIG_CAP> bs;
+                    bs.w = nullptr;
+                    bs.b = W.pts;
+                    if (!process_start_candidate(bs, bm, x, y, P.legacy != 0, emit)) atomicMax(&S.error[q / R], 6);
+                }
+                __syncwarp();
+            }
         }
         __syncthreads();
     }
@@ -754,7 +750,7 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
     if (warp >= nenv) return;
     const int env = env0 + warp;
     if (!env_live(env)) return;
-    dev_err = S.error[warp];
+    const int dev_err = S.error[warp];
     WarpScratch& WS = S.ws[warp];
     // ---- phase D ----
     const int sel = P.sel;

@@ -33,7 +33,17 @@ extern "C" int hull_bits(const uint16_t* rows, int legacy, int use_big, uint32_t
         irbpp::StridedScratch<1, 32> sc; sc.w = w; sc.b = b; sc.kept = 0;
         return irbpp::process_level_image_cf_lockstep(sc, bm, true, legacy != 0, emit) ? 0 : 1;
     }
-    return -1;   // modes 3 (serial, long buffers) and 4 (lock-step routine, one lane) only
+    if (use_big == 5) {   // micro-task formulation (no visited bits), long buffers
+        static uint32_t w[16]; static uint8_t b[2 * 1024];
+        irbpp::FlatScratch<1024> sc; sc.w = w; sc.b = b;
+        return irbpp::process_level_image_mt(sc, bm, legacy != 0, emit) ? 0 : 1;
+    }
+    if (use_big == 6) {   // micro-task formulation, 64-point fast buffers
+        static uint32_t w[16]; static uint8_t b[64];
+        irbpp::StridedScratch<1, 64> sc; sc.w = w; sc.b = b; sc.kept = 0;
+        return irbpp::process_level_image_mt(sc, bm, legacy != 0, emit) ? 0 : 1;
+    }
+    return -1;   // modes 3-6 only
 }
 
 extern "C" void floor_div_many(const double* a, double b, int n, double* out) {
