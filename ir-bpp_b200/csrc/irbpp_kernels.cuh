@@ -48,7 +48,12 @@ constexpr int CTA_WARPS = CTA_THREADS / 32;
 #define IRBPP_ENVS_PER_CTA 4
 #endif
 constexpr int ENVS_PER_CTA = IRBPP_ENVS_PER_CTA;   // bins (= warps) per CTA of the candidates kernel
-constexpr int CAND_THREADS = 32 * ENVS_PER_CTA;
+#ifndef IRBPP_CAND_WARPS
+#define IRBPP_CAND_WARPS ENVS_PER_CTA
+#endif
+constexpr int CAND_WARPS = IRBPP_CAND_WARPS;          // warps per CTA of the candidates kernel (>= ENVS_PER_CTA)
+constexpr int CAND_THREADS = 32 * CAND_WARPS;
+static_assert(CAND_WARPS >= ENVS_PER_CTA, "phase D needs one warp per bin");
 #ifndef IRBPP_TASK_LANES
 #define IRBPP_TASK_LANES 32
 #endif
@@ -609,12 +614,14 @@ static_assert(sizeof(WarpScratch) >= 2 * BIG_CAP, "overflow buffers must fit the
 
 struct CandSmem {
     uint32_t slots[CAND_THREADS * SLOT_WORDS];            // level images of this round (one per thread)
-    WarpScratch ws[ENVS_PER_CTA];
+    WarpScratch ws[CAND_WARPS];
     uint32_t candbits[ENVS_PER_CTA * MAX_ROT * 8];        // 256-bit candidate set per (bin, rotation)
     int32_t pre[ENVS_PER_CTA * MAX_ROT + 1];              // prefix of level counts over (bin, rotation)
-    int32_t cand_off[CAND_THREADS + 1];                   // prefix of start-candidate counts over the images
+    int32_t cand_off[CAND_THREADS + 1];                   // prefix of start-candidate counts over the images, in cost order
+    uint16_t slot_of[CAND_THREADS];                       // image slot at each position of the cost order
+    int32_t hist[64], hbase[64];
     uint16_t pair_of[CAND_THREADS];                       // (bin, rotation) pair of image t
-    int32_t warp_tot[ENVS_PER_CTA];
+    int32_t warp_tot[CAND_WARPS];
     int32_t error[ENVS_PER_CTA];
 };
 
@@ -659,8 +666,11 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
     // ---- phase C: rounds of CAND_THREADS level images; inside a round one (image, start pixel) per lane ----
     for (int base = 0; base < nimg; base += CAND_THREADS) {
         const int nround = min(CAND_THREADS, nimg - base);
-        // 1. thread t loads image t and counts its start candidates (background at W, NW, N, NE)
-        int cnt = 0;
+        // 1. thread t loads image t, counts its start candidates (background at W, NW, N, NE) and a cost key
+        //    (foreground/background transitions ~ border length)
+        int cnt = 0, bucket = 63, my_off = 0;
+        if (tid < 64) S.hist[tid] = 0;
+        __syncthreads();
         if (tid < nround) {
             const int t = base + tid;
             int lo = 0, hi = npairs;                        // pre[lo] <= t < pre[hi]
@@ -673,16 +683,43 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
             S.pair_of[tid] = (uint16_t)lo;
             const uint32_t wv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
             uint32_t up = 0;
+            int key = 0;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const uint32_t r0 = wv[k] & 0xFFFFu, r1 = wv[k] >> 16;
                 cnt += __popc(r0 & ~(r0 << 1) & ~(up | (up << 1) | (up >> 1)) & 0xFFFFu);
                 cnt += __popc(r1 & ~(r1 << 1) & ~(r0 | (r0 << 1) | (r0 >> 1)) & 0xFFFFu);
+                key += __popc(r0 ^ (r0 << 1)) + __popc(r1 ^ (r1 << 1)) + __popc(r0 ^ up) + __popc(r1 ^ r0);
                 up = r1;
             }
+            bucket = 63 - min(63, key >> 2);                // bucket 0 = longest borders
+            my_off = atomicAdd(&S.hist[bucket], 1);
         }
-        {   // CTA-wide exclusive prefix of cnt -> cand_off
-            int incl = cnt;
+        __syncthreads();
+        if (warp == 0) {   // exclusive prefix over the 64 buckets
+            const int h0 = S.hist[lane], h1 = S.hist[32 + lane];
+            int i0 = h0, i1 = h1;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t0 = __shfl_up_sync(0xffffffffu, i0, o), t1 = __shfl_up_sync(0xffffffffu, i1, o);
+                if (lane >= o) { i0 += t0; i1 += t1; }
+            }
+            const int tot0 = __shfl_sync(0xffffffffu, i0, 31);
+            S.hbase[lane] = i0 - h0;
+            S.hbase[32 + lane] = tot0 + i1 - h1;
+        }
+        __syncthreads();
+        // position in cost order -> (slot, count); cand_off[] temporarily holds the counts
+        if (tid < nround) {
+            const int pos = S.hbase[bucket] + my_off;
+            S.slot_of[pos] = (uint16_t)tid;
+            S.cand_off[pos + 1] = cnt;
+        } 
+        for (int i = nround + tid; i < CAND_THREADS; i += CAND_THREADS) S.cand_off[i + 1] = 0;
+        __syncthreads();
+        {   // CTA-wide inclusive prefix of the counts in cost order
+            const int c = S.cand_off[tid + 1];
+            int incl = c;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const int tt = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += tt; }
             if (lane == 31) S.warp_tot[warp] = incl;
@@ -703,7 +740,7 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
             if (has) {
                 int lo = 0, hi = CAND_THREADS;              // cand_off[lo] <= m < cand_off[hi]
                 while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (S.cand_off[mid] <= m) lo = mid; else hi = mid; }
-                slot = lo;
+                slot = S.slot_of[lo];
                 int k = m - S.cand_off[lo];
                 const uint32_t* bmi = S.slots + slot * SLOT_WORDS;
                 for (y = 0; y < 16; ++y) {
@@ -718,12 +755,20 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
             uint32_t* cb = S.candbits + q * 8;
             auto emit = [&](int ex, int ey) { const int b = ex * 16 + ey; atomicOr(cb + (b >> 5), 1u << (b & 31)); };
             bool okc = true;
-            if (has) {
+            {
+                // follow and approximate as two warp-converged phases: lanes that finish following early
+                // wait, so that the approximation loops run with all lanes in the same code
                 StridedScratch<32, FAST_CAP> sc;
                 sc.w = nullptr;
                 sc.b = W.pts + lane;
                 sc.kept = 0;
-                okc = process_start_candidate(sc, bm, x, y, P.legacy != 0, emit);
+                int area2 = 1, n = -2;
+                if (has) n = follow_outer_from(sc, bm, x, y, area2);
+                __syncwarp();
+                if (has && n != -2 && area2 <= 0) {        // a raster-first start of an outer border
+                    if (n < 0) okc = false;
+                    else approx_and_emit(sc, n, P.legacy != 0, emit);
+                }
             }
             __syncwarp();
             // rare: a contour longer than FAST_CAP points; the lanes concerned redo it one at a time with
