@@ -27,6 +27,7 @@ struct irbpp_env {
     int cand_smem = 0, scan_smem = 0;
     std::string err;
     bool shapes_loaded = false, sequences_set = false, was_reset = false, waiting_step = false;
+    bool results_on_host = false;           // the pending step wrote its results straight to the host mirror
     cudaStream_t pending_stream = nullptr;
     int64_t launches = 0;
     // device allocations
@@ -35,7 +36,9 @@ struct irbpp_env {
     void* results_host = nullptr;  // pinned mirror
     size_t results_bytes = 0;
     int64_t* actions_dev = nullptr;
-    int64_t* actions_pinned = nullptr;
+    int64_t* actions_pinned = nullptr;      // [2][N] mapped pinned: step actions, order actions (read zero-copy)
+    int64_t* actions_mapped = nullptr;      // device view of actions_pinned
+    char* results_mapped = nullptr;         // device view of results_host
     uint8_t* which_dev = nullptr;
     // shape pools
     ShapeRot* srot_dev = nullptr; double* Bs_dev = nullptr; double* Ts_dev = nullptr;
@@ -146,9 +149,11 @@ int irbpp_create(const irbpp_config* cfg, irbpp_handle* out) {
     h->results_bytes = (size_t)N * (8 + 8 + 4 + 4 + 4 + 1 + 1 + 1);
     TRY_ALLOC(cudaMalloc(&h->results_dev, h->results_bytes + 64));
     TRY_ALLOC(cudaMemset(h->results_dev, 0, h->results_bytes + 64));
-    TRY_ALLOC(cudaMallocHost(&h->results_host, h->results_bytes + 64));
+    TRY_ALLOC(cudaHostAlloc(&h->results_host, h->results_bytes + 64, cudaHostAllocMapped));
+    TRY_ALLOC(cudaHostGetDevicePointer((void**)&h->results_mapped, h->results_host, 0));
     memset(h->results_host, 0, h->results_bytes + 64);
-    TRY_ALLOC(cudaMallocHost((void**)&h->actions_pinned, (size_t)N * sizeof(int64_t)));
+    TRY_ALLOC(cudaHostAlloc((void**)&h->actions_pinned, 2 * (size_t)N * sizeof(int64_t), cudaHostAllocMapped));
+    TRY_ALLOC(cudaHostGetDevicePointer((void**)&h->actions_mapped, h->actions_pinned, 0));
     {
         char* b = reinterpret_cast<char*>(h->results_dev);
         P.r_ratio = reinterpret_cast<double*>(b); b += (size_t)N * 8;
@@ -377,10 +382,22 @@ int irbpp_step_async(irbpp_handle h, const int64_t* actions, int32_t on_device, 
     P.mode = MODE_STEP; P.obs = obs_out;
     if (on_device) P.actions = actions;
     else {
+        // host actions: staged in mapped pinned memory and read by the kernel over PCIe (one 8-byte read per
+        // bin) -- no separate copy node in front of the kernel; results go back the same way (posted stores)
         memcpy(h->actions_pinned, actions, (size_t)P.N * sizeof(int64_t));
-        CUDA_TRY(h, cudaMemcpyAsync(h->actions_dev, h->actions_pinned, (size_t)P.N * sizeof(int64_t), cudaMemcpyHostToDevice, s));
-        P.actions = h->actions_dev;
+        P.actions = h->actions_mapped;
+        char* b = h->results_mapped;
+        const size_t N = P.N;
+        P.h_ratio = reinterpret_cast<double*>(b); b += N * 8;
+        P.h_eprew = reinterpret_cast<double*>(b); b += N * 8;
+        P.h_reward = reinterpret_cast<float*>(b); b += N * 4;
+        P.h_counter = reinterpret_cast<int32_t*>(b); b += N * 4;
+        P.h_eplen = reinterpret_cast<int32_t*>(b); b += N * 4;
+        P.h_done = reinterpret_cast<uint8_t*>(b); b += N;
+        P.h_valid = reinterpret_cast<uint8_t*>(b); b += N;
+        P.h_error = reinterpret_cast<uint8_t*>(b);
     }
+    h->results_on_host = !on_device;
     rc = launch(h, P, s); if (rc) return rc;
     h->waiting_step = true; h->pending_stream = s;
     return IRBPP_OK;
@@ -403,7 +420,8 @@ int irbpp_step_wait(irbpp_handle h, irbpp_step_result* out) {
     if (!h->waiting_step) return fail(h, IRBPP_ESTATE, "not running an async step");   // vec_env.py:18-26
     cudaStream_t s = h->pending_stream;
     h->waiting_step = false;
-    if (out) CUDA_TRY(h, cudaMemcpyAsync(h->results_host, h->results_dev, h->results_bytes, cudaMemcpyDeviceToHost, s));
+    if (out && !h->results_on_host)
+        CUDA_TRY(h, cudaMemcpyAsync(h->results_host, h->results_dev, h->results_bytes, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(h, cudaStreamSynchronize(s));
     if (out) {
         host_views(h, reinterpret_cast<char*>(h->results_host), out);
@@ -436,8 +454,9 @@ int irbpp_get_action_candidates(irbpp_handle h, const int64_t* order_actions, in
     P.mode = MODE_CANDIDATES; P.obs = loc_obs_out; P.obs_stride = P.loc_len;
     if (on_device) P.actions = order_actions;
     else {
-        memcpy(h->actions_pinned, order_actions, (size_t)P.N * sizeof(int64_t));
-        CUDA_TRY(h, cudaMemcpyAsync(h->actions_dev, h->actions_pinned, (size_t)P.N * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+        // staged copy (not zero-copy): the caller may enqueue the following step before this kernel ran
+        memcpy(h->actions_pinned + P.N, order_actions, (size_t)P.N * sizeof(int64_t));
+        CUDA_TRY(h, cudaMemcpyAsync(h->actions_dev, h->actions_pinned + P.N, (size_t)P.N * sizeof(int64_t), cudaMemcpyHostToDevice, s));
         P.actions = h->actions_dev;
     }
     return launch(h, P, s);

@@ -152,6 +152,9 @@ struct Params {
     float* r_reward; uint8_t* r_done; uint8_t* r_valid; uint8_t* r_error;
     int32_t* r_counter; int32_t* r_eplen; double* r_ratio; double* r_eprew;
     double* dbg_cand; int32_t* dbg_nhull;
+    // host-mapped mirror of the result arrays (zero-copy stores; NULL on the device-resident path)
+    float* h_reward; uint8_t* h_done; uint8_t* h_valid; uint8_t* h_error;
+    int32_t* h_counter; int32_t* h_eplen; double* h_ratio; double* h_eprew;
     unsigned long long* phase_cycles;    // [8] summed SM cycles per phase (thread 0 of every CTA), or NULL
     int32_t mode;
 };
@@ -457,6 +460,10 @@ __global__ void __launch_bounds__(CTA_THREADS, IRBPP_SCAN_MIN_CTAS) irbpp_scan_k
                 const double rew = P.reward_tab[item];
                 P.r_reward[env] = (float)rew; P.r_done[env] = 0; P.r_valid[env] = 1;
                 P.r_counter[env] = -1; P.r_eplen[env] = 0; P.r_ratio[env] = -1.0; P.r_eprew[env] = 0.0;
+                if (P.h_reward) {
+                    P.h_reward[env] = (float)rew; P.h_done[env] = 0; P.h_valid[env] = 1;
+                    P.h_counter[env] = -1; P.h_eplen[env] = 0; P.h_ratio[env] = -1.0; P.h_eprew[env] = 0.0;
+                }
                 st_s.packed += 1; st_s.ep_len += 1;
                 st_s.vol_sum += P.vol[item];
                 st_s.ep_rew += rew;
@@ -470,6 +477,11 @@ __global__ void __launch_bounds__(CTA_THREADS, IRBPP_SCAN_MIN_CTAS) irbpp_scan_k
                 P.r_ratio[env] = st_s.vol_sum / P.binvol;
                 P.r_eplen[env] = st_s.ep_len + 1;
                 P.r_eprew[env] = st_s.ep_rew + 0.0;
+                if (P.h_reward) {
+                    P.h_reward[env] = 0.0f; P.h_done[env] = 1; P.h_valid[env] = 1;
+                    P.h_counter[env] = st_s.packed; P.h_ratio[env] = st_s.vol_sum / P.binvol;
+                    P.h_eplen[env] = st_s.ep_len + 1; P.h_eprew[env] = st_s.ep_rew + 0.0;
+                }
                 st_s.packed = 0; st_s.ep_len = 0; st_s.vol_sum = 0.0; st_s.ep_rew = 0.0;
                 st_s.order_act = 0;
                 for (int q = 0; q < nfill; ++q) queue_g[q] = draw_item(P, env, cursor);   // reset(): clear + preview
@@ -516,7 +528,7 @@ __global__ void __launch_bounds__(CTA_THREADS, IRBPP_SCAN_MIN_CTAS) irbpp_scan_k
     if (!emit_loc) {
         // order observation: [next k item ids | heightmap]  (binPhy.py:229-230)
         for (int i = tid; i < P.K; i += CTA_THREADS) obs_g[i] = (float)queue_g[i];
-        if (tid == 0) P.r_error[env] = (uint8_t)err_sh;
+        if (tid == 0) { P.r_error[env] = (uint8_t)err_sh; if (P.h_error) P.h_error[env] = (uint8_t)err_sh; }
         if (st_dirty && warp == 0) reinterpret_cast<uint32_t*>(P.state + env)[lane] = reinterpret_cast<const uint32_t*>(&st_s)[lane];
         return;
     }
@@ -555,6 +567,7 @@ __global__ void __launch_bounds__(CTA_THREADS, IRBPP_SCAN_MIN_CTAS) irbpp_scan_k
     __syncthreads();
     if (tid == 0) {
         P.r_error[env] = (uint8_t)err_sh;          // the candidates kernel may overwrite with its own code
+        if (P.h_error) P.h_error[env] = (uint8_t)err_sh;
         const bool write_state = (mode == MODE_STEP || mode == MODE_RESET || mode == MODE_CANDIDATES ||
                                   (mode == MODE_ALL_OBS && P.slot == P.K - 1));
         if (write_state) { st_s.cur_item = item; st_s.mask_any = any_sh; }
@@ -927,7 +940,7 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
         if (Ktot < sel) zero_rows(Ktot);
     }
     if (lane == 0) {
-        if (dev_err) P.r_error[env] = (uint8_t)dev_err;
+        if (dev_err) { P.r_error[env] = (uint8_t)dev_err; if (P.h_error) P.h_error[env] = (uint8_t)dev_err; }
         if (P.dbg_nhull) P.dbg_nhull[env] = Ktot;
     }
     phase_mark(3);   // select / pad, candidate rows of the observation

@@ -211,6 +211,9 @@ class GpuVecEnv(VecEnv):
     def _actions_arg(self, actions, what):
         """Host array / list (copied through pinned staging) or a CUDA int64 tensor (used in place)."""
         torch = self._torch
+        if type(actions) is np.ndarray and actions.dtype == np.int64 and actions.ndim == 1 \
+                and actions.shape[0] == self.num_envs and actions.flags.c_contiguous:
+            return actions, actions.ctypes.data, 0              # the common case (trainer.py:165), no conversion
         if isinstance(actions, torch.Tensor):
             if actions.is_cuda:
                 a = actions.reshape(-1).to(torch.int64).contiguous()
