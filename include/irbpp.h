@@ -156,8 +156,8 @@ int64_t irbpp_launch_count(irbpp_handle h);
 
 /* Profiling aid: when enabled, thread 0 of every CTA adds the SM cycles it spent in each kernel phase
  * (0 scan kernel: load + apply action, 1 scan kernel: observation heightmap + scan + level bitmaps,
- * 2 candidates kernel: contour tasks, 3 candidates kernel: select / pad; 4-6: warp 0 of every candidates
- * CTA, cycles spent finding border starts / following borders / in approxPolyDP) to 8 counters.  The call
+ * 2 candidates kernel: contour tasks, 3 candidates kernel: select / pad) to counters 0-3; counters 4-7 count
+ * level images, (image, start pixel) micro-tasks, rounds and >64-point overflow redos.  The call
  * returns the counters accumulated so far in out8 (may be NULL), clears them and sets the switch. */
 int irbpp_debug_phase_cycles(irbpp_handle h, int32_t enable, uint64_t* out8);
 

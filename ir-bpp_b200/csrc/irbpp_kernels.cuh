@@ -636,6 +636,7 @@ struct CandSmem {
     uint16_t pair_of[CAND_THREADS];                       // (bin, rotation) pair of image t
     int32_t warp_tot[CAND_WARPS];
     int32_t error[ENVS_PER_CTA];
+    int32_t rank_hist[ENVS_PER_CTA][128];                 // phase D truncation: bucket bases / cursors per warp
 };
 
 __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Params P) {
@@ -744,6 +745,7 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
         }
         __syncthreads();
         const int ntask = S.cand_off[CAND_THREADS];
+        if (P.phase_cycles && tid == 0) { atomicAdd(P.phase_cycles + 4, (unsigned long long)nround); atomicAdd(P.phase_cycles + 5, (unsigned long long)ntask); atomicAdd(P.phase_cycles + 6, 1ull); }
 
         // 2. one (image, start pixel) micro-task per lane
         for (int mb = 0; mb < ntask; mb += CAND_THREADS) {
@@ -791,6 +793,7 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
                 const int src_lane = __ffs((int)ovf) - 1;
                 ovf &= ovf - 1;
                 if (lane == src_lane) {
+                    if (P.phase_cycles) atomicAdd(P.phase_cycles + 7, 1ull);     // overflow redo counter
                     FlatScratch<BIG_CAP> bs;
                     bs.w = nullptr;
                     bs.b = W.pts;
@@ -873,7 +876,7 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
         // Pass 1 compacts the set bits into a list (no memory loads); pass 2 gives every lane one
         // candidate, so the height gathers of 32 candidates are in flight together.
         uint16_t* list = reinterpret_cast<uint16_t*>(&WS);            // lane scratch is idle now
-        constexpr int LIST_CAP = (int)(sizeof(WarpScratch) / 2);
+        constexpr int LIST_CAP = (int)(sizeof(WarpScratch) / 4);      // list + bucket-sorted index list
         auto cell_of = [](int e) { const int b = e & 255; return (e >> 8) * NPOSE + (b & 15) * 16 + (b >> 4); };
         if (Ktot <= LIST_CAP) {
             for (int r = 0; r < R; ++r) {
@@ -888,22 +891,62 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
                 }
             }
             __syncwarp();
-            for (int i = lane; i < Ktot; i += 32) {
-                const int e = list[i];
-                const int r = e >> 8, b = e & 255;
-                bool m; const double H = height_of(cell_of(e), m);
-                int dest = i;
-                if (Ktot > sel) {
-                    // truncate to the `sel` lowest heights, ties by original order (stable argsort;
-                    // binPhy.py:209-212)
-                    int rank = 0;
-                    for (int j = 0; j < Ktot; ++j) {
+            if (Ktot <= sel) {
+                for (int i = lane; i < Ktot; i += 32) {
+                    const int e = list[i];
+                    const int b = e & 255;
+                    bool m; const double H = height_of(cell_of(e), m);
+                    put_row(i, e >> 8, b & 15, b >> 4, H, m ? 1.0 : 0.0);
+                }
+            } else {
+                // More candidates than rows: keep the `sel` lowest heights, ties by original order (stable
+                // argsort; binPhy.py:209-212).  Exact ranks from a monotone bucketing of the heights: a
+                // candidate's rank = (candidates in lower buckets) + (its rank inside its own bucket), so
+                // each candidate is compared only with its bucket instead of with all K.
+                uint16_t* sorted = list + LIST_CAP;                  // second half of the lane scratch
+                int32_t* hist = S.rank_hist[warp];                   // [0,64): counts, [64,128): running offsets
+                auto bucket_of = [&](double H) { const int v = (int)((H + 0.32) * 100.0); return v < 0 ? 0 : (v > 63 ? 63 : v); };
+                hist[lane] = 0; hist[32 + lane] = 0;
+                __syncwarp();
+                for (int i = lane; i < Ktot; i += 32) {
+                    bool m; const double H = height_of(cell_of(list[i]), m);
+                    atomicAdd(&hist[bucket_of(H)], 1);
+                }
+                __syncwarp();
+                {   // exclusive prefix over the 64 buckets
+                    const int h0 = hist[lane], h1 = hist[32 + lane];
+                    int i0 = h0, i1 = h1;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int t0 = __shfl_up_sync(0xffffffffu, i0, o), t1 = __shfl_up_sync(0xffffffffu, i1, o);
+                        if (lane >= o) { i0 += t0; i1 += t1; }
+                    }
+                    const int tot0 = __shfl_sync(0xffffffffu, i0, 31);
+                    __syncwarp();
+                    hist[lane] = i0 - h0; hist[32 + lane] = tot0 + i1 - h1;            // bucket bases
+                    hist[64 + lane] = i0 - h0; hist[96 + lane] = tot0 + i1 - h1;      // fill cursors
+                }
+                __syncwarp();
+                for (int i = lane; i < Ktot; i += 32) {
+                    bool m; const double H = height_of(cell_of(list[i]), m);
+                    sorted[atomicAdd(&hist[64 + bucket_of(H)], 1)] = (uint16_t)i;
+                }
+                __syncwarp();
+                for (int i = lane; i < Ktot; i += 32) {
+                    const int e = list[i];
+                    const int b = e & 255;
+                    bool m; const double H = height_of(cell_of(e), m);
+                    const int bk = bucket_of(H);
+                    const int lo = hist[bk], hi = hist[64 + bk];        // this bucket's segment of `sorted`
+                    if (lo >= sel) continue;                             // everything in it ranks beyond the table
+                    int rank = lo;
+                    for (int t = lo; t < hi; ++t) {
+                        const int j = sorted[t];
                         bool m2; const double H2 = height_of(cell_of(list[j]), m2);
                         rank += (H2 < H) || (H2 == H && j < i);
                     }
-                    dest = rank;
+                    if (rank < sel) put_row(rank, e >> 8, b & 15, b >> 4, H, m ? 1.0 : 0.0);
                 }
-                if (dest < sel) put_row(dest, r, b & 15, b >> 4, H, m ? 1.0 : 0.0);
             }
         } else {
             for (int r = 0; r < R; ++r) {
