@@ -201,7 +201,7 @@ int irbpp_load_shapes(irbpp_handle h, int32_t S, int32_t R, const int32_t* dims,
     std::vector<double> Bs, Ts;
     std::vector<TileEntry> tiles;
     std::vector<double> rew(S);
-    int maxwh = 1;
+    int maxwh = 1, max_entries = 1;
     for (int s = 0; s < S; ++s) {
         rew[s] = (vol[s] / h->P.binvol) * 10;                        // binPhy.py:155-156,321-322
         for (int r = 0; r < R; ++r) {
@@ -267,7 +267,7 @@ int irbpp_load_shapes(irbpp_handle h, int32_t S, int32_t R, const int32_t* dims,
                             }
                         if (!any_open) continue;                  // fully masked block contributes nothing
                         if (any_masked || !same || i1 - bi * t != t || j1 - bj * t != t) { ok = false; break; }
-                        TileEntry e; e.du = (int16_t)(bi * t / 2); e.dv = (int16_t)(bj * t / 2); e.pad = 0; e.b = b0;
+                        TileEntry e; e.off = (bi * t / 2) * 16 + (bj * t / 2); e.pad = 0; e.b = b0;
                         found[r].push_back(e);
                     }
             }
@@ -280,6 +280,23 @@ int irbpp_load_shapes(irbpp_handle h, int32_t S, int32_t R, const int32_t* dims,
                 break;
             }
         }
+        if (srot[(size_t)s * R].tile == 1) {
+            // no block structure: one entry per unmasked cell, offset into the column-parity planes
+            for (int r = 0; r < R; ++r) {
+                ShapeRot& q = srot[(size_t)s * R + r];
+                const double* Bq = Bs.data() + q.off;
+                q.tile_off = (int32_t)tiles.size();
+                for (int i = 0; i < q.w; ++i)
+                    for (int j = 0; j < q.h; ++j) {
+                        const double b = Bq[(size_t)i * q.h + j];
+                        if (std::isinf(b)) continue;
+                        TileEntry e; e.off = ((j & 1) * HX + i) * (HY / 2) + (j >> 1); e.pad = 0; e.b = b;
+                        tiles.push_back(e);
+                    }
+                q.ntiles = (int32_t)tiles.size() - q.tile_off;
+            }
+        }
+        for (int r = 0; r < R; ++r) max_entries = std::max(max_entries, (int)srot[(size_t)s * R + r].ntiles);
     }
     cudaSetDevice(c.device);
     CUDA_TRY(h, dev_alloc(h, &h->srot_dev, srot.size(), false));
@@ -297,8 +314,9 @@ int irbpp_load_shapes(irbpp_handle h, int32_t S, int32_t R, const int32_t* dims,
     CUDA_TRY(h, cudaMemcpy(h->rew_dev, rew.data(), (size_t)S * 8, cudaMemcpyHostToDevice));
     h->P.S = S; h->P.srot = h->srot_dev; h->P.Bs = h->Bs_dev; h->P.Ts = h->Ts_dev;
     h->P.vol = h->vol_dev; h->P.reward_tab = h->rew_dev;
-    h->P.maxwh = (maxwh + 1) & ~1;
-    h->scan_smem = CTA_WARPS * h->P.maxwh * (int)sizeof(double);
+    (void)maxwh;
+    h->P.maxwh = max_entries;
+    h->scan_smem = CTA_WARPS * h->P.maxwh * (int)sizeof(TileEntry);
     {   // the attribute is per function, not per handle: only ever raise it (several handles may coexist)
         static int scan_attr = 0;
         if (h->scan_smem > scan_attr) {

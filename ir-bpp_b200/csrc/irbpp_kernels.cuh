@@ -82,7 +82,7 @@ struct ShapeRot {          // one (shape, rotation) entry, device resident
     int32_t nX, nY;        // number of X / Y positions scanned: A - ceil(ext/resA) + 1 (space.py:115-116)
     uint32_t okx, oky;     // bit lx set <=> prejudge passes in x / y for that lx (binPhy.py:240-241)
     int32_t any_zero;      // maskB has a zero cell -> the window max includes a 0 term
-    int32_t tile;          // 4 / 2: the bottom table is constant on tile x tile blocks (see TileEntry); 1: not
+    int32_t tile;          // 4 / 2: the bottom table is constant on tile x tile blocks (see TileEntry); 1: cell list
     double ez;             // round(extent_z, 6)   (space.py:104,120)
     int64_t off;           // offset of Bs / Ts of this entry in the pools (doubles)
     int32_t tile_off;      // first TileEntry of this (shape, rotation)
@@ -94,10 +94,13 @@ struct ShapeRot {          // one (shape, rotation) entry, device resident
 // block maxima M of the heightmap once per bin and then visit one entry per BLOCK instead of one per
 // cell -- bit-identical, 16x fewer window operations for 4x4 blocks.  Detected per shape at load time;
 // tables without that structure use the per-cell loop.
+// One entry of a rotation's scan list: either a block of a block-structured table (offset into the
+// block-maxima array M, indexed like the action grid) or one unmasked cell of an arbitrary table (offset
+// into the column-parity heightmap planes).  Masked cells / blocks have no entry.
 struct TileEntry {
-    int16_t du, dv;        // block origin in units of 2 heightmap cells (= action-grid steps)
+    int32_t off;           // added to the pose's base index: block (du*16 + dv), cell hm_index(i, j)
     int32_t pad;
-    double b;              // bottom height of the block
+    double b;              // bottom height of the block / cell
 };
 
 // Scalar state of one bin, 128 bytes so that one warp loads / stores it with one coalesced access.
@@ -123,7 +126,7 @@ struct Params {
     double binz, resZ, binvol;
     // shapes
     int32_t S;
-    int32_t maxwh;                       // largest w*h of the library (size of a warp's table buffer)
+    int32_t maxwh;                       // largest scan list of the library (entries of a warp's staging buffer)
     const ShapeRot* srot;                // [S*R]
     const double* Bs;                    // bottom tables, +inf where maskB == 0
     const double* Ts;                    // top tables, -inf where maskT == 0
@@ -207,22 +210,22 @@ __device__ __forceinline__ int level_of(const Params& P, double posz, double inv
 // ---- phase B: one warp scans one rotation -------------------------------------------------------------
 // Writes posz[r][256], maskbits[r][8], the level bitmaps and their count (space.py:98-129,
 // cvTools.py:78-85).  Returns true if any pose is feasible.
-// The bottom table is staged in this warp's shared-memory buffer (every lane reads the same element:
-// a broadcast); each lane carries two poses, (X, Y) and (X + 8, Y), so one table element serves two
-// window cells.
-__device__ __forceinline__ bool scan_rotation(const Params& P, const double* hm_s, double* bs, int env, int item,
-                                              int r, int lane, int& err) {
+// `arr` is the array the entry offsets refer to: the block maxima M (pose base = X*16 + Y) for block
+// tables, the heightmap planes (pose base = 2X*16 + Y) for cell lists.  The entry list is staged in this
+// warp's shared-memory buffer (all lanes read the same entry: a broadcast); each lane carries two poses,
+// (X, Y) and (X + 8, Y), so one entry serves two window positions.
+__device__ __forceinline__ bool scan_rotation(const Params& P, const double* arr, int stride_x, TileEntry* es,
+                                              int env, int item, int r, int lane, int& err) {
     const ShapeRot* sr = P.srot + (int64_t)item * P.R + r;
-    const int w = sr->w, h = sr->h, nX = sr->nX, nY = sr->nY;
+    const int nX = sr->nX, nY = sr->nY, nt = sr->ntiles;
     const double ez = sr->ez;
     const double init = sr->any_zero ? 0.0 : -INFINITY;
     {
-        const double* __restrict__ B = P.Bs + sr->off;
+        const TileEntry* __restrict__ te = P.tiles + sr->tile_off;
         __syncwarp();                                   // previous rotation's readers are done
-        for (int c = lane; c < w * h; c += 32) bs[c] = __ldg(B + c);
+        for (int k = lane; k < nt; k += 32) es[k] = te[k];
         __syncwarp();
     }
-    const int hpairs = h >> 1;
     const double inv = 1.0 / P.resZ;
     double* posz_g = P.posz + ((int64_t)env * P.R + r) * NPOSE;
     uint32_t* mask_g = P.maskbits + ((int64_t)env * P.R + r) * 8;
@@ -239,32 +242,14 @@ __device__ __forceinline__ bool scan_rotation(const Params& P, const double* hm_
         bool feasA = false, feasB = false;
         if (validA) {
             accA = init; accB = init;
-            const double* a0 = hm_s + (STEP * X) * (HY / 2) + Y;                   // even heightmap columns
-            const double* b0 = validB ? a0 + STEP * 8 * (HY / 2) : a0;             // pose (X + 8, Y)
-            const double* brow = bs;
-#pragma unroll 1
-            for (int i = 0; i < w; ++i) {
-                const double* a1 = a0 + HX * (HY / 2);                              // odd heightmap columns
-                const double* b1 = b0 + HX * (HY / 2);
-                int jj = 0;
-#pragma unroll 2
-                for (; jj < hpairs; ++jj) {
-                    const double t0 = brow[2 * jj], t1 = brow[2 * jj + 1];
-                    const double u0 = a0[jj] - t0, u1 = a1[jj] - t1;
-                    const double v0 = b0[jj] - t0, v1 = b1[jj] - t1;
-                    accA = (u0 > accA) ? u0 : accA;
-                    accB = (v0 > accB) ? v0 : accB;
-                    accA = (u1 > accA) ? u1 : accA;
-                    accB = (v1 > accB) ? v1 : accB;
-                }
-                if (h & 1) {
-                    const double t0 = brow[2 * jj];
-                    const double u0 = a0[jj] - t0, v0 = b0[jj] - t0;
-                    accA = (u0 > accA) ? u0 : accA;
-                    accB = (v0 > accB) ? v0 : accB;
-                }
-                a0 += HY / 2; b0 += HY / 2;
-                brow += h;
+            const double* a0 = arr + X * stride_x + Y;
+            const double* b0 = validB ? a0 + 8 * stride_x : a0;                  // pose (X + 8, Y)
+#pragma unroll 4
+            for (int k = 0; k < nt; ++k) {
+                const TileEntry e = es[k];
+                const double u = a0[e.off] - e.b, v = b0[e.off] - e.b;
+                accA = (u > accA) ? u : accA;
+                accB = (v > accB) ? v : accB;
             }
             feasA = round6_le0(accA + ez - P.binz);
             if (validB) feasB = round6_le0(accB + ez - P.binz); else accB = POSZ_INVALID;
@@ -286,69 +271,15 @@ __device__ __forceinline__ bool scan_rotation(const Params& P, const double* hm_
     return any != 0;
 }
 
-// ---- phase B, block form: one warp scans one rotation from the block maxima ------------------------------
-// M_s[u*16 + v] = max of the heightmap over cells [2u, 2u+tile) x [2v, 2v+tile).
-__device__ __forceinline__ bool scan_rotation_tiles(const Params& P, const double* M_s, double* bs, int env,
-                                                    int item, int r, int lane, int& err) {
-    const ShapeRot* sr = P.srot + (int64_t)item * P.R + r;
-    const int nX = sr->nX, nY = sr->nY, nt = sr->ntiles;
-    const double ez = sr->ez;
-    const double init = sr->any_zero ? 0.0 : -INFINITY;
-    {   // stage the block list: bs[2k] = b, bs[2k+1] = offset into M_s (as a double-sized slot holding an int)
-        const TileEntry* __restrict__ te = P.tiles + sr->tile_off;
-        __syncwarp();
-        for (int k = lane; k < nt; k += 32) {
-            const TileEntry e = te[k];
-            bs[2 * k] = e.b;
-            reinterpret_cast<int*>(bs + 2 * k + 1)[0] = e.du * 16 + e.dv;
-        }
-        __syncwarp();
-    }
-    const double inv = 1.0 / P.resZ;
-    double* posz_g = P.posz + ((int64_t)env * P.R + r) * NPOSE;
-    uint32_t* mask_g = P.maskbits + ((int64_t)env * P.R + r) * 8;
-    int lv[8];
-    uint32_t pres_lo = 0, pres_hi = 0, any = 0;
-#pragma unroll
-    for (int pass = 0; pass < 8; ++pass) {
-        const int p = pass * 32 + lane;
-        const int X = p >> 4, Y = p & 15;
-        const bool valid = (X < nX) && (Y < nY);
-        double acc = POSZ_INVALID;
-        bool feas = false;
-        if (valid) {
-            acc = init;
-            const double* m0 = M_s + p;
-#pragma unroll 4
-            for (int k = 0; k < nt; ++k) {
-                const double v = m0[reinterpret_cast<const int*>(bs + 2 * k + 1)[0]] - bs[2 * k];
-                acc = (v > acc) ? v : acc;
-            }
-            feas = round6_le0(acc + ez - P.binz);
-        }
-        posz_g[p] = acc;
-        const uint32_t mb = __ballot_sync(0xffffffffu, feas);
-        if (lane == 0) mask_g[pass] = mb;
-        any |= mb;
-        lv[pass] = feas ? level_of(P, acc, inv, pres_lo, pres_hi, err) : -1;
-    }
-    pres_lo = __reduce_or_sync(0xffffffffu, pres_lo);
-    pres_hi = __reduce_or_sync(0xffffffffu, pres_hi);
-    const int nl = emit_level_bitmaps(P.bitmaps + ((int64_t)env * P.R + r) * MAX_LEVELS * 8, lane, lv,
-                                      ((uint64_t)pres_hi << 32) | pres_lo);
-    if (lane == 0) P.nlevels[(int64_t)env * P.R + r] = nl;
-    return any != 0;
-}
-
 // ---- scan kernel ------------------------------------------------------------------------------------------
 #ifndef IRBPP_SCAN_MIN_CTAS
 #define IRBPP_SCAN_MIN_CTAS 8
 #endif
 __global__ void __launch_bounds__(CTA_THREADS, IRBPP_SCAN_MIN_CTAS) irbpp_scan_kernel(const Params P) {
     __shared__ __align__(16) double hm_s[HX * HY];
-    extern __shared__ __align__(16) double bstage[];     // CTA_WARPS x P.maxwh: bottom table of each warp's rotation
+    extern __shared__ __align__(16) TileEntry estage[];  // CTA_WARPS x P.maxwh: scan list of each warp's rotation
     __shared__ __align__(16) EnvState st_s;              // this bin's scalar state (loaded / stored by warp 0)
-    __shared__ double M_s[NPOSE + 16 * 16];              // block maxima of the heightmap (block form of phase B)
+    __shared__ double M_s[NPOSE];                        // block maxima of the heightmap (block form of phase B)
     __shared__ double z_sh;
     __shared__ int ok_sh, rot_sh, lx_sh, ly_sh, item_sh, err_sh, any_sh;
     const int env = P.env_lo + blockIdx.x;
@@ -553,13 +484,12 @@ __global__ void __launch_bounds__(CTA_THREADS, IRBPP_SCAN_MIN_CTAS) irbpp_scan_k
                 }
                 M_s[e] = m;
             }
-            for (int e = NPOSE + tid; e < NPOSE + 16 * 16; e += CTA_THREADS) M_s[e] = -INFINITY;   // (reads of unused lanes)
             __syncthreads();
             for (int r = warp; r < P.R; r += CTA_WARPS)
-                any |= scan_rotation_tiles(P, M_s, bstage + warp * P.maxwh, env, item, r, lane, err);
+                any |= scan_rotation(P, M_s, 16, estage + warp * P.maxwh, env, item, r, lane, err);
         } else {
             for (int r = warp; r < P.R; r += CTA_WARPS)
-                any |= scan_rotation(P, hm_s, bstage + warp * P.maxwh, env, item, r, lane, err);
+                any |= scan_rotation(P, hm_s, STEP * (HY / 2), estage + warp * P.maxwh, env, item, r, lane, err);
         }
         if (lane == 0 && any) any_sh = 1;
         if (__any_sync(0xffffffffu, err) && lane == 0) err_sh = 4;
