@@ -405,3 +405,27 @@ def test_two_handles_with_different_libraries_coexist():
         assert np.array_equal(a.step(acts)[0].cpu().numpy(), oa.step(acts)[0].astype(np.float32))
         assert np.array_equal(b.step(acts)[0].cpu().numpy(), ob.step(acts)[0].astype(np.float32))
     a.close(); b.close()
+
+
+def test_24_rotations_match_oracle():
+    """BASELINE.json config 3 speaks of 24 poses per shape; the rotation count is a runtime parameter
+    (up to 32).  6 rotation groups per scan CTA, 24 x levels images per bin in the candidates kernel."""
+    from irbpp_b200 import shapes
+    from oracle.oracle_env import OracleConfig, OracleVecEnv
+    lib = shapes.make_irregular_library(6, seed=9, num_rotations=24)
+    seqs = shapes.make_sequences(6, 24, lib.num_shapes, seed=4)
+    ora = OracleVecEnv(OracleConfig(ZRotNum=24), lib, seqs)
+    env = _env(lib, seqs)
+    o = ora.reset(); g = env.reset()
+    assert np.array_equal(g.cpu().numpy(), o.astype(np.float32))
+    rng = np.random.default_rng(2)
+    max_valid = 0
+    for t in range(14):
+        acts = _random_valid_actions(rng, o, 500)
+        max_valid = max(max_valid, int((o[:, :2500].reshape(6, 500, 5)[:, :, 4] == 1).sum(axis=1).max()))
+        o, orew, odone, _ = ora.step(acts)
+        g, grew, gdone, _ = env.step(acts)
+        assert np.array_equal(g.cpu().numpy(), o.astype(np.float32)), t
+        assert np.array_equal(gdone, odone)
+    assert max_valid == 500          # with 24 rotations the >selectedAction truncation is the normal case
+    env.close()
