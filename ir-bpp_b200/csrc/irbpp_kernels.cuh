@@ -295,19 +295,36 @@ __global__ void __launch_bounds__(CTA_THREADS, IRBPP_SCAN_MIN_CTAS) irbpp_scan_k
         }
     };
 
-    // ---- load heightmap (column-parity planes, 8 KB) ----
+    // ---- load heightmap (column-parity planes, 8 KB) and the bin's scalar state ----
+    // All of these are first-touch DRAM reads (the agent's forward pass sits between two steps).  Warp 0
+    // puts its dependent chain  state -> item, action -> candidate -> rotation  in flight before anybody
+    // waits, so that it overlaps with the heightmap load instead of following it.
     double* hm_g = P.hm + (int64_t)env * (HX * HY);
+    int64_t a_pf = 0;
+    uint32_t c_pf = 0;
     {
+        uint32_t stw = 0;
+        if (warp == 0) {
+            stw = reinterpret_cast<const uint32_t*>(P.state + env)[lane];
+            if (mode == MODE_STEP) a_pf = P.actions[env];
+        }
         const double2* src = reinterpret_cast<const double2*>(hm_g);
         double2* dst = reinterpret_cast<double2*>(hm_s);
+        static_assert(HX * HY / 2 == 4 * CTA_THREADS, "four double2 per thread");
+        double2 hreg[4];
         if (mode == MODE_RESET) {
-            for (int i = tid; i < HX * HY / 2; i += CTA_THREADS) dst[i] = make_double2(0.0, 0.0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) hreg[k] = make_double2(0.0, 0.0);
         } else {
-            for (int i = tid; i < HX * HY / 2; i += CTA_THREADS) dst[i] = src[i];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) hreg[k] = src[tid + k * CTA_THREADS];
         }
+        if (warp == 0 && mode == MODE_STEP && a_pf >= 0 && a_pf < P.sel) c_pf = P.cand[(int64_t)env * P.sel + a_pf];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) dst[tid + k * CTA_THREADS] = hreg[k];
+        if (warp == 0) reinterpret_cast<uint32_t*>(&st_s)[lane] = stw;
     }
     if (tid == 0) { err_sh = 0; any_sh = 0; }
-    if (warp == 0) reinterpret_cast<uint32_t*>(&st_s)[lane] = reinterpret_cast<const uint32_t*>(P.state + env)[lane];
     __syncthreads();
 
     int32_t* queue_g = st_s.queue;
@@ -330,13 +347,13 @@ __global__ void __launch_bounds__(CTA_THREADS, IRBPP_SCAN_MIN_CTAS) irbpp_scan_k
     } else if (mode == MODE_STEP) {
         // decode the action (warp 0 computes the drop height of that single pose)
         if (warp == 0) {
-            const int64_t a = P.actions[env];
+            const int64_t a = a_pf;
             const int item = st_s.cur_item;
             int rot = 0, lx = 0, ly = 0;
             bool ok = true;
             if (a < 0 || a >= P.sel) { ok = false; if (lane == 0) err_sh = 2; }
             else {
-                const uint16_t c = P.cand[(int64_t)env * P.sel + a];
+                const uint32_t c = c_pf;
                 rot = c >> 8; lx = (c >> 4) & 15; ly = c & 15;
             }
             const ShapeRot* sr = P.srot + (int64_t)item * P.R + rot;
