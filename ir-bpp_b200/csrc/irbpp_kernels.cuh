@@ -579,6 +579,9 @@ struct CandSmem {
     int32_t pre[ENVS_PER_CTA * MAX_ROT + 1];              // prefix of level counts over (bin, rotation)
     int32_t cand_off[CAND_THREADS + 1];                   // prefix of start-candidate counts over the images, in cost order
     uint16_t slot_of[CAND_THREADS];                       // image slot at each position of the cost order
+    uint16_t order2[CAND_THREADS];                        // contour owner (thread) by decreasing contour length
+    uint16_t q_of[CAND_THREADS];                          // (bin, rotation) pair of a thread's contour
+    uint8_t n_of[CAND_THREADS];                           // points of a thread's contour (0: nothing to approximate)
     int32_t hist[64], hbase[64];
     uint16_t pair_of[CAND_THREADS];                       // (bin, rotation) pair of image t
     int32_t warp_tot[CAND_WARPS];
@@ -714,28 +717,60 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
             }
             const uint32_t* bm = S.slots + slot * SLOT_WORDS;
             const int q = S.pair_of[slot];
-            uint32_t* cb = S.candbits + q * 8;
-            auto emit = [&](int ex, int ey) { const int b = ex * 16 + ey; atomicOr(cb + (b >> 5), 1u << (b & 31)); };
-            bool okc = true;
+            // (a) every lane follows its border; the points stay in the lane's scratch
+            int n = -2, area2 = 1;
             {
-                // follow and approximate as two warp-converged phases: lanes that finish following early
-                // wait, so that the approximation loops run with all lanes in the same code
                 StridedScratch<32, FAST_CAP> sc;
                 sc.w = nullptr;
                 sc.b = W.pts + lane;
                 sc.kept = 0;
-                int area2 = 1, n = -2;
                 if (has) n = follow_outer_from(sc, bm, x, y, area2);
-                __syncwarp();
-                if (has && n != -2 && area2 <= 0) {        // a raster-first start of an outer border
-                    if (n < 0) okc = false;
-                    else approx_and_emit(sc, n, P.legacy != 0, emit);
+            }
+            const bool keep = has && n != -2 && area2 <= 0;        // a raster-first start of an outer border
+            const bool ovf_mine = keep && n < 0;
+            const int npts = (keep && n > 0) ? n : 0;
+            // (b) the contours of the CTA are re-dealt in decreasing length, so that the approximation loops
+            //     of a warp have similar trip counts and abandoned / hole paths drop out
+            if (tid < 64) S.hist[tid] = 0;
+            __syncthreads();
+            const int bucket = 63 - min(63, npts);
+            const int boff = atomicAdd(&S.hist[bucket], 1);
+            S.n_of[tid] = (uint8_t)npts;
+            S.q_of[tid] = (uint16_t)q;
+            __syncthreads();
+            if (warp == 0) {   // exclusive prefix over the 64 buckets
+                const int h0 = S.hist[lane], h1 = S.hist[32 + lane];
+                int i0 = h0, i1 = h1;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t0 = __shfl_up_sync(0xffffffffu, i0, o), t1 = __shfl_up_sync(0xffffffffu, i1, o);
+                    if (lane >= o) { i0 += t0; i1 += t1; }
+                }
+                const int tot0 = __shfl_sync(0xffffffffu, i0, 31);
+                S.hbase[lane] = i0 - h0;
+                S.hbase[32 + lane] = tot0 + i1 - h1;
+            }
+            __syncthreads();
+            S.order2[S.hbase[bucket] + boff] = (uint16_t)tid;
+            __syncthreads();
+            // (c) lane i approximates the i-th longest contour (points live in its owner's scratch)
+            {
+                const int owner = S.order2[tid];
+                const int on = S.n_of[owner];
+                if (on > 0) {
+                    StridedScratch<32, FAST_CAP> sc;
+                    sc.w = nullptr;
+                    sc.b = S.ws[owner >> 5].pts + (owner & 31);
+                    sc.kept = 0;
+                    uint32_t* cb = S.candbits + (int)S.q_of[owner] * 8;
+                    approx_and_emit(sc, on, P.legacy != 0,
+                                    [&](int ex, int ey) { const int b = ex * 16 + ey; atomicOr(cb + (b >> 5), 1u << (b & 31)); });
                 }
             }
-            __syncwarp();
+            __syncthreads();           // scratch of every lane is free again
             // rare: a contour longer than FAST_CAP points; the lanes concerned redo it one at a time with
             // 1024-point buffers laid over the (now idle) lane scratch of this warp
-            uint32_t ovf = __ballot_sync(0xffffffffu, !okc);
+            uint32_t ovf = __ballot_sync(0xffffffffu, ovf_mine);
             while (ovf) {
                 const int src_lane = __ffs((int)ovf) - 1;
                 ovf &= ovf - 1;
@@ -744,10 +779,14 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
                     FlatScratch<BIG_CAP> bs;
                     bs.w = nullptr;
                     bs.b = W.pts;
-                    if (!process_start_candidate(bs, bm, x, y, P.legacy != 0, emit)) atomicMax(&S.error[q / R], 6);
+                    uint32_t* cb = S.candbits + q * 8;
+                    if (!process_start_candidate(bs, bm, x, y, P.legacy != 0,
+                            [&](int ex, int ey) { const int b = ex * 16 + ey; atomicOr(cb + (b >> 5), 1u << (b & 31)); }))
+                        atomicMax(&S.error[q / R], 6);
                 }
                 __syncwarp();
             }
+            __syncthreads();
         }
         __syncthreads();
     }
