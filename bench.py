@@ -220,6 +220,8 @@ def main_gpu(args):
     for _ in range(BURN_IN + args.warmup):          # burn-in: bins spread over all episode phases
         acts = device_policy(torch, obs, gen)
         obs, _ = env.step_device(acts)
+    if world > 1:                                   # warm-up of the rollout-end collective (NCCL channel setup)
+        sharding.gather_rollout(obs, world)
     torch.cuda.synchronize(dev)
     launches0 = env.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
