@@ -131,7 +131,8 @@ int irbpp_create(const irbpp_config* cfg, irbpp_handle* out) {
     P.binz = cfg->bin_dimension[2];
     P.resZ = cfg->resolution_z;
     P.binvol = (cfg->bin_dimension[0] * cfg->bin_dimension[1]) * cfg->bin_dimension[2];   // np.prod
-    h->cand_smem = (int)sizeof(CandSmem);
+    P.ws_bytes = ws_bytes_for(P.R);
+    h->cand_smem = (int)((sizeof(CandSmem) + 15) & ~(size_t)15) + CAND_WARPS * P.ws_bytes;
 
 #define TRY_ALLOC(expr)                                                                          \
     do { cudaError_t e2_ = (expr); if (e2_ != cudaSuccess) {                                      \
@@ -165,7 +166,13 @@ int irbpp_create(const irbpp_config* cfg, irbpp_handle* out) {
         P.r_valid = reinterpret_cast<uint8_t*>(b); b += N;
         P.r_error = reinterpret_cast<uint8_t*>(b);
     }
-    TRY_ALLOC(cudaFuncSetAttribute(irbpp_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->cand_smem));
+    {   // per-function attribute shared by all handles: only ever raise it
+        static int cand_attr = 0;
+        if (h->cand_smem > cand_attr) {
+            TRY_ALLOC(cudaFuncSetAttribute(irbpp_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->cand_smem));
+            cand_attr = h->cand_smem;
+        }
+    }
 #undef TRY_ALLOC
     *out = h;
     return IRBPP_OK;

@@ -149,6 +149,7 @@ struct Params {
     const uint8_t* which;                // MODE_RESET (NULL = all)
     const int32_t* dbg_items;            // MODE_DEBUG_SCAN
     int32_t slot;                        // MODE_ALL_OBS: queue slot of this pass
+    int32_t ws_bytes;                    // per-warp scratch of the candidates kernel (ws_bytes_for(R))
     int32_t env_lo, env_hi;              // bins [env_lo, env_hi) handled by this launch (chunked pipeline)
     // outputs
     float* obs;                          // [N][obs_stride] (+ slot offset in MODE_ALL_OBS)
@@ -566,15 +567,19 @@ __global__ void __launch_bounds__(CTA_THREADS) irbpp_levels_kernel(const Params 
 // that the lanes of a warp carry images of similar size -- the lanes run in lock step and a warp costs
 // what its heaviest lane costs (the floor-level image of each rotation is an order of magnitude
 // heavier than the small plateaus above it).
-struct WarpScratch {
-    uint8_t pts[FAST_CAP * 32];               // per-lane contour points, element stride 32 (also the overflow buffers)
-    uint8_t spare[4096 - FAST_CAP * 32];      // together: the row list of phase D
-};
-static_assert(sizeof(WarpScratch) >= 2 * BIG_CAP, "overflow buffers must fit the lane scratch");
+// Per-warp scratch of the candidates kernel, sized at run time (Params::ws_bytes, >= WS_MIN_BYTES): the first
+// FAST_CAP * 32 bytes are the lane-strided contour points of phase C (also the 1024-point overflow
+// buffers); in phase D the whole block holds the candidate list and its bucket-sorted index list, so its
+// size grows with the rotation count (a bin can have up to R * 256 candidates).
+constexpr int WS_MIN_BYTES = 4096;
+static_assert(WS_MIN_BYTES >= 2 * BIG_CAP && WS_MIN_BYTES >= FAST_CAP * 32, "overflow buffers must fit the lane scratch");
+__host__ __device__ inline int ws_bytes_for(int R) {
+    const int need = R * NPOSE * 4;                      // uint16 list + uint16 sorted list for every pose
+    return ((need > WS_MIN_BYTES ? need : WS_MIN_BYTES) + 15) & ~15;
+}
 
 struct CandSmem {
     uint32_t slots[CAND_THREADS * SLOT_WORDS];            // level images of this round (one per thread)
-    WarpScratch ws[CAND_WARPS];
     uint32_t candbits[ENVS_PER_CTA * MAX_ROT * 8];        // 256-bit candidate set per (bin, rotation)
     int32_t pre[ENVS_PER_CTA * MAX_ROT + 1];              // prefix of level counts over (bin, rotation)
     int32_t cand_off[CAND_THREADS + 1];                   // prefix of start-candidate counts over the images, in cost order
@@ -625,7 +630,8 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
     }
     __syncthreads();
     const int nimg = S.pre[npairs];
-    WarpScratch& W = S.ws[warp];
+    unsigned char* ws_base = smem_raw + ((sizeof(CandSmem) + 15) & ~(size_t)15);     // CAND_WARPS blocks of P.ws_bytes
+    uint8_t* W_pts = ws_base + (size_t)warp * P.ws_bytes;
 
     // ---- phase C: rounds of CAND_THREADS level images; inside a round one (image, start pixel) per lane ----
     for (int base = 0; base < nimg; base += CAND_THREADS) {
@@ -722,7 +728,7 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
             {
                 StridedScratch<32, FAST_CAP> sc;
                 sc.w = nullptr;
-                sc.b = W.pts + lane;
+                sc.b = W_pts + lane;
                 sc.kept = 0;
                 if (has) n = follow_outer_from(sc, bm, x, y, area2);
             }
@@ -760,7 +766,7 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
                 if (on > 0) {
                     StridedScratch<32, FAST_CAP> sc;
                     sc.w = nullptr;
-                    sc.b = S.ws[owner >> 5].pts + (owner & 31);
+                    sc.b = ws_base + (size_t)(owner >> 5) * P.ws_bytes + (owner & 31);
                     sc.kept = 0;
                     uint32_t* cb = S.candbits + (int)S.q_of[owner] * 8;
                     approx_and_emit(sc, on, P.legacy != 0,
@@ -778,7 +784,7 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
                     if (P.phase_cycles) atomicAdd(P.phase_cycles + 7, 1ull);     // overflow redo counter
                     FlatScratch<BIG_CAP> bs;
                     bs.w = nullptr;
-                    bs.b = W.pts;
+                    bs.b = W_pts;
                     uint32_t* cb = S.candbits + q * 8;
                     if (!process_start_candidate(bs, bm, x, y, P.legacy != 0,
                             [&](int ex, int ey) { const int b = ex * 16 + ey; atomicOr(cb + (b >> 5), 1u << (b & 31)); }))
@@ -798,7 +804,6 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
     const int env = env0 + warp;
     if (!env_live(env)) return;
     const int dev_err = S.error[warp];
-    WarpScratch& WS = S.ws[warp];
     // ---- phase D ----
     const int sel = P.sel;
     const uint32_t* cbits = S.candbits + warp * R * 8;
@@ -861,10 +866,10 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
         // rows in rotation order, then (col, row) ascending == bit order of the per-rotation sets.
         // Pass 1 compacts the set bits into a list (no memory loads); pass 2 gives every lane one
         // candidate, so the height gathers of 32 candidates are in flight together.
-        uint16_t* list = reinterpret_cast<uint16_t*>(&WS);            // lane scratch is idle now
-        constexpr int LIST_CAP = (int)(sizeof(WarpScratch) / 4);      // list + bucket-sorted index list
+        uint16_t* list = reinterpret_cast<uint16_t*>(W_pts);          // lane scratch is idle now
+        const int LIST_CAP = P.ws_bytes / 4;                          // list + bucket-sorted index list; >= R * 256 >= Ktot
         auto cell_of = [](int e) { const int b = e & 255; return (e >> 8) * NPOSE + (b & 15) * 16 + (b >> 4); };
-        if (Ktot <= LIST_CAP) {
+        {
             for (int r = 0; r < R; ++r) {
                 const uint32_t* cb = cbits + r * 8;
                 int ord0 = __shfl_sync(0xffffffffu, excl, r);
@@ -932,37 +937,6 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
                         rank += (H2 < H) || (H2 == H && j < i);
                     }
                     if (rank < sel) put_row(rank, e >> 8, b & 15, b >> 4, H, m ? 1.0 : 0.0);
-                }
-            }
-        } else {
-            for (int r = 0; r < R; ++r) {
-                const uint32_t* cb = cbits + r * 8;
-                int ord0 = __shfl_sync(0xffffffffu, excl, r);
-#pragma unroll 1
-                for (int qd = 0; qd < 8; ++qd) {
-                    const uint32_t wbits = cb[qd];
-                    if ((wbits >> lane) & 1u) {
-                        const int ord = ord0 + __popc(wbits & ((1u << lane) - 1u));
-                        const int b = qd * 32 + lane;
-                        const int col = b >> 4, row = b & 15;
-                        bool m; const double H = height_of(r * NPOSE + row * 16 + col, m);
-                        int rank = 0, ord2 = 0;                   // Ktot > LIST_CAP >= sel: always truncating
-                        for (int r2 = 0; r2 < R; ++r2) {
-                            const uint32_t* cb2 = cbits + r2 * 8;
-                            for (int q2 = 0; q2 < 8; ++q2) {
-                                uint32_t w2 = cb2[q2];
-                                while (w2) {
-                                    const int bb = q2 * 32 + __ffs((int)w2) - 1;
-                                    w2 &= w2 - 1;
-                                    bool m2; const double H2 = height_of(r2 * NPOSE + (bb & 15) * 16 + (bb >> 4), m2);
-                                    rank += (H2 < H) || (H2 == H && ord2 < ord);
-                                    ++ord2;
-                                }
-                            }
-                        }
-                        if (rank < sel) put_row(rank, r, row, col, H, m ? 1.0 : 0.0);
-                    }
-                    ord0 += __popc(wbits);
                 }
             }
         }
