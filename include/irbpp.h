@@ -131,6 +131,30 @@ int irbpp_get_action_candidates(irbpp_handle h, const int64_t* order_actions, in
  * out: dev float32 [N, k * loc_obs_len].  Leaves the candidate state of slot k-1 current. */
 int irbpp_get_all_possible_observation(irbpp_handle h, float* out, void* stream);
 
+/* Replaces: Space.get_heuristic_action(dirIdx, method, next_item_ID, next_item)
+ * (environment/physics0/space.py:162-227) for every bin, over the drop heights / feasibility mask of
+ * the bin's current item (the scan of the last reset / step (buffer_size 1) or
+ * get_action_candidates).  method: IRBPP_HEUR_*; dir_idx 0..3 selects the X/Y flips (:163-166).
+ * poses_out: int32[N,3] (rotIdx, lx, ly); index_out: int64[N] row of that pose in the bin's candidate
+ * table (what envs.step takes), -1 if the pose is not a candidate; either may be NULL; both host
+ * pointers, or device pointers when outputs_on_device != 0 (then nothing is synchronised).
+ * The reference's RANDOM branch raises on every call and has no counterpart.
+ * Returns IRBPP_ESTATE when no current scan exists (before reset, or buffer_size > 1 without
+ * get_action_candidates). */
+#define IRBPP_HEUR_MINZ      0
+#define IRBPP_HEUR_DBLF      1
+#define IRBPP_HEUR_FIRSTFIT  2
+#define IRBPP_HEUR_HM        3
+int irbpp_heuristic_actions(irbpp_handle h, int32_t method, int32_t dir_idx, int32_t* poses_out,
+                            int64_t* index_out, int32_t outputs_on_device, void* stream);
+
+/* irbpp_step_async with explicit poses instead of candidate rows: poses int64[N], each
+ * (rotIdx * Ax + lx) * Ay + ly -- the (rotIdx, lx, ly) binPhy.action_to_position (binPhy.py:234-236)
+ * would have read from candidates[action].  Everything after that line of PackingGame.step is
+ * unchanged (prejudge, placement, reward, auto-reset); pair with irbpp_step_wait as usual. */
+int irbpp_step_poses_async(irbpp_handle h, const int64_t* poses, int32_t poses_on_device,
+                           float* obs_out, void* stream);
+
 /* ---- parity / debugging views (float64, host destinations; any pointer may be NULL) ---- */
 
 /* Current bin state: heightmap [N,Hx,Hy] row-major, the candidate table [N,selected_action,5]

@@ -41,6 +41,8 @@ SIGNATURES = {
     "irbpp_step_wait_device": (c_i32, [c_void_p, ctypes.POINTER(IrbppStepResult)]),
     "irbpp_get_action_candidates": (c_i32, [c_void_p, c_void_p, c_i32, c_void_p, c_void_p]),
     "irbpp_get_all_possible_observation": (c_i32, [c_void_p, c_void_p, c_void_p]),
+    "irbpp_heuristic_actions": (c_i32, [c_void_p, c_i32, c_i32, c_void_p, c_void_p, c_i32, c_void_p]),
+    "irbpp_step_poses_async": (c_i32, [c_void_p, c_void_p, c_i32, c_void_p, c_void_p]),
     "irbpp_debug_state": (c_i32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "irbpp_debug_set_heightmap": (c_i32, [c_void_p, c_void_p]),
     "irbpp_debug_scan": (c_i32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -27,6 +27,8 @@ struct irbpp_env {
     int cand_smem = 0, scan_smem = 0;
     std::string err;
     bool shapes_loaded = false, sequences_set = false, was_reset = false, waiting_step = false;
+    bool scan_current = false;        // the scan scratch holds the drop heights of every bin's cur_item
+    int32_t* heur_pose_dev = nullptr; int64_t* heur_index_dev = nullptr;
     bool results_on_host = false;           // the pending step wrote its results straight to the host mirror
     cudaStream_t pending_stream = nullptr;
     int64_t launches = 0;
@@ -75,8 +77,6 @@ static cudaError_t dev_alloc(irbpp_env* h, T** p, size_t count, bool zero = true
     return cudaSuccess;
 }
 
-// np.round(x, 6): multiply, rint, divide
-static inline double np_round6(double x) { return rint(x * 1e6) / 1e6; }
 
 extern "C" {
 
@@ -130,6 +130,7 @@ int irbpp_create(const irbpp_config* cfg, irbpp_handle* out) {
     P.legacy = cfg->approx_legacy;
     P.binz = cfg->bin_dimension[2];
     P.resZ = cfg->resolution_z;
+    P.resA = cfg->resolution_act;
     P.binvol = (cfg->bin_dimension[0] * cfg->bin_dimension[1]) * cfg->bin_dimension[2];   // np.prod
     P.ws_bytes = ws_bytes_for(P.R);
     h->cand_smem = (int)((sizeof(CandSmem) + 15) & ~(size_t)15) + CAND_WARPS * P.ws_bytes;
@@ -346,6 +347,7 @@ int irbpp_set_sequences(irbpp_handle h, const int32_t* ids, int32_t length) {
     CUDA_TRY(h, cudaMemcpy(h->seq_dev, ids, n * 4, cudaMemcpyHostToDevice));
     CUDA_TRY(h, cudaMemset(h->P.state, 0, (size_t)h->P.N * sizeof(EnvState)));   // cursors restart
     h->was_reset = false;
+    h->scan_current = false;
     h->P.seq = h->seq_dev; h->P.L = length;
     h->sequences_set = true;
     return IRBPP_OK;
@@ -362,11 +364,23 @@ static int launch(irbpp_env* h, Params& P, cudaStream_t s) {
     else irbpp_scan_kernel<<<P.N, CTA_THREADS, h->scan_smem, s>>>(P);
     h->launches += 1;
     if (mode_emits_loc(P.mode, P.K)) {
-        irbpp_candidates_kernel<<<(P.N + ENVS_PER_CTA - 1) / ENVS_PER_CTA, CAND_THREADS, h->cand_smem, s>>>(P);
+        // programmatic dependent launch: the candidates grid is scheduled while the scan grid's last
+        // wave drains and waits at griddepcontrol.wait for the scan's completion
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3((P.N + ENVS_PER_CTA - 1) / ENVS_PER_CTA); lc.blockDim = dim3(CAND_THREADS);
+        lc.dynamicSmemBytes = (size_t)h->cand_smem; lc.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = (P.mode == MODE_DEBUG_HULLS) ? 0 : 1;
+        lc.attrs = at; lc.numAttrs = 1;
+        cudaLaunchKernelEx(&lc, irbpp_candidates_kernel, P);
         h->launches += 1;
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(h, IRBPP_ECUDA, "kernel launch: %s", cudaGetErrorString(e));
+    // buffered step / reset change the heightmap without a scan; the debug modes scan foreign inputs
+    h->scan_current = (P.mode == MODE_CANDIDATES || P.mode == MODE_ALL_OBS ||
+                       ((P.mode == MODE_STEP || P.mode == MODE_RESET) && P.K == 1));
     return IRBPP_OK;
 }
 
@@ -397,14 +411,15 @@ int irbpp_reset(irbpp_handle h, const uint8_t* which, float* obs_out, void* stre
     return IRBPP_OK;
 }
 
-int irbpp_step_async(irbpp_handle h, const int64_t* actions, int32_t on_device, float* obs_out, void* stream) {
+static int step_async_impl(irbpp_env* h, const int64_t* actions, int32_t on_device, float* obs_out, void* stream,
+                           int pose_actions) {
     int rc = ready(h); if (rc) return rc;
     if (!actions || !obs_out) return fail(h, IRBPP_EINVAL, "null argument");
     if (!h->was_reset) return fail(h, IRBPP_ESTATE, "step before reset");
     if (h->waiting_step) return fail(h, IRBPP_ESTATE, "already running an async step");   // vec_env.py:7-16
     cudaStream_t s = (cudaStream_t)stream;
     Params P = h->P;
-    P.mode = MODE_STEP; P.obs = obs_out;
+    P.mode = MODE_STEP; P.obs = obs_out; P.pose_actions = pose_actions;
     if (on_device) P.actions = actions;
     else {
         // host actions: staged in mapped pinned memory and read by the kernel over PCIe (one 8-byte read per
@@ -426,6 +441,14 @@ int irbpp_step_async(irbpp_handle h, const int64_t* actions, int32_t on_device, 
     rc = launch(h, P, s); if (rc) return rc;
     h->waiting_step = true; h->pending_stream = s;
     return IRBPP_OK;
+}
+
+int irbpp_step_async(irbpp_handle h, const int64_t* actions, int32_t on_device, float* obs_out, void* stream) {
+    return step_async_impl(h, actions, on_device, obs_out, stream, 0);
+}
+
+int irbpp_step_poses_async(irbpp_handle h, const int64_t* poses, int32_t on_device, float* obs_out, void* stream) {
+    return step_async_impl(h, poses, on_device, obs_out, stream, 1);
 }
 
 static void host_views(irbpp_env* h, char* b, irbpp_step_result* out) {
@@ -498,6 +521,36 @@ int irbpp_get_all_possible_observation(irbpp_handle h, float* out, void* stream)
         P.slot = slot;
         rc = launch(h, P, (cudaStream_t)stream);
         if (rc) return rc;
+    }
+    return IRBPP_OK;
+}
+
+int irbpp_heuristic_actions(irbpp_handle h, int32_t method, int32_t dir_idx, int32_t* poses_out, int64_t* index_out,
+                            int32_t on_device, void* stream) {
+    int rc = ready(h); if (rc) return rc;
+    if (method < 0 || method >= HEUR_COUNT) return fail(h, IRBPP_EINVAL, "unknown heuristic %d", method);
+    if (dir_idx < 0 || dir_idx > 3) return fail(h, IRBPP_EINVAL, "dir_idx %d not in 0..3", dir_idx);   // space.py:167
+    if (!h->was_reset || !h->scan_current)
+        return fail(h, IRBPP_ESTATE, "no current scan (call after reset / step, or after get_action_candidates when buffer_size > 1)");
+    if (h->waiting_step) return fail(h, IRBPP_ESTATE, "a step is pending");
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t N = h->P.N;
+    if (!h->heur_pose_dev) {
+        CUDA_TRY(h, dev_alloc(h, &h->heur_pose_dev, N * 3));
+        CUDA_TRY(h, dev_alloc(h, &h->heur_index_dev, N));
+    }
+    Params P = h->P;
+    P.heur_method = method; P.heur_dir = dir_idx;
+    P.heur_pose = (on_device && poses_out) ? poses_out : h->heur_pose_dev;
+    P.heur_index = (on_device && index_out) ? index_out : h->heur_index_dev;
+    irbpp_heuristic_kernel<<<P.N, CTA_THREADS, 0, s>>>(P);
+    h->launches += 1;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(h, IRBPP_ECUDA, "kernel launch: %s", cudaGetErrorString(e));
+    if (!on_device) {
+        if (poses_out) CUDA_TRY(h, cudaMemcpyAsync(poses_out, h->heur_pose_dev, N * 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+        if (index_out) CUDA_TRY(h, cudaMemcpyAsync(index_out, h->heur_index_dev, N * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(h, cudaStreamSynchronize(s));
     }
     return IRBPP_OK;
 }

@@ -35,6 +35,7 @@
 #include <math.h>
 #include "irbpp_contour.cuh"
 #include "irbpp_math.cuh"
+#include "irbpp_heuristic.cuh"
 
 namespace irbpp {
 
@@ -123,7 +124,7 @@ struct Params {
     int32_t N, R, sel, K;                // K = buffer_size (1 = online)
     int32_t loc_len, order_len, obs_stride;
     int32_t legacy;
-    double binz, resZ, binvol;
+    double binz, resZ, binvol, resA;
     // shapes
     int32_t S;
     int32_t maxwh;                       // largest scan list of the library (entries of a warp's staging buffer)
@@ -150,6 +151,10 @@ struct Params {
     const int32_t* dbg_items;            // MODE_DEBUG_SCAN
     int32_t slot;                        // MODE_ALL_OBS: queue slot of this pass
     int32_t ws_bytes;                    // per-warp scratch of the candidates kernel (ws_bytes_for(R))
+    int32_t pose_actions;                // MODE_STEP: actions are flat poses (rot*256 + lx*16 + ly), not candidate rows
+    int32_t heur_method, heur_dir;       // heuristic kernel: Heuristic, dirIdx 0..3 (space.py:162-166)
+    int32_t* heur_pose;                  // [N][3] rot, lx, ly
+    int64_t* heur_index;                 // [N] row of that pose in the candidate table, -1 if absent
     int32_t env_lo, env_hi;              // bins [env_lo, env_hi) handled by this launch (chunked pipeline)
     // outputs
     float* obs;                          // [N][obs_stride] (+ slot offset in MODE_ALL_OBS)
@@ -281,11 +286,13 @@ __global__ void __launch_bounds__(CTA_THREADS, IRBPP_SCAN_MIN_CTAS) irbpp_scan_k
     extern __shared__ __align__(16) TileEntry estage[];  // CTA_WARPS x P.maxwh: scan list of each warp's rotation
     __shared__ __align__(16) EnvState st_s;              // this bin's scalar state (loaded / stored by warp 0)
     __shared__ double M_s[NPOSE];                        // block maxima of the heightmap (block form of phase B)
+    __shared__ double P2_s[NPOSE];                       // 2x2 block maxima
     __shared__ double z_sh;
     __shared__ int ok_sh, rot_sh, lx_sh, ly_sh, item_sh, err_sh, any_sh;
     const int env = P.env_lo + blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int mode = P.mode;
+    asm volatile("griddepcontrol.launch_dependents;");      // the candidates grid may be scheduled as this one drains (PDL)
     if (mode == MODE_RESET && P.which && !P.which[env]) return;
     long long t_prev = P.phase_cycles ? clock64() : 0;
     auto phase_mark = [&](int idx) {
@@ -303,6 +310,7 @@ __global__ void __launch_bounds__(CTA_THREADS, IRBPP_SCAN_MIN_CTAS) irbpp_scan_k
     double* hm_g = P.hm + (int64_t)env * (HX * HY);
     int64_t a_pf = 0;
     uint32_t c_pf = 0;
+    int seq_pf = -1;             // thread 0: the sequence entry at the bin's cursor (first draw of this call)
     {
         uint32_t stw = 0;
         if (warp == 0) {
@@ -320,7 +328,9 @@ __global__ void __launch_bounds__(CTA_THREADS, IRBPP_SCAN_MIN_CTAS) irbpp_scan_k
 #pragma unroll
             for (int k = 0; k < 4; ++k) hreg[k] = src[tid + k * CTA_THREADS];
         }
-        if (warp == 0 && mode == MODE_STEP && a_pf >= 0 && a_pf < P.sel) c_pf = P.cand[(int64_t)env * P.sel + a_pf];
+        if (tid == 0 && (mode == MODE_STEP || mode == MODE_RESET))
+            seq_pf = P.seq[(int64_t)env * P.L + ((int)stw % P.L)];          // lane 0's word is EnvState::cursor
+        if (warp == 0 && mode == MODE_STEP && !P.pose_actions && a_pf >= 0 && a_pf < P.sel) c_pf = P.cand[(int64_t)env * P.sel + a_pf];
 #pragma unroll
         for (int k = 0; k < 4; ++k) dst[tid + k * CTA_THREADS] = hreg[k];
         if (warp == 0) reinterpret_cast<uint32_t*>(&st_s)[lane] = stw;
@@ -329,6 +339,10 @@ __global__ void __launch_bounds__(CTA_THREADS, IRBPP_SCAN_MIN_CTAS) irbpp_scan_k
     __syncthreads();
 
     int32_t* queue_g = st_s.queue;
+    auto draw = [&](int& cursor) {                    // draw_item, the first one served from the prefetch
+        if (seq_pf >= 0) { const int id = seq_pf; seq_pf = -1; ++cursor; return id; }
+        return draw_item(P, env, cursor);
+    };
     bool hm_changed = false;
     bool st_dirty = false;
 
@@ -337,7 +351,7 @@ __global__ void __launch_bounds__(CTA_THREADS, IRBPP_SCAN_MIN_CTAS) irbpp_scan_k
         if (tid == 0) {
             int cursor = st_s.cursor;
             const int nfill = P.K > 1 ? P.K : 1;
-            for (int q = 0; q < nfill; ++q) queue_g[q] = draw_item(P, env, cursor);
+            for (int q = 0; q < nfill; ++q) queue_g[q] = draw(cursor);
             st_s.cursor = cursor;
             st_s.packed = 0; st_s.ep_len = 0; st_s.vol_sum = 0.0; st_s.ep_rew = 0.0;
             st_s.order_act = 0;
@@ -352,9 +366,9 @@ __global__ void __launch_bounds__(CTA_THREADS, IRBPP_SCAN_MIN_CTAS) irbpp_scan_k
             const int item = st_s.cur_item;
             int rot = 0, lx = 0, ly = 0;
             bool ok = true;
-            if (a < 0 || a >= P.sel) { ok = false; if (lane == 0) err_sh = 2; }
+            if (a < 0 || a >= (P.pose_actions ? P.R * NPOSE : P.sel)) { ok = false; if (lane == 0) err_sh = 2; }
             else {
-                const uint32_t c = c_pf;
+                const uint32_t c = P.pose_actions ? (uint32_t)a : c_pf;
                 rot = c >> 8; lx = (c >> 4) & 15; ly = c & 15;
             }
             const ShapeRot* sr = P.srot + (int64_t)item * P.R + rot;
@@ -419,7 +433,7 @@ __global__ void __launch_bounds__(CTA_THREADS, IRBPP_SCAN_MIN_CTAS) irbpp_scan_k
                 // item_creator.update_item_queue(orderAction); generate_item()  (binPhy.py:324-325)
                 const int oa = st_s.order_act;
                 for (int q = oa; q + 1 < nfill; ++q) queue_g[q] = queue_g[q + 1];
-                queue_g[nfill - 1] = draw_item(P, env, cursor);
+                queue_g[nfill - 1] = draw(cursor);
             } else {
                 P.r_reward[env] = 0.0f; P.r_done[env] = 1; P.r_valid[env] = 1;
                 P.r_counter[env] = st_s.packed;
@@ -433,7 +447,7 @@ __global__ void __launch_bounds__(CTA_THREADS, IRBPP_SCAN_MIN_CTAS) irbpp_scan_k
                 }
                 st_s.packed = 0; st_s.ep_len = 0; st_s.vol_sum = 0.0; st_s.ep_rew = 0.0;
                 st_s.order_act = 0;
-                for (int q = 0; q < nfill; ++q) queue_g[q] = draw_item(P, env, cursor);   // reset(): clear + preview
+                for (int q = 0; q < nfill; ++q) queue_g[q] = draw(cursor);   // reset(): clear + preview
             }
             st_s.cursor = cursor;
             item_sh = queue_g[0];
@@ -489,22 +503,31 @@ __global__ void __launch_bounds__(CTA_THREADS, IRBPP_SCAN_MIN_CTAS) irbpp_scan_k
         bool any = false;
         const int tile = P.srot[(int64_t)item * P.R].tile;      // same for every rotation of a shape
         if (tile > 1) {
-            // block maxima of the heightmap, one entry per action-grid offset
+            // block maxima of the heightmap, one entry per action-grid offset.  max is exact, so the
+            // 4x4 maximum is taken as the maximum of four 2x2 maxima (8 loads per entry instead of 16).
             for (int e = tid; e < NPOSE; e += CTA_THREADS) {
-                const int u = e >> 4, v = e & 15;
-                double m = -INFINITY;
-                if (2 * u + tile <= HX && 2 * v + tile <= HY) {
-                    for (int i = 0; i < tile; ++i)
-                        for (int j = 0; j < tile; ++j) {
-                            const double x = hm_s[hm_index(2 * u + i, 2 * v + j)];
-                            m = (x > m) ? x : m;
-                        }
-                }
-                M_s[e] = m;
+                const double* p0 = hm_s + (2 * (e >> 4)) * (HY / 2) + (e & 15);     // plane of even y, row x = 2a
+                const double* p1 = p0 + HX * (HY / 2);                              // plane of odd y
+                const double m0 = (p0[0] > p0[HY / 2]) ? p0[0] : p0[HY / 2];
+                const double m1 = (p1[0] > p1[HY / 2]) ? p1[0] : p1[HY / 2];
+                P2_s[e] = (m0 > m1) ? m0 : m1;
             }
             __syncthreads();
+            if (tile == 4) {
+                for (int e = tid; e < NPOSE; e += CTA_THREADS) {
+                    double m = -INFINITY;
+                    if ((e >> 4) < AX - 1 && (e & 15) < AY - 1) {
+                        const double m0 = (P2_s[e] > P2_s[e + 1]) ? P2_s[e] : P2_s[e + 1];
+                        const double m1 = (P2_s[e + 16] > P2_s[e + 17]) ? P2_s[e + 16] : P2_s[e + 17];
+                        m = (m0 > m1) ? m0 : m1;
+                    }
+                    M_s[e] = m;
+                }
+                __syncthreads();
+            }
+            const double* Marr = (tile == 4) ? M_s : P2_s;
             for (int r = warp; r < P.R; r += CTA_WARPS)
-                any |= scan_rotation(P, M_s, 16, estage + warp * P.maxwh, env, item, r, lane, err);
+                any |= scan_rotation(P, Marr, 16, estage + warp * P.maxwh, env, item, r, lane, err);
         } else {
             for (int r = warp; r < P.R; r += CTA_WARPS)
                 any |= scan_rotation(P, hm_s, STEP * (HY / 2), estage + warp * P.maxwh, env, item, r, lane, err);
@@ -561,6 +584,69 @@ __global__ void __launch_bounds__(CTA_THREADS) irbpp_levels_kernel(const Params 
     if (threadIdx.x == 0) P.r_error[env] = (uint8_t)err_sh;
 }
 
+// ---- heuristic kernel (space.py:162-227) ---------------------------------------------------------------------
+// One CTA per bin over the scan scratch of the bin's current item: every thread scores the poses
+// e = tid, tid + 128, ... (flat (rot, lx, ly) order), then a lexicographic (score, e) minimum gives
+// np.argmin's first-minimum pose.  Also looks the pose up in the bin's candidate table.
+__global__ void __launch_bounds__(CTA_THREADS) irbpp_heuristic_kernel(const Params P) {
+    __shared__ __align__(16) double hm_s[HX * HY];
+    __shared__ double best_sh[CTA_WARPS];
+    __shared__ int beste_sh[CTA_WARPS];
+    __shared__ int idx_sh;
+    const int env = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int item = P.state[env].cur_item;
+    const int method = P.heur_method;
+    if (method == HEUR_HM) {
+        const double2* src = reinterpret_cast<const double2*>(P.hm + (int64_t)env * (HX * HY));
+        double2* dst = reinterpret_cast<double2*>(hm_s);
+        for (int i = tid; i < HX * HY / 2; i += CTA_THREADS) dst[i] = src[i];
+    }
+    if (tid == 0) idx_sh = 0x7fffffff;
+    __syncthreads();
+    auto hm_at = [&](int x, int y) { return hm_s[hm_index(x, y)]; };
+    double best = INFINITY;
+    int beste = 0x7fffffff;
+    for (int e = tid; e < P.R * NPOSE; e += CTA_THREADS) {
+        const int r = e >> 8, p = e & 255;
+        const bool feas = (P.maskbits[((int64_t)env * P.R + r) * 8 + (p >> 5)] >> (p & 31)) & 1u;
+        double s = HEUR_INVALID;
+        if (feas) {
+            const ShapeRot* sr = P.srot + (int64_t)item * P.R + r;
+            const double z = P.posz[((int64_t)env * P.R + r) * NPOSE + p];
+            s = heuristic_score(method, P.heur_dir, p >> 4, p & 15, z, P.resA, AX, AY, STEP, hm_at,
+                                P.Ts + sr->off, sr->w, sr->h);
+        }
+        if (s < best) { best = s; beste = e; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double s2 = __shfl_xor_sync(0xffffffffu, best, o);
+        const int e2 = __shfl_xor_sync(0xffffffffu, beste, o);
+        if (s2 < best || (s2 == best && e2 < beste)) { best = s2; beste = e2; }
+    }
+    if (lane == 0) { best_sh[warp] = best; beste_sh[warp] = beste; }
+    __syncthreads();
+    best = best_sh[0]; beste = beste_sh[0];
+#pragma unroll
+    for (int k = 1; k < CTA_WARPS; ++k) {
+        const double s2 = best_sh[k]; const int e2 = beste_sh[k];
+        if (s2 < best || (s2 == best && e2 < beste)) { best = s2; beste = e2; }
+    }
+    const uint16_t* cand_g = P.cand + (int64_t)env * P.sel;
+    int first = 0x7fffffff;
+    for (int i = tid; i < P.sel; i += CTA_THREADS)
+        if ((int)cand_g[i] == beste) { first = i; break; }
+    if (first != 0x7fffffff) atomicMin(&idx_sh, first);
+    __syncthreads();
+    if (tid == 0) {
+        P.heur_pose[env * 3 + 0] = beste >> 8;
+        P.heur_pose[env * 3 + 1] = (beste >> 4) & 15;
+        P.heur_pose[env * 3 + 2] = beste & 15;
+        P.heur_index[env] = (idx_sh == 0x7fffffff) ? -1 : idx_sh;
+    }
+}
+
 // ---- candidates kernel ----------------------------------------------------------------------------------
 // One CTA per ENVS_PER_CTA bins, one warp per bin in phase D.  In phase C every (bin, rotation, level)
 // image of the CTA is one lane's task; the tasks are ordered by a cost key (number of border pixels) so
@@ -597,6 +683,7 @@ struct CandSmem {
 __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Params P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CandSmem& S = *reinterpret_cast<CandSmem*>(smem_raw);
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // PDL: scan grid complete, its scratch writes visible
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int env0 = P.env_lo + blockIdx.x * ENVS_PER_CTA;
     const int nenv = min(ENVS_PER_CTA, P.env_hi - env0);

@@ -324,6 +324,52 @@ class GpuVecEnv(VecEnv):
         self._check(self._lib.irbpp_get_all_possible_observation(self._h, out.data_ptr(), self._stream()))
         return out
 
+    HEURISTICS = ("MINZ", "DBLF", "FIRSTFIT", "HM")     # space.py:168-199; ids = IRBPP_HEUR_* (include/irbpp.h)
+
+    def get_heuristic_actions(self, method, dirIdx=0, as_tensor=False):
+        """``Space.get_heuristic_action(dirIdx, method, ...)`` (space.py:162-227) for every env, on the
+        scan of the env's current item.  Returns ``(poses, index)``: int32 [N, 3] (rotIdx, lx, ly) and
+        int64 [N], the row of that pose in the env's candidate table (a valid ``step`` action) or -1
+        when the pose is not a candidate (use ``step_poses`` then).  NumPy arrays, or CUDA tensors
+        without any synchronisation when ``as_tensor``."""
+        if method not in self.HEURISTICS:
+            raise ValueError("unknown heuristic %r (the reference's RANDOM branch raises too)" % (method,))
+        m = self.HEURISTICS.index(method)
+        if as_tensor:
+            torch = self._torch
+            poses = torch.empty((self.num_envs, 3), dtype=torch.int32, device=self.device)
+            index = torch.empty((self.num_envs,), dtype=torch.int64, device=self.device)
+            self._check(self._lib.irbpp_heuristic_actions(self._h, m, int(dirIdx), poses.data_ptr(), index.data_ptr(),
+                                                          1, self._stream()))
+            return poses, index
+        poses = np.empty((self.num_envs, 3), dtype=np.int32)
+        index = np.empty((self.num_envs,), dtype=np.int64)
+        self._check(self._lib.irbpp_heuristic_actions(self._h, m, int(dirIdx), poses.ctypes.data, index.ctypes.data,
+                                                      0, self._stream()))
+        return poses, index
+
+    def step_poses(self, poses):
+        """``step`` with explicit poses: int64 [N] flat ``(rotIdx * Ax + lx) * Ay + ly`` or an [N, 3]
+        array / tensor of (rotIdx, lx, ly) -- what ``action_to_position`` (binPhy.py:234-236) would
+        have read from ``candidates[action]``.  Same return tuple as ``step``."""
+        if self.waiting_step:
+            raise AlreadySteppingError()
+        torch = self._torch
+        if isinstance(poses, torch.Tensor):
+            if poses.dim() == 2:
+                poses = (poses[:, 0].to(torch.int64) * 16 + poses[:, 1].to(torch.int64)) * 16 + poses[:, 2].to(torch.int64)
+        else:
+            poses = np.asarray(poses)
+            if poses.ndim == 2:
+                poses = (poses[:, 0].astype(np.int64) * 16 + poses[:, 1]) * 16 + poses[:, 2]
+            poses = np.ascontiguousarray(poses, dtype=np.int64)
+        keep, ptr, on_dev = self._actions_arg(poses, "poses")
+        obs = self._new_obs(self.obs_len)
+        self._check(self._lib.irbpp_step_poses_async(self._h, ptr, on_dev, obs.data_ptr(), self._stream()))
+        self._obs_pending = (obs, keep)
+        self.waiting_step = True
+        return self.step_wait()
+
     def close_extras(self):
         if getattr(self, "_h", None) is not None and self._h:
             self._lib.irbpp_destroy(self._h)

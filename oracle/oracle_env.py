@@ -216,6 +216,56 @@ def select_candidates(cfg, candidates, posZValid, naiveMask):
 
 
 # ---------------------------------------------------------------------------
+# placement heuristics (space.py:162-227)
+# ---------------------------------------------------------------------------
+
+HEURISTICS = ("MINZ", "DBLF", "FIRSTFIT", "HM")
+
+
+def heuristic_action_port(cfg, lib, heightmap, item_id, posZmap, naiveMask, method, dirIdx):
+    """Restatement of ``Space.get_heuristic_action`` (space.py:162-227): score every pose, 1e6 where
+    ``naiveMask == 0``, ``np.round(score, 6)``, ``np.argmin`` (first minimum in flat (rot, lx, ly)
+    order).  The RANDOM branch of the reference (space.py:220-226) raises on every call
+    (``np.random.choice`` of a tuple) and is not restated.  ``np.sum`` below is NumPy's own pairwise
+    reduction, i.e. the very arithmetic the reference executes."""
+    assert 0 <= dirIdx <= 3                                           # space.py:167
+    Xflip, Yflip = dirIdx >= 2, dirIdx % 2 == 1                       # space.py:163-166
+    R, AX, AY = naiveMask.shape
+    X = np.arange(AX, dtype=np.float64)[:, None].repeat(AY, axis=1)   # coors[:, :, 0]  (space.py:43-47)
+    Y = np.arange(AY, dtype=np.float64)[None, :].repeat(AX, axis=0)
+    coorsX = AX - X if Xflip else X
+    coorsY = AY - Y if Yflip else Y
+    invalid = naiveMask == 0
+    if method == "MINZ":
+        score = posZmap.copy()
+    elif method == "DBLF":
+        score = np.broadcast_to(coorsX + coorsY, naiveMask.shape) * cfg.resolutionAct + 100 * posZmap
+    elif method == "FIRSTFIT":
+        score = np.broadcast_to(coorsX + coorsY, naiveMask.shape).copy()
+    elif method == "HM":
+        score = np.broadcast_to((coorsX + coorsY) * cfg.resolutionAct, naiveMask.shape).copy()
+        score[invalid] = 1e6
+        for r in range(R):
+            T, _, mT, _ = lib.tables[item_id][r]
+            w, h = T.shape
+            for cx in range(AX):
+                for cy in range(AY):
+                    if naiveMask[r, cx, cy] == 0:
+                        continue
+                    z = posZmap[r, cx, cy]
+                    x0, y0 = cx * cfg.stepSize, cy * cfg.stepSize
+                    prime = np.max(((T + z) * mT, heightmap[x0:x0 + w, y0:y0 + h]), axis=0)
+                    score[r, cx, cy] += np.sum(prime) * 100
+    else:
+        raise ValueError(method)
+    score = np.array(score, dtype=np.float64)
+    score[invalid] = 1e6
+    score = np.round(score, decimals=6)
+    rot, lx, ly = np.unravel_index(int(np.argmin(score)), score.shape)
+    return int(rot), int(lx), int(ly)
+
+
+# ---------------------------------------------------------------------------
 # the environment (binPhy.PackingGame with simulation=False semantics)
 # ---------------------------------------------------------------------------
 
@@ -242,6 +292,16 @@ class RefGeometry(object):
     def hull_actions(self, posZValid, naiveMask):
         return self._cv.getConvexHullActions(posZValid, naiveMask, self.cfg.resolutionZ)
 
+    def heuristic_action(self, heightmap, item_id, posZmap, naiveMask, method, dirIdx):
+        """Verbatim ``Space.get_heuristic_action`` (space.py:162-227) on the state of the last scan."""
+        sp = self.space
+        sp.heightmapC = heightmap
+        sp.posZmap[:] = posZmap
+        sp.naiveMask = naiveMask.copy()
+        meshes = [self._mesh(self.lib.extents[item_id, r]) for r in range(self.cfg.ZRotNum)]
+        rot, lx, ly = sp.get_heuristic_action(dirIdx, method, item_id, meshes)
+        return int(rot), int(lx), int(ly)
+
 
 class PortGeometry(object):
     def __init__(self, cfg, lib, scan="vectorized", contours="port"):
@@ -255,6 +315,9 @@ class PortGeometry(object):
 
     def hull_actions(self, posZValid, naiveMask):
         return convex_hull_actions(posZValid, naiveMask, self.cfg.resolutionZ, self._contours)
+
+    def heuristic_action(self, heightmap, item_id, posZmap, naiveMask, method, dirIdx):
+        return heuristic_action_port(self.cfg, self.lib, heightmap, item_id, posZmap, naiveMask, method, dirIdx)
 
 
 class OracleEnv(object):
@@ -336,9 +399,21 @@ class OracleEnv(object):
         self.next_k_item_ID = self._preview(cfg.bufferSize)
         return np.concatenate((np.array(self.next_k_item_ID, dtype=np.float64), self.heightmap.reshape(-1)))
 
+    def heuristic_action(self, method, dirIdx=0):  # space.py:162-227 on the current scan
+        return self.geo.heuristic_action(self.heightmap, self.next_item_ID, self.posZmap, self.naiveMask,
+                                         method, dirIdx)
+
+    def candidate_index(self, pose):
+        """First row of the candidate table holding ``pose`` (rot, lx, ly), -1 if absent."""
+        hit = np.nonzero((self.candidates[:, 0:3] == np.asarray(pose, dtype=np.float64)).all(axis=1))[0]
+        return int(hit[0]) if len(hit) else -1
+
     def step(self, action):  # binPhy.py:248-337 with simulation=False
+        rotIdx, lx, ly = [int(v) for v in self.candidates[int(action)][0:3]]   # action_to_position, :234-236
+        return self.step_pose(rotIdx, lx, ly)
+
+    def step_pose(self, rotIdx, lx, ly):  # PackingGame.step after action_to_position
         cfg = self.cfg
-        rotIdx, lx, ly = [int(v) for v in self.candidates[int(action)][0:3]]
         targetFLB = np.round((lx * cfg.resolutionAct, ly * cfg.resolutionAct, cfg.bin_dimension[2]), decimals=6)
         item = self.next_item_ID
         extents = self.lib.extents[item, rotIdx]
@@ -395,10 +470,20 @@ class OracleVecEnv(object):
     def get_action_candidates(self, order_actions):
         return [e.get_action_candidates(int(a)) for e, a in zip(self.envs, order_actions)]
 
-    def step(self, actions):
+    def heuristic_actions(self, method, dirIdx=0):
+        poses = np.array([e.heuristic_action(method, dirIdx) for e in self.envs], dtype=np.int32)
+        index = np.array([e.candidate_index(p) for e, p in zip(self.envs, poses)], dtype=np.int64)
+        return poses, index
+
+    def step(self, actions, poses=False):
         obs, rews, dones, infos = [], [], [], []
         for i, e in enumerate(self.envs):
-            o, r, d, info = e.step(int(actions[i]))
+            if poses:
+                a = int(actions[i])
+                o, r, d, info = e.step_pose(a // (self.cfg.rangeX_A * self.cfg.rangeY_A),
+                                            (a // self.cfg.rangeY_A) % self.cfg.rangeX_A, a % self.cfg.rangeY_A)
+            else:
+                o, r, d, info = e.step(int(actions[i]))
             self._ep_rewards[i].append(r)
             if d:
                 info["episode"] = {"r": round(sum(self._ep_rewards[i]), 6), "l": len(self._ep_rewards[i])}

@@ -22,7 +22,7 @@ sys.path.insert(0, ROOT)
 
 from irbpp_b200 import shapes  # noqa: E402
 from oracle import ref_loader  # noqa: E402
-from oracle.oracle_env import OracleConfig, OracleVecEnv, RefGeometry  # noqa: E402
+from oracle.oracle_env import HEURISTICS, OracleConfig, OracleVecEnv, RefGeometry  # noqa: E402
 
 
 def lib_arrays(lib, prefix="lib_"):
@@ -191,9 +191,46 @@ def gen_episode(tag, lib, R, n_envs, n_steps, seed, selectedAction=500, bufferSi
     return d
 
 
+def gen_heuristic_episode(tag, lib, R, n_envs, n_steps, seed):
+    """Episodes driven by the reference's own placement heuristics: at every step the verbatim
+    ``Space.get_heuristic_action`` (space.py:162-227) is evaluated for all four scores and all four
+    flip directions on every bin (stored), then the bins are stepped with the pose of one
+    (method, dirIdx), rotating over the sixteen combinations."""
+    cfg = OracleConfig(ZRotNum=R)
+    seqs = shapes.make_sequences(n_envs, 48, lib.num_shapes, seed=seed)
+    vec = OracleVecEnv(cfg, lib, seqs, lambda c, l: RefGeometry(c, l))
+    obs_log = [vec.reset().copy()]
+    pose_log, index_log, act_log, rew_log, done_log = [], [], [], [], []
+    for t in range(n_steps):
+        poses = np.zeros((4, 4, n_envs, 3), np.int32)
+        index = np.zeros((4, 4, n_envs), np.int64)
+        for mi, m in enumerate(HEURISTICS):
+            for d in range(4):
+                poses[mi, d], index[mi, d] = vec.heuristic_actions(m, d)
+        pose_log.append(poses); index_log.append(index)
+        p = poses[t % 4, (t // 4) % 4]
+        acts = (p[:, 0].astype(np.int64) * 16 + p[:, 1]) * 16 + p[:, 2]
+        obs, rew, done, _ = vec.step(acts, poses=True)
+        act_log.append(acts); obs_log.append(obs.copy()); rew_log.append(rew); done_log.append(done)
+    d = lib_arrays(lib)
+    d.update(R=np.array(R), sequences=seqs, poses=np.array(pose_log), index=np.array(index_log),
+             actions=np.array(act_log), obs=np.array(obs_log).astype(np.float32),   # as VecPyTorch casts (envs.py:151,163)
+             reward=np.array(rew_log), done=np.array(done_log))
+    print(tag, "dones", int(np.sum(done_log)), "poses", d["poses"].shape, "not-a-candidate", int((d["index"] < 0).sum()))
+    return d
+
+
 def main():
     assert ref_loader.reference_available(), "needs /root/reference"
     _, space_mod, cv_mod = ref_loader.load_reference()
+    heur = {
+        "heuristic_blockout": gen_heuristic_episode("heur-blockout", shapes.make_blockout_library(16, seed=6), 4, 3, 64, 26),
+        "heuristic_irregular": gen_heuristic_episode("heur-irregular", shapes.make_irregular_library(12, seed=7), 8, 3, 48, 27),
+    }
+    for k, d in heur.items():
+        np.savez_compressed(os.path.join(HERE, k + ".npz"), **d)
+    if "--heuristics-only" in sys.argv:
+        return
     for tag, d in gen_scan_cases(space_mod).items():
         np.savez_compressed(os.path.join(HERE, "scan_%s.npz" % tag), **d)
     np.savez_compressed(os.path.join(HERE, "hulls.npz"), **gen_hull_cases(cv_mod))

@@ -50,3 +50,30 @@ extern "C" void floor_div_many(const double* a, double b, int n, double* out) {
     const double inv = 1.0 / b;
     for (int i = 0; i < n; ++i) out[i] = irbpp::floor_divide_exact(a[i], b, inv);
 }
+
+#include "../../ir-bpp_b200/csrc/irbpp_heuristic.cuh"
+
+// np.sum of n contiguous doubles as irbpp_math.cuh restates it (checked against NumPy itself)
+extern "C" double pairwise_sum_host(const double* a, int n) {
+    auto at = [&](int i) { return a[i]; };
+    return irbpp::np_pairwise_sum(at, n);
+}
+
+// argmin pose of one bin exactly as irbpp_heuristic_kernel scores it (serial): hm row-major [32][32],
+// posz / mask [R][256], top tables with -inf where maskT == 0
+extern "C" int heuristic_pose_host(int method, int dir_idx, int R, const double* hm, const double* posz,
+                                   const uint8_t* mask, const double* Ts, const int64_t* offs, const int32_t* w,
+                                   const int32_t* h, double resA) {
+    auto hm_at = [&](int x, int y) { return hm[x * 32 + y]; };
+    double best = INFINITY;
+    int beste = 0;
+    for (int e = 0; e < R * 256; ++e) {
+        const int r = e >> 8, p = e & 255;
+        double s = irbpp::HEUR_INVALID;
+        if (mask[e])
+            s = irbpp::heuristic_score(method, dir_idx, p >> 4, p & 15, posz[e], resA, 16, 16, 2, hm_at,
+                                       Ts + offs[r], w[r], h[r]);
+        if (s < best) { best = s; beste = e; }
+    }
+    return beste;
+}

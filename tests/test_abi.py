@@ -125,3 +125,52 @@ def test_device_contour_routines_match_oracle(contour_harness):
                 assert maxlen > 32                        # overflow of the 32-point harness buffer only
             n_ovf += rc_cfl
     assert n_ovf > 0                                         # the overflow path was exercised
+
+
+def test_device_pairwise_sum_equals_numpy(contour_harness):
+    """np.sum(heightmapC_Prime) (space.py:217) is a pairwise reduction; the device restatement must
+    associate identically for every window size up to 32 x 32."""
+    contour_harness.pairwise_sum_host.restype = ctypes.c_double
+    rng = np.random.default_rng(5)
+    for n in list(range(0, 300)) + [511, 512, 513, 767, 1000, 1016, 1023, 1024]:
+        for rep in range(3):
+            a = np.ascontiguousarray(rng.random(n) * rng.choice([1.0, 1e-3, 37.0]))
+            got = contour_harness.pairwise_sum_host(a.ctypes.data_as(ctypes.c_void_p), n)
+            assert got == float(np.sum(a)), n
+
+
+def test_device_heuristic_scores_match_oracle(contour_harness):
+    """The per-pose arithmetic of irbpp_heuristic_kernel, compiled for the host, against the oracle's
+    restatement of Space.get_heuristic_action (itself pinned to the reference by tests/golden)."""
+    from irbpp_b200 import shapes
+    from oracle.oracle_env import OracleConfig, OracleVecEnv, HEURISTICS
+    lib = shapes.make_irregular_library(8, seed=5, num_rotations=4)
+    R = lib.num_rotations
+    cfg = OracleConfig(ZRotNum=R)
+    env = OracleVecEnv(cfg, lib, shapes.make_sequences(2, 30, lib.num_shapes, seed=2))
+    env.reset()
+    for t in range(12):
+        acts = []
+        for e in env.envs:
+            item = e.next_item_ID
+            pool, offs, ws, hs = [], [], [], []
+            for r in range(R):
+                T, _, mT, _ = lib.tables[item][r]
+                offs.append(sum(len(p) for p in pool)); ws.append(T.shape[0]); hs.append(T.shape[1])
+                pool.append(np.where(mT != 0, T, -np.inf).reshape(-1))
+            Ts = np.ascontiguousarray(np.concatenate(pool))
+            offs = np.array(offs, np.int64); ws = np.array(ws, np.int32); hs = np.array(hs, np.int32)
+            hm = np.ascontiguousarray(e.heightmap); posz = np.ascontiguousarray(e.posZmap)
+            mask = np.ascontiguousarray(e.naiveMask.astype(np.uint8))
+            for mi, m in enumerate(HEURISTICS):
+                for d in range(4):
+                    got = contour_harness.heuristic_pose_host(
+                        mi, d, R, hm.ctypes.data_as(ctypes.c_void_p), posz.ctypes.data_as(ctypes.c_void_p),
+                        mask.ctypes.data_as(ctypes.c_void_p), Ts.ctypes.data_as(ctypes.c_void_p),
+                        offs.ctypes.data_as(ctypes.c_void_p), ws.ctypes.data_as(ctypes.c_void_p),
+                        hs.ctypes.data_as(ctypes.c_void_p), ctypes.c_double(cfg.resolutionAct))
+                    want = e.heuristic_action(m, d)
+                    assert (got >> 8, (got >> 4) & 15, got & 15) == want, (t, m, d)
+            r_, x_, y_ = e.heuristic_action(HEURISTICS[t % 4], t % 4)
+            acts.append((r_ * 16 + x_) * 16 + y_)
+        env.step(acts, poses=True)

@@ -429,3 +429,82 @@ def test_24_rotations_match_oracle():
         assert np.array_equal(gdone, odone)
     assert max_valid == 500          # with 24 rotations the >selectedAction truncation is the normal case
     env.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["heuristic_blockout", "heuristic_irregular"])
+def test_heuristic_episode_matches_reference_golden(name):
+    """irbpp_heuristic_actions + irbpp_step_poses_async against episodes generated by the reference's own
+    Space.get_heuristic_action (space.py:162-227): every score x flip direction at every step, host and
+    device outputs, then a pose step."""
+    from irbpp_b200.vec_env import GpuVecEnv
+    d = load_golden(name)
+    lib = lib_from_fixture(d)
+    env = _env(lib, d["sequences"])
+    obs = env.reset()
+    assert np.array_equal(obs.cpu().numpy(), d["obs"][0])
+    for t in range(len(d["actions"])):
+        for mi, m in enumerate(GpuVecEnv.HEURISTICS):
+            for k in range(4):
+                poses, index = env.get_heuristic_actions(m, k)
+                assert np.array_equal(poses, d["poses"][t, mi, k]), (t, m, k)
+                assert np.array_equal(index, d["index"][t, mi, k]), (t, m, k)
+        pt, it = env.get_heuristic_actions("HM", t % 4, as_tensor=True)
+        assert pt.is_cuda and np.array_equal(pt.cpu().numpy(), d["poses"][t, 3, t % 4])
+        assert np.array_equal(it.cpu().numpy(), d["index"][t, 3, t % 4])
+        if t % 2:
+            p = d["poses"][t, t % 4, (t // 4) % 4]
+            obs, rew, done, infos = env.step_poses(p)                        # [N, 3] form
+        else:
+            obs, rew, done, infos = env.step_poses(d["actions"][t])         # flat int64 form
+        assert np.array_equal(obs.cpu().numpy(), d["obs"][t + 1]), t
+        assert np.array_equal(rew.numpy()[:, 0], d["reward"][t].astype(np.float32))
+        assert np.array_equal(done, d["done"][t])
+    env.close()
+
+
+@pytest.mark.gpu
+def test_heuristic_policy_matches_oracle_at_scale():
+    """96 bins stepped with the heuristic poses, the method and flip direction changing over time; CUDA path
+    vs the oracle, including auto-resets; plus the call-order errors."""
+    from irbpp_b200 import shapes, _lib
+    from irbpp_b200.vec_env import GpuVecEnv
+    from oracle.oracle_env import OracleConfig, OracleVecEnv
+    lib = shapes.make_irregular_library(16, seed=41, num_rotations=4)
+    seqs = shapes.make_sequences(96, 64, lib.num_shapes, seed=8)
+    ora = OracleVecEnv(OracleConfig(ZRotNum=4), lib, seqs)
+    env = _env(lib, seqs)
+    o = ora.reset(); g = env.reset()
+    ndone = 0
+    for t in range(60):
+        m = GpuVecEnv.HEURISTICS[(t // 5) % 4]
+        po, io = ora.heuristic_actions(m, t % 4)
+        pg, ig = env.get_heuristic_actions(m, t % 4)
+        assert np.array_equal(pg, po) and np.array_equal(ig, io), (t, m)
+        flat = (po[:, 0].astype(np.int64) * 16 + po[:, 1]) * 16 + po[:, 2]
+        o, orew, odone, _ = ora.step(flat, poses=True)
+        g, grew, gdone, _ = env.step_poses(flat)
+        assert np.array_equal(g.cpu().numpy(), o.astype(np.float32)), t
+        assert np.array_equal(gdone, odone)
+        ndone += int(odone.sum())
+    assert ndone > 0
+    # an out-of-range pose is a device error like an out-of-range candidate row
+    bad = np.full(96, 4 * 256, dtype=np.int64)
+    with pytest.raises(RuntimeError):
+        env.step_poses(bad)
+    with pytest.raises(ValueError):
+        env.get_heuristic_actions("RANDOM")
+    env.close()
+    # buffered mode: heuristics need get_action_candidates first
+    seqs2 = shapes.make_sequences(8, 32, lib.num_shapes, seed=9)
+    envb = _env(lib, seqs2, buffer_size=3)
+    envb.reset()
+    with pytest.raises(RuntimeError):
+        envb.get_heuristic_actions("MINZ")
+    envb.get_action_candidates(np.zeros(8, dtype=np.int64))
+    orab = OracleVecEnv(OracleConfig(ZRotNum=4, bufferSize=3), lib, seqs2)
+    orab.reset(); orab.get_action_candidates(np.zeros(8, dtype=np.int64))
+    pg, ig = envb.get_heuristic_actions("DBLF", 1)
+    po, io = orab.heuristic_actions("DBLF", 1)
+    assert np.array_equal(pg, po) and np.array_equal(ig, io)
+    envb.close()
