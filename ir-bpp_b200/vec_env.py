@@ -106,15 +106,24 @@ class Discrete(object):
 
 class LazyInfos(Sequence):
     """``infos`` of one step: behaves like the reference's tuple of N dicts but builds a dict only
-    when indexed (at N = 4096 eagerly building them would dominate the step)."""
+    when indexed (at N = 4096 eagerly building them would dominate the step).  Holds this step's private
+    copy of the library's result block; the typed views are cut out of it on first use."""
 
-    def __init__(self, valid, done, counter, ratio, ep_reward, ep_len, t_rel):
-        self._valid, self._done = valid, done
-        self._counter, self._ratio, self._ep_reward, self._ep_len = counter, ratio, ep_reward, ep_len
-        self._t = t_rel
+    _FIELDS = (("valid", np.bool_), ("counter", np.int32), ("ratio", np.float64),
+               ("ep_reward", np.float64), ("ep_len", np.int32))
+
+    def __init__(self, n, block, offsets, done, t_rel):
+        self._n, self._block, self._offsets, self._done, self._t = n, block, offsets, done, t_rel
+        self._v = None
+
+    def _views(self):
+        if self._v is None:
+            n, b, o = self._n, self._block, self._offsets
+            self._v = {k: b[o[k]:o[k] + n * np.dtype(dt).itemsize].view(dt) for k, dt in self._FIELDS}
+        return self._v
 
     def __len__(self):
-        return len(self._valid)
+        return self._n
 
     def __getitem__(self, i):
         if isinstance(i, slice):
@@ -123,12 +132,13 @@ class LazyInfos(Sequence):
             i += len(self)
         if not 0 <= i < len(self):
             raise IndexError(i)
-        info = {"Valid": bool(self._valid[i])}
+        v = self._views()
+        info = {"Valid": bool(v["valid"][i])}
         if self._done[i]:
             # binPhy.py:306-309 and monitor.py:58-75 (round(eprew, 6) is Python's round, as there)
-            info["counter"] = int(self._counter[i])
-            info["ratio"] = float(self._ratio[i])
-            info["episode"] = {"r": round(float(self._ep_reward[i]), 6), "l": int(self._ep_len[i]), "t": self._t}
+            info["counter"] = int(v["counter"][i])
+            info["ratio"] = float(v["ratio"][i])
+            info["episode"] = {"r": round(float(v["ep_reward"][i]), 6), "l": int(v["ep_len"][i]), "t": self._t}
         return info
 
 
@@ -195,6 +205,10 @@ class GpuVecEnv(VecEnv):
         VecEnv.__init__(self, num_envs, obs_space, act_space)
         self.waiting_step = False
         self._obs_pending = None
+        self._spare_obs = None
+        self._spare_stream = None
+        self._dev_index = idx
+        self._raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
         self._tstart = time.time()
         self._result = _lib.IrbppStepResult()
 
@@ -203,6 +217,11 @@ class GpuVecEnv(VecEnv):
         _lib.check(self._lib, self._h, rc)
 
     def _stream(self):
+        """Raw handle of torch's current stream on this device (queried per call: the caller may switch
+        streams); the private fast accessor when this torch has it."""
+        raw = self._raw_stream
+        if raw is not None:
+            return raw(self._dev_index)
         return self._torch.cuda.current_stream(self.device).cuda_stream
 
     def _new_obs(self, width):
@@ -243,11 +262,19 @@ class GpuVecEnv(VecEnv):
         self._torch.cuda.current_stream(self.device).synchronize()   # `which` is read asynchronously
         return obs
 
+    def _take_obs(self):
+        """Observation buffer of the step being launched: the one ``step_wait`` allocated while the GPU
+        was busy with the previous step, if there is one."""
+        obs, self._spare_obs = self._spare_obs, None
+        if obs is not None and self._spare_stream != self._stream():
+            obs = None                            # allocated under another stream: let the allocator decide
+        return obs if obs is not None else self._new_obs(self.obs_len)
+
     def step_async(self, actions):
         if self.waiting_step:
             raise AlreadySteppingError()
         keep, ptr, on_dev = self._actions_arg(actions, "actions")
-        obs = self._new_obs(self.obs_len)
+        obs = self._take_obs()
         self._check(self._lib.irbpp_step_async(self._h, ptr, on_dev, obs.data_ptr(), self._stream()))
         self._obs_pending = (obs, keep)
         self.waiting_step = True
@@ -261,35 +288,37 @@ class GpuVecEnv(VecEnv):
         self.waiting_step = False
         obs, _ = self._obs_pending
         self._obs_pending = None
+        if self._spare_obs is None:               # host work that does not need the results: while the kernels run
+            self._spare_obs = self._new_obs(self.obs_len)
+            self._spare_stream = self._stream()
+        t_rel = round(time.time() - self._tstart, 6)
         res = self._result
         self._check(self._lib.irbpp_step_wait(self._h, ctypes.byref(res)))
-        v = self._host_views(res)
-        reward = v["reward"].copy()
-        done = v["done"].copy()
-        infos = LazyInfos(v["valid"].copy(), done, v["counter"].copy(), v["ratio"].copy(), v["ep_reward"].copy(),
-                          v["ep_len"].copy(), round(time.time() - self._tstart, 6))
+        src, offs = self._result_block(res)
+        n = self.num_envs
+        block = src.copy()                        # one copy of the pinned block; everything else is a view of it
+        reward = block[offs["reward"]:offs["reward"] + 4 * n].view(np.float32)
+        done = block[offs["done"]:offs["done"] + n].view(np.bool_)
+        infos = LazyInfos(n, block, offs, done, t_rel)
         return obs, torch.from_numpy(reward).unsqueeze(dim=1), done, infos
 
-    def _host_views(self, res):
-        """NumPy views of the library's pinned result block (fixed addresses for the life of the handle;
-        built once -- constructing them per step costs more than the kernels' launch)."""
+    _RESULT_BYTES = (("ratio", 8), ("ep_reward", 8), ("reward", 4), ("counter", 4), ("ep_len", 4),
+                     ("done", 1), ("valid", 1), ("error", 1))
+
+    def _result_block(self, res):
+        """uint8 view of the library's pinned result block and the byte offset of every array in it (from
+        the pointers of ``irbpp_step_result``; fixed for the life of the handle, so built once)."""
         key = (res.reward, res.done)
-        if getattr(self, "_views_key", None) != key:
+        if getattr(self, "_block_key", None) != key:
             n = self.num_envs
-
-            def view(ptr, ctype, dtype):
-                buf = (ctype * n).from_address(ptr)
-                return np.frombuffer(buf, dtype=dtype, count=n)
-
-            self._views = {"reward": view(res.reward, ctypes.c_float, np.float32),
-                           "done": view(res.done, ctypes.c_uint8, np.bool_),
-                           "valid": view(res.valid, ctypes.c_uint8, np.bool_),
-                           "counter": view(res.counter, ctypes.c_int32, np.int32),
-                           "ep_len": view(res.ep_len, ctypes.c_int32, np.int32),
-                           "ratio": view(res.ratio, ctypes.c_double, np.float64),
-                           "ep_reward": view(res.ep_reward, ctypes.c_double, np.float64)}
-            self._views_key = key
-        return self._views
+            ptrs = {k: getattr(res, k) for k, _ in self._RESULT_BYTES}
+            base = min(ptrs.values())
+            end = max(ptrs[k] + n * sz for k, sz in self._RESULT_BYTES)
+            buf = (ctypes.c_uint8 * (end - base)).from_address(base)
+            self._block_src = np.frombuffer(buf, dtype=np.uint8)
+            self._block_offs = {k: ptrs[k] - base for k, _ in self._RESULT_BYTES}
+            self._block_key = key
+        return self._block_src, self._block_offs
 
     def step_device(self, actions):
         """Device-resident loop: ``actions`` is a CUDA int64 tensor; nothing is copied to the host and
@@ -364,7 +393,7 @@ class GpuVecEnv(VecEnv):
                 poses = (poses[:, 0].astype(np.int64) * 16 + poses[:, 1]) * 16 + poses[:, 2]
             poses = np.ascontiguousarray(poses, dtype=np.int64)
         keep, ptr, on_dev = self._actions_arg(poses, "poses")
-        obs = self._new_obs(self.obs_len)
+        obs = self._take_obs()
         self._check(self._lib.irbpp_step_poses_async(self._h, ptr, on_dev, obs.data_ptr(), self._stream()))
         self._obs_pending = (obs, keep)
         self.waiting_step = True
