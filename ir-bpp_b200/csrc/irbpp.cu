@@ -133,7 +133,7 @@ int irbpp_create(const irbpp_config* cfg, irbpp_handle* out) {
     P.resA = cfg->resolution_act;
     P.binvol = (cfg->bin_dimension[0] * cfg->bin_dimension[1]) * cfg->bin_dimension[2];   // np.prod
     P.ws_bytes = ws_bytes_for(P.R);
-    h->cand_smem = (int)((sizeof(CandSmem) + 15) & ~(size_t)15) + CAND_WARPS * P.ws_bytes;
+    h->cand_smem = (int)((sizeof(CandSmem) + 15) & ~(size_t)15) + CAND_WARPS * P.ws_bytes + ENVS_PER_CTA * P.R * 8 * 4;
 
 #define TRY_ALLOC(expr)                                                                          \
     do { cudaError_t e2_ = (expr); if (e2_ != cudaSuccess) {                                      \

@@ -5,17 +5,16 @@
 //   cvTools.py:91  cv2.approxPolyDP(contour, 1, True)
 //   cvTools.py:92  find_convex_vetex (:40-59)
 // (paths relative to the reference root).  Algorithms: border following with the outer start rule of
-// Suzuki-Abe and the CHAIN_APPROX_SIMPLE emission rule, in a component-first formulation that never
-// follows hole borders (see below); Douglas-Peucker with OpenCV's closed-curve seeding and clean-up
-// pass.  All arithmetic is integer (coordinates are 0..15), so there is nothing to round: the float
+// Suzuki-Abe and the CHAIN_APPROX_SIMPLE emission rule, one independent task per start pixel (see
+// below); Douglas-Peucker with OpenCV's closed-curve seeding and clean-up pass.  All arithmetic is integer (coordinates are 0..15), so there is nothing to round: the float
 // comparisons OpenCV performs are between exactly representable values and are restated as integer
 // cross-multiplications.
 //
-// The level image is 8 words, two 16-bit rows per word (row y = bits (y&1)*16.. of word y>>1, bit x =
-// column x).  Border following works on the 8-neighbourhood ring of the current pixel (one byte built
-// from three row words) instead of probing pixels one by one.  The code is templated on a scratch
-// accessor so the same routine serves the fast path (one thread per (rotation, level) task, <= 64
-// point contours, kept-set in a 64-bit register) and the overflow path (one thread, long buffers).
+// The followers read the level image in padded row form (ROWS_WORDS words, see below).  Border
+// following works on the 8-neighbourhood ring of the current pixel (one byte built from three row
+// words) instead of probing pixels one by one.  The code is templated on a scratch accessor so the
+// same routine serves the fast path (one lane per start pixel, <= 64 point contours, kept-set in a
+// 64-bit register) and the overflow path (one thread, long buffers).
 #pragma once
 #include <stdint.h>
 #include <type_traits>
@@ -32,22 +31,13 @@ __device__ __forceinline__ int ddy(int s) {
     return (int)((0xA901u >> (2 * s)) & 3u) - 1;
 }
 
-// row y of the image as 16 bits, 0 outside the image
-__device__ __forceinline__ uint32_t row16(const uint32_t* bm, int y) {
-    return ((unsigned)y < 16u) ? ((bm[y >> 1] >> ((y & 1) * 16)) & 0xFFFFu) : 0u;
-}
-
 // ---- scratch accessors -------------------------------------------------------------------------
-// marks: one word per image row, bit x = pixel (x, y) has been visited by a followed border.
 template <int STRIDE, int CAP_>
 struct StridedScratch {
     static constexpr int CAP = CAP_;
     static_assert(CAP_ <= 64, "kept-set is one register pair at most");
-    uint32_t* w;   // 16 mark rows, element stride STRIDE
     uint8_t* b;    // CAP contour points, element stride STRIDE
     typename std::conditional<(CAP_ <= 32), uint32_t, uint64_t>::type kept;
-    __device__ __forceinline__ uint32_t mk(int y) const { return w[y * STRIDE]; }
-    __device__ __forceinline__ void set_mk(int y, uint32_t v) { w[y * STRIDE] = v; }
     __device__ __forceinline__ int pt(int i) const { return b[i * STRIDE]; }
     __device__ __forceinline__ void set_pt(int i, int v) { b[i * STRIDE] = (uint8_t)v; }
     __device__ __forceinline__ void kept_clear(int) { kept = 0; }
@@ -72,10 +62,7 @@ struct StridedScratch {
 template <int CAP_>
 struct FlatScratch {
     static constexpr int CAP = CAP_;
-    uint32_t* w;     // 16 mark words
     uint8_t* b;      // CAP points, CAP kept flags
-    __device__ __forceinline__ uint32_t mk(int y) const { return w[y]; }
-    __device__ __forceinline__ void set_mk(int y, uint32_t v) { w[y] = v; }
     __device__ __forceinline__ int pt(int i) const { return b[i]; }
     __device__ __forceinline__ void set_pt(int i, int v) { b[i] = (uint8_t)v; }
     __device__ __forceinline__ void kept_clear(int n) { for (int i = 0; i < n; ++i) b[CAP + i] = 0; }
@@ -87,65 +74,6 @@ struct FlatScratch {
         return k;
     }
 };
-
-// ---- border following ------------------------------------------------------------------------------------
-// 8-neighbourhood ring of a pixel from the three (padded) image rows around it
-__device__ __forceinline__ uint32_t ring_from_rows(uint32_t rm, uint32_t r0, uint32_t rp, int x) {
-    const uint32_t wm = (rm >> x) & 7u;   // bit0 = col x-1, bit1 = col x, bit2 = col x+1
-    const uint32_t w0 = (r0 >> x) & 7u;
-    const uint32_t wp = (rp >> x) & 7u;
-    const uint32_t rev = ((wm & 1u) << 2) | (wm & 2u) | (wm >> 2);   // NE, N, NW in direction order
-    return (w0 >> 2) | (rev << 1) | ((w0 & 1u) << 4) | (wp << 5);
-}
-
-// Outer-rule border follower used by the component-first formulation below: starts at (x0, y0) whose
-// W, NW, N, NE neighbours are background, follows the border with the outer start rule, sets the
-// "visited" bit of every pixel it passes, stores the CHAIN_APPROX_SIMPLE points and accumulates twice
-// the signed area of the closed path (<= 0: the path is an outer border; > 0: it ran around a hole).
-template <class S>
-__device__ int follow_outer(S& sc, const uint32_t* bm, int x0, int y0, int& area2) {
-    uint32_t rm = row16(bm, y0 - 1) << 1, r0 = row16(bm, y0) << 1, rp = row16(bm, y0 + 1) << 1;
-    uint32_t ring = ring_from_rows(rm, r0, rp, x0);
-    area2 = 0;
-    sc.set_mk(y0, sc.mk(y0) | (1u << x0));
-    if (!ring) {  // isolated pixel
-        sc.set_pt(0, (x0 << 4) | y0);
-        return 1;
-    }
-    int s;
-    {   // clockwise search from direction 3 down to 4: highest set bit of the ring rotated by 4
-        const uint32_t r2 = ((ring | (ring << 8)) >> 4) & 0xFFu;
-        s = (4 + (31 - __clz((int)r2))) & 7;
-    }
-    const int x1 = x0 + ddx(s), y1 = y0 + ddy(s);
-    int x3 = x0, y3 = y0;
-    int prev_s = s ^ 4;
-    int n = 0, a2 = 0;
-    bool ovf = false;
-    for (;;) {
-        const int s_end = s;
-        const uint32_t rot = ((ring | (ring << 8)) >> ((s_end + 1) & 7)) & 0xFFu;
-        s = (s_end + __ffs((int)rot)) & 7;
-        const int dy = ddy(s);
-        const int x4 = x3 + ddx(s), y4 = y3 + dy;
-        a2 += x3 * y4 - x4 * y3;
-        if (s != prev_s) {
-            if (n < S::CAP) sc.set_pt(n, (x3 << 4) | y3);
-            else ovf = true;
-            ++n;
-        }
-        prev_s = s;
-        if (x4 == x0 && y4 == y0 && x3 == x1 && y3 == y1) break;
-        if (dy > 0) { rm = r0; r0 = rp; rp = row16(bm, y4 + 1) << 1; }
-        else if (dy < 0) { rp = r0; r0 = rm; rm = row16(bm, y4 - 1) << 1; }
-        x3 = x4; y3 = y4;
-        sc.set_mk(y3, sc.mk(y3) | (1u << x3));
-        s = (s + 4) & 7;
-        ring = ring_from_rows(rm, r0, rp, x3);
-    }
-    area2 = a2;
-    return ovf ? -1 : n;
-}
 
 // ---- approxPolyDP(eps = 1, closed) + convex-vertex filter ---------------------------------------
 // Emits the selected vertices through `emit(x, y)`.
@@ -204,21 +132,40 @@ __device__ void approx_and_emit(S& sc, int n, bool legacy, Emit emit) {
             const int seg2 = dx * dx + dy * dy;
             int best = -1, bi = s;
             int k = s;
-            for (int t = 1; t < len; ++t) {
-                k = (k + 1 == n) ? 0 : k + 1;
-                const int p = sc.pt(k);
-                const int vx = (p >> 4) - sx, vy = (p & 15) - sy;
-                // dist^2 to the segment times seg2 (4.13 rule) or |cross| (legacy line rule), select form
-                const int cr = vy * dx - vx * dy;
-                const int d2 = vx * vx + vy * vy;
-                const int dot = vx * dx + vy * dy;
-                const int wx = vx - dx, wy = vy - dy;
-                int num = cr * cr;                                            // projection inside the segment
-                num = (dot >= seg2) ? (wx * wx + wy * wy) * seg2 : num;      // beyond the end point
-                num = (dot <= 0) ? d2 * seg2 : num;                          // before the start point
-                num = (seg2 == 0) ? d2 : num;                                // degenerate segment
-                num = legacy ? (cr < 0 ? -cr : cr) : num;
-                if (num > best) { best = num; bi = k; }
+            // Squared distance to the segment times seg2 (4.13 rule).  With cr = v x d and dot = v . d,
+            // |v|^2 |d|^2 = cr^2 + dot^2 (Lagrange), and for w = v - d: w x d = cr, w . d = dot - seg2, so
+            //   inside the segment: cr^2;  before its start: cr^2 + dot^2;  beyond its end: cr^2 + (dot - seg2)^2
+            // i.e. cr^2 + t^2 with t = dot - clamp(dot, 0, seg2): identical integers to the three-case form.
+            // A degenerate segment (seg2 == 0) uses |v|^2, the legacy line rule |cr|.
+            if (legacy) {
+                for (int t = 1; t < len; ++t) {
+                    k = (k + 1 == n) ? 0 : k + 1;
+                    const int p = sc.pt(k);
+                    const int vx = (p >> 4) - sx, vy = (p & 15) - sy;
+                    const int cr = vy * dx - vx * dy;
+                    const int num = cr < 0 ? -cr : cr;
+                    if (num > best) { best = num; bi = k; }
+                }
+            } else if (seg2 == 0) {
+                for (int t = 1; t < len; ++t) {
+                    k = (k + 1 == n) ? 0 : k + 1;
+                    const int p = sc.pt(k);
+                    const int vx = (p >> 4) - sx, vy = (p & 15) - sy;
+                    const int num = vx * vx + vy * vy;
+                    if (num > best) { best = num; bi = k; }
+                }
+            } else {
+                for (int t = 1; t < len; ++t) {
+                    k = (k + 1 == n) ? 0 : k + 1;
+                    const int p = sc.pt(k);
+                    const int vx = (p >> 4) - sx, vy = (p & 15) - sy;
+                    const int cr = vy * dx - vx * dy;
+                    const int dot = vx * dx + vy * dy;
+                    const int cl = dot < 0 ? 0 : (dot > seg2 ? seg2 : dot);
+                    const int tt = dot - cl;
+                    const int num = cr * cr + tt * tt;
+                    if (num > best) { best = num; bi = k; }
+                }
             }
             bool le;
             if (legacy) le = (best * best <= seg2);
@@ -317,77 +264,21 @@ __device__ void approx_and_emit(S& sc, int n, bool legacy, Emit emit) {
     }
 }
 
-// ---- component-first formulation ------------------------------------------------------------------------
+// ---- start pixels ------------------------------------------------------------------------------------------
 // cv2.findContours(RETR_TREE) + find_out_contour keep exactly one contour per 8-connected foreground
 // component (nested islands included): its outer border, followed from the component's raster-first
-// pixel.  That pixel has background at W, NW, N and NE.  Instead of following every hole border just to
-// maintain Suzuki's labels, every unvisited pixel with that local property is tried as a start: if it is
-// a component's first pixel the path is the outer border (signed area <= 0); the only other
-// possibility is a pixel on a hole border of an already followed component, whose path runs the other
-// way round (signed area > 0) and is dropped.  Plain holes (e.g. rectangular footprints inside a level
-// set) contain no such pixel and are never followed at all.
-__device__ __forceinline__ uint32_t start_candidates(const uint32_t* bm, int y, uint32_t visited) {
-    const uint32_t f = row16(bm, y);
-    const uint32_t up = row16(bm, y - 1);
-    return f & ~(f << 1) & ~(up | (up << 1) | (up >> 1)) & ~visited & 0xFFFFu;
-}
+// pixel.  That pixel has background at W, NW, N and NE; every pixel with that local property is a start
+// candidate (bit mask per row below).
+// Padded row form of a level image (what the followers read): ROWS_WORDS words, rows[y + 1] = (row y) << 1
+// (bit x + 1 = column x), rows[0] = rows[17] = 0, one pad word: no bounds tests, no half-word extraction.
+constexpr int ROWS_WORDS = 19;
 
-template <class S, class Emit>
-__device__ bool process_level_image_cf(S& sc, const uint32_t* bm, bool legacy, Emit emit) {
-    for (int y = 0; y < 16; ++y) sc.set_mk(y, 0u);
-    bool ok = true;
-    for (int y = 0; y < 16; ++y) {
-        for (;;) {
-            const uint32_t c = start_candidates(bm, y, sc.mk(y));
-            if (!c) break;
-            const int x = __ffs((int)c) - 1;
-            int area2;
-            const int n = follow_outer(sc, bm, x, y, area2);
-            if (area2 <= 0) {
-                if (n < 0) ok = false;
-                else approx_and_emit(sc, n, legacy, emit);
-            }
-        }
-    }
-    return ok;
+// start-candidate mask of row y from the row and the row above it (16-bit, unshifted)
+__device__ __forceinline__ uint32_t start_mask(uint32_t f, uint32_t up) {
+    return f & ~(f << 1) & ~(up | (up << 1) | (up >> 1)) & 0xFFFFu;
 }
-
-// Warp lock-step variant (all 32 lanes call it; has_task = false for idle lanes): every lane finds its
-// next start, then all lanes follow their borders together, then all approximate together.
-template <class S, class Emit>
-__device__ bool process_level_image_cf_lockstep(S& sc, const uint32_t* bm, bool has_task, bool legacy, Emit emit,
-                                                long long* tm = nullptr) {
-    bool active = has_task;
-    bool ok = true;
-    int y = 0;
-    if (active) { for (int q = 0; q < 16; ++q) sc.set_mk(q, 0u); }
-    for (;;) {
-        long long t0 = 0;
-        if (tm) t0 = clock64();
-        int x = 0;
-        if (active) {
-            bool found = false;
-            while (y < 16) {
-                const uint32_t c = start_candidates(bm, y, sc.mk(y));
-                if (c) { x = __ffs((int)c) - 1; found = true; break; }
-                ++y;
-            }
-            active = found;
-        }
-        if (!__any_sync(0xffffffffu, active)) break;
-        long long t1 = 0;
-        if (tm) { t1 = clock64(); tm[0] += t1 - t0; }
-        int n = 0, area2 = 1;
-        if (active) n = follow_outer(sc, bm, x, y, area2);
-        long long t2 = 0;
-        if (tm) { __syncwarp(); t2 = clock64(); tm[1] += t2 - t1; }
-        if (active && area2 <= 0) {
-            if (n < 0) ok = false;
-            else approx_and_emit(sc, n, legacy, emit);
-        }
-        if (tm) { __syncwarp(); tm[2] += clock64() - t2; }
-    }
-    return ok;
+__device__ __forceinline__ uint32_t start_candidates_rows(const uint32_t* rows, int y) {
+    return start_mask(rows[y + 1] >> 1, rows[y] >> 1);
 }
 
 // ---- micro-task formulation -------------------------------------------------------------------------------
@@ -400,9 +291,16 @@ __device__ bool process_level_image_cf_lockstep(S& sc, const uint32_t* bm, bool 
 // Returns the number of stored points (>= 1), -1 if the contour exceeded S::CAP, or -2 if the path
 // was abandoned (not a raster-first start) -- in which case nothing must be emitted.
 template <class S>
-__device__ int follow_outer_from(S& sc, const uint32_t* bm, int x0, int y0, int& area2) {
-    uint32_t rm = row16(bm, y0 - 1) << 1, r0 = row16(bm, y0) << 1, rp = row16(bm, y0 + 1) << 1;
-    uint32_t ring = ring_from_rows(rm, r0, rp, x0);
+__device__ int follow_outer_rows(S& sc, const uint32_t* rows, int x0, int y0, int& area2) {
+    // 8-neighbourhood ring of pixel (x, y), bit d = neighbour in direction d
+    auto ring_at = [&](int x, int y) -> uint32_t {
+        const uint32_t wm = (rows[y] >> x) & 7u;        // bit0 = col x-1, bit1 = col x, bit2 = col x+1
+        const uint32_t w0 = (rows[y + 1] >> x) & 7u;
+        const uint32_t wp = (rows[y + 2] >> x) & 7u;
+        const uint32_t lo = (w0 >> 2) | ((wm & 4u) >> 1) | ((wm & 2u) << 1) | ((wm & 1u) << 3);   // E, NE, N, NW
+        return lo | ((w0 & 1u) << 4) | (wp << 5);                                                    // W, SW, S, SE
+    };
+    uint32_t ring = ring_at(x0, y0);
     area2 = 0;
     if (!ring) {  // isolated pixel
         sc.set_pt(0, (x0 << 4) | y0);
@@ -413,57 +311,53 @@ __device__ int follow_outer_from(S& sc, const uint32_t* bm, int x0, int y0, int&
         const uint32_t r2 = ((ring | (ring << 8)) >> 4) & 0xFFu;
         s = (4 + (31 - __clz((int)r2))) & 7;
     }
-    const int x1 = x0 + ddx(s), y1 = y0 + ddy(s);
+    const int p0 = (y0 << 5) | x0;                       // raster order == numeric order of (y << 5 | x)
+    const int p1 = p0 + (ddy(s) << 5) + ddx(s);          // the pixel the walk returns from
     int x3 = x0, y3 = y0;
     int prev_s = s ^ 4;
     int n = 0, a2 = 0;
-    bool ovf = false;
     for (;;) {
-        const int s_end = s;
-        const uint32_t rot = ((ring | (ring << 8)) >> ((s_end + 1) & 7)) & 0xFFu;
-        s = (s_end + __ffs((int)rot)) & 7;
-        const int dy = ddy(s);
-        const int x4 = x3 + ddx(s), y4 = y3 + dy;
-        if (y4 < y0 || (y4 == y0 && x4 < x0)) return -2;      // a pixel of this border precedes the start
+        const uint32_t rot = ((ring * 0x101u) >> ((s + 1) & 7)) & 0xFFu;     // s points back to the previous pixel
+        s = (s + __ffs((int)rot)) & 7;
+        const int x4 = x3 + ddx(s), y4 = y3 + ddy(s);
+        const int p4 = (y4 << 5) | x4;
+        if (p4 < p0) return -2;                          // a pixel of this border precedes the start
         a2 += x3 * y4 - x4 * y3;
         if (s != prev_s) {
             if (n < S::CAP) sc.set_pt(n, (x3 << 4) | y3);
-            else ovf = true;
             ++n;
         }
         prev_s = s;
-        if (x4 == x0 && y4 == y0 && x3 == x1 && y3 == y1) break;
-        if (dy > 0) { rm = r0; r0 = rp; rp = row16(bm, y4 + 1) << 1; }
-        else if (dy < 0) { rp = r0; r0 = rm; rm = row16(bm, y4 - 1) << 1; }
+        if (p4 == p0 && ((y3 << 5) | x3) == p1) break;
         x3 = x4; y3 = y4;
-        s = (s + 4) & 7;
-        ring = ring_from_rows(rm, r0, rp, x3);
+        s ^= 4;
+        ring = ring_at(x3, y3);
     }
     area2 = a2;
-    return ovf ? -1 : n;
+    return (n > S::CAP) ? -1 : n;
 }
 
 // one micro-task: returns false only when the contour overflowed S::CAP points
 template <class S, class Emit>
-__device__ bool process_start_candidate(S& sc, const uint32_t* bm, int x, int y, bool legacy, Emit emit) {
+__device__ bool process_start_candidate(S& sc, const uint32_t* rows, int x, int y, bool legacy, Emit emit) {
     int area2;
-    const int n = follow_outer_from(sc, bm, x, y, area2);
+    const int n = follow_outer_rows(sc, rows, x, y, area2);
     if (n == -2 || area2 > 0) return true;       // not a raster-first start, or a hole border
     if (n < 0) return false;
     approx_and_emit(sc, n, legacy, emit);
     return true;
 }
 
-// whole image, serially (overflow path and host validation)
+// whole image, serially (host validation of the routines above)
 template <class S, class Emit>
-__device__ bool process_level_image_mt(S& sc, const uint32_t* bm, bool legacy, Emit emit) {
+__device__ bool process_level_image_mt(S& sc, const uint32_t* rows, bool legacy, Emit emit) {
     bool ok = true;
     for (int y = 0; y < 16; ++y) {
-        uint32_t c = start_candidates(bm, y, 0u);
+        uint32_t c = start_candidates_rows(rows, y);
         while (c) {
             const int x = __ffs((int)c) - 1;
             c &= c - 1;
-            ok &= process_start_candidate(sc, bm, x, y, legacy, emit);
+            ok &= process_start_candidate(sc, rows, x, y, legacy, emit);
         }
     }
     return ok;

@@ -61,7 +61,7 @@ static_assert(CAND_WARPS >= ENVS_PER_CTA, "phase D needs one warp per bin");
 constexpr int TASK_LANES = IRBPP_TASK_LANES;          // lanes of a warp that carry a level image in phase C
 constexpr int ROUND_TASKS = ENVS_PER_CTA * TASK_LANES; // level images a CTA processes per round
 constexpr int MAX_LEVELS = 64;           // level-image slots per (bin, rotation) in the scratch
-constexpr int SLOT_WORDS = 9;            // 8 bitmap words + 1 pad (bank spread) in shared memory
+constexpr int TASK_TAB = 256;            // start pixels of a round listed explicitly (the rest are found by search)
 constexpr int FAST_CAP = 64;             // contour points on the fast path (32 was measured slower: every overflow redo stalls a warp)
 constexpr int BIG_CAP = 1024;            // contour points on the overflow path
 constexpr int LEVEL_OFFSET = 32;         // levels in [-32, 31] -> presence bit (level + 32)
@@ -659,14 +659,15 @@ __global__ void __launch_bounds__(CTA_THREADS) irbpp_heuristic_kernel(const Para
 // size grows with the rotation count (a bin can have up to R * 256 candidates).
 constexpr int WS_MIN_BYTES = 4096;
 static_assert(WS_MIN_BYTES >= 2 * BIG_CAP && WS_MIN_BYTES >= FAST_CAP * 32, "overflow buffers must fit the lane scratch");
+static_assert(CAND_THREADS * ROWS_WORDS >= ENVS_PER_CTA * 128, "phase D's rank histograms reuse the image slots");
 __host__ __device__ inline int ws_bytes_for(int R) {
     const int need = R * NPOSE * 4;                      // uint16 list + uint16 sorted list for every pose
     return ((need > WS_MIN_BYTES ? need : WS_MIN_BYTES) + 15) & ~15;
 }
 
 struct CandSmem {
-    uint32_t slots[CAND_THREADS * SLOT_WORDS];            // level images of this round (one per thread)
-    uint32_t candbits[ENVS_PER_CTA * MAX_ROT * 8];        // 256-bit candidate set per (bin, rotation)
+    uint32_t slots[CAND_THREADS * ROWS_WORDS];            // level images of this round in padded row form (one per thread)
+    uint16_t task_tab[TASK_TAB];                          // micro-task m < TASK_TAB: slot << 8 | x << 4 | y of its start pixel
     int32_t pre[ENVS_PER_CTA * MAX_ROT + 1];              // prefix of level counts over (bin, rotation)
     int32_t cand_off[CAND_THREADS + 1];                   // prefix of start-candidate counts over the images, in cost order
     uint16_t slot_of[CAND_THREADS];                       // image slot at each position of the cost order
@@ -677,7 +678,6 @@ struct CandSmem {
     uint16_t pair_of[CAND_THREADS];                       // (bin, rotation) pair of image t
     int32_t warp_tot[CAND_WARPS];
     int32_t error[ENVS_PER_CTA];
-    int32_t rank_hist[ENVS_PER_CTA][128];                 // phase D truncation: bucket bases / cursors per warp
 };
 
 __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Params P) {
@@ -699,7 +699,9 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
     };
     auto env_live = [&](int e) { return !(P.mode == MODE_RESET && P.which && !P.which[e]); };
 
-    for (int i = tid; i < ENVS_PER_CTA * R * 8; i += CAND_THREADS) S.candbits[i] = 0u;
+    // dynamic tail: CAND_WARPS blocks of P.ws_bytes, then the 256-bit candidate sets per (bin, rotation)
+    uint32_t* candbits = reinterpret_cast<uint32_t*>(smem_raw + ((sizeof(CandSmem) + 15) & ~(size_t)15) + (size_t)CAND_WARPS * P.ws_bytes);
+    for (int i = tid; i < ENVS_PER_CTA * R * 8; i += CAND_THREADS) candbits[i] = 0u;
     if (tid < ENVS_PER_CTA) S.error[tid] = 0;
     if (warp == 0) {   // prefix of the level counts over the (bin, rotation) pairs, 32 pairs per step
         int carry = 0;
@@ -726,6 +728,7 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
         // 1. thread t loads image t, counts its start candidates (background at W, NW, N, NE) and a cost key
         //    (foreground/background transitions ~ border length)
         int cnt = 0, bucket = 63, my_off = 0;
+        uint32_t wv[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};   // this thread's image, two 16-bit rows per word
         if (tid < 64) S.hist[tid] = 0;
         __syncthreads();
         if (tid < nround) {
@@ -735,17 +738,18 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
             const uint4* src = reinterpret_cast<const uint4*>(
                 P.bitmaps + (((int64_t)env0 * R + lo) * MAX_LEVELS + (t - S.pre[lo])) * 8);
             const uint4 a = src[0], b = src[1];
-            uint32_t* bm = S.slots + tid * SLOT_WORDS;
-            bm[0] = a.x; bm[1] = a.y; bm[2] = a.z; bm[3] = a.w; bm[4] = b.x; bm[5] = b.y; bm[6] = b.z; bm[7] = b.w;
+            uint32_t* rows = S.slots + tid * ROWS_WORDS;
             S.pair_of[tid] = (uint16_t)lo;
-            const uint32_t wv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            wv[0] = a.x; wv[1] = a.y; wv[2] = a.z; wv[3] = a.w; wv[4] = b.x; wv[5] = b.y; wv[6] = b.z; wv[7] = b.w;
+            rows[0] = 0u; rows[17] = 0u;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { rows[1 + 2 * k] = (wv[k] & 0xFFFFu) << 1; rows[2 + 2 * k] = (wv[k] >> 16) << 1; }
             uint32_t up = 0;
             int key = 0;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const uint32_t r0 = wv[k] & 0xFFFFu, r1 = wv[k] >> 16;
-                cnt += __popc(r0 & ~(r0 << 1) & ~(up | (up << 1) | (up >> 1)) & 0xFFFFu);
-                cnt += __popc(r1 & ~(r1 << 1) & ~(r0 | (r0 << 1) | (r0 >> 1)) & 0xFFFFu);
+                cnt += __popc(start_mask(r0, up)) + __popc(start_mask(r1, r0));
                 key += __popc(r0 ^ (r0 << 1)) + __popc(r1 ^ (r1 << 1)) + __popc(r0 ^ up) + __popc(r1 ^ r0);
                 up = r1;
             }
@@ -767,11 +771,12 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
         }
         __syncthreads();
         // position in cost order -> (slot, count); cand_off[] temporarily holds the counts
+        int my_pos = 0;
         if (tid < nround) {
-            const int pos = S.hbase[bucket] + my_off;
-            S.slot_of[pos] = (uint16_t)tid;
-            S.cand_off[pos + 1] = cnt;
-        } 
+            my_pos = S.hbase[bucket] + my_off;
+            S.slot_of[my_pos] = (uint16_t)tid;
+            S.cand_off[my_pos + 1] = cnt;
+        }
         for (int i = nround + tid; i < CAND_THREADS; i += CAND_THREADS) S.cand_off[i + 1] = 0;
         __syncthreads();
         {   // CTA-wide inclusive prefix of the counts in cost order
@@ -788,36 +793,58 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
         }
         __syncthreads();
         const int ntask = S.cand_off[CAND_THREADS];
+        // every image lists its start pixels (raster order) at its offset of the task table, so that a
+        // micro-task lane finds its pixel with one load
+        if (tid < nround && cnt > 0) {
+            int off = S.cand_off[my_pos];
+            uint32_t up = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t r0 = wv[k] & 0xFFFFu, r1 = wv[k] >> 16;
+                uint32_t c = start_mask(r0, up);
+                while (c && off < TASK_TAB) { S.task_tab[off++] = (uint16_t)((tid << 8) | ((__ffs((int)c) - 1) << 4) | (2 * k)); c &= c - 1; }
+                c = start_mask(r1, r0);
+                while (c && off < TASK_TAB) { S.task_tab[off++] = (uint16_t)((tid << 8) | ((__ffs((int)c) - 1) << 4) | (2 * k + 1)); c &= c - 1; }
+                up = r1;
+            }
+        }
+        __syncthreads();
+#ifdef IRBPP_PROBE_FINE
+        phase_mark(4);   // prologue, image loads, cost sort, start-pixel prefix
+#else
         if (P.phase_cycles && tid == 0) { atomicAdd(P.phase_cycles + 4, (unsigned long long)nround); atomicAdd(P.phase_cycles + 5, (unsigned long long)ntask); atomicAdd(P.phase_cycles + 6, 1ull); }
+#endif
 
         // 2. one (image, start pixel) micro-task per lane
         for (int mb = 0; mb < ntask; mb += CAND_THREADS) {
             const int m = mb + tid;
             const bool has = m < ntask;
             int slot = 0, x = 0, y = 0;
-            if (has) {
+            if (has && m < TASK_TAB) {
+                const int tk = S.task_tab[m];
+                slot = tk >> 8; x = (tk >> 4) & 15; y = tk & 15;
+            } else if (has) {                               // beyond the table: search the prefix and the image
                 int lo = 0, hi = CAND_THREADS;              // cand_off[lo] <= m < cand_off[hi]
                 while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (S.cand_off[mid] <= m) lo = mid; else hi = mid; }
                 slot = S.slot_of[lo];
                 int k = m - S.cand_off[lo];
-                const uint32_t* bmi = S.slots + slot * SLOT_WORDS;
+                const uint32_t* ri = S.slots + slot * ROWS_WORDS;
                 for (y = 0; y < 16; ++y) {
-                    const uint32_t c = start_candidates(bmi, y, 0u);
+                    const uint32_t c = start_candidates_rows(ri, y);
                     const int pc = __popc(c);
                     if (k < pc) { x = (int)__fns(c, 0u, k + 1); break; }
                     k -= pc;
                 }
             }
-            const uint32_t* bm = S.slots + slot * SLOT_WORDS;
+            const uint32_t* rows = S.slots + slot * ROWS_WORDS;
             const int q = S.pair_of[slot];
             // (a) every lane follows its border; the points stay in the lane's scratch
             int n = -2, area2 = 1;
             {
                 StridedScratch<32, FAST_CAP> sc;
-                sc.w = nullptr;
                 sc.b = W_pts + lane;
                 sc.kept = 0;
-                if (has) n = follow_outer_from(sc, bm, x, y, area2);
+                if (has) n = follow_outer_rows(sc, rows, x, y, area2);
             }
             const bool keep = has && n != -2 && area2 <= 0;        // a raster-first start of an outer border
             const bool ovf_mine = keep && n < 0;
@@ -826,6 +853,9 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
             //     of a warp have similar trip counts and abandoned / hole paths drop out
             if (tid < 64) S.hist[tid] = 0;
             __syncthreads();
+#ifdef IRBPP_PROBE_FINE
+            phase_mark(5);   // find start pixel + follow (incl. waiting for the slowest warp)
+#endif
             const int bucket = 63 - min(63, npts);
             const int boff = atomicAdd(&S.hist[bucket], 1);
             S.n_of[tid] = (uint8_t)npts;
@@ -846,21 +876,26 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
             __syncthreads();
             S.order2[S.hbase[bucket] + boff] = (uint16_t)tid;
             __syncthreads();
+#ifdef IRBPP_PROBE_FINE
+            phase_mark(6);   // length sort
+#endif
             // (c) lane i approximates the i-th longest contour (points live in its owner's scratch)
             {
                 const int owner = S.order2[tid];
                 const int on = S.n_of[owner];
                 if (on > 0) {
                     StridedScratch<32, FAST_CAP> sc;
-                    sc.w = nullptr;
                     sc.b = ws_base + (size_t)(owner >> 5) * P.ws_bytes + (owner & 31);
                     sc.kept = 0;
-                    uint32_t* cb = S.candbits + (int)S.q_of[owner] * 8;
+                    uint32_t* cb = candbits + (int)S.q_of[owner] * 8;
                     approx_and_emit(sc, on, P.legacy != 0,
                                     [&](int ex, int ey) { const int b = ex * 16 + ey; atomicOr(cb + (b >> 5), 1u << (b & 31)); });
                 }
             }
             __syncthreads();           // scratch of every lane is free again
+#ifdef IRBPP_PROBE_FINE
+            phase_mark(7);   // approxPolyDP + emit
+#endif
             // rare: a contour longer than FAST_CAP points; the lanes concerned redo it one at a time with
             // 1024-point buffers laid over the (now idle) lane scratch of this warp
             uint32_t ovf = __ballot_sync(0xffffffffu, ovf_mine);
@@ -868,12 +903,13 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
                 const int src_lane = __ffs((int)ovf) - 1;
                 ovf &= ovf - 1;
                 if (lane == src_lane) {
+#ifndef IRBPP_PROBE_FINE
                     if (P.phase_cycles) atomicAdd(P.phase_cycles + 7, 1ull);     // overflow redo counter
+#endif
                     FlatScratch<BIG_CAP> bs;
-                    bs.w = nullptr;
                     bs.b = W_pts;
-                    uint32_t* cb = S.candbits + q * 8;
-                    if (!process_start_candidate(bs, bm, x, y, P.legacy != 0,
+                    uint32_t* cb = candbits + q * 8;
+                    if (!process_start_candidate(bs, rows, x, y, P.legacy != 0,
                             [&](int ex, int ey) { const int b = ex * 16 + ey; atomicOr(cb + (b >> 5), 1u << (b & 31)); }))
                         atomicMax(&S.error[q / R], 6);
                 }
@@ -893,7 +929,7 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
     const int dev_err = S.error[warp];
     // ---- phase D ----
     const int sel = P.sel;
-    const uint32_t* cbits = S.candbits + warp * R * 8;
+    const uint32_t* cbits = candbits + warp * R * 8;
     const uint32_t* mask_g = P.maskbits + (int64_t)env * R * 8;
     const double* posz_g = P.posz + (int64_t)env * R * NPOSE;
     float* obs_g = P.obs + (int64_t)env * P.obs_stride + (P.mode == MODE_ALL_OBS ? P.slot * P.loc_len : 0);
@@ -982,7 +1018,7 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
                 // candidate's rank = (candidates in lower buckets) + (its rank inside its own bucket), so
                 // each candidate is compared only with its bucket instead of with all K.
                 uint16_t* sorted = list + LIST_CAP;                  // second half of the lane scratch
-                int32_t* hist = S.rank_hist[warp];                   // [0,64): counts, [64,128): running offsets
+                int32_t* hist = reinterpret_cast<int32_t*>(S.slots) + warp * 128;   // image slots are idle now; [0,64): counts, [64,128): running offsets
                 auto bucket_of = [&](double H) { const int v = (int)((H + 0.32) * 100.0); return v < 0 ? 0 : (v > 63 ? 63 : v); };
                 hist[lane] = 0; hist[32 + lane] = 0;
                 __syncwarp();

@@ -18,32 +18,22 @@ static inline void __syncwarp() {}
 #include "../../ir-bpp_b200/csrc/irbpp_contour.cuh"
 #include "../../ir-bpp_b200/csrc/irbpp_math.cuh"
 
-extern "C" int hull_bits(const uint16_t* rows, int legacy, int use_big, uint32_t* out_bits) {
+extern "C" int hull_bits(const uint16_t* rows16, int legacy, int mode, uint32_t* out_bits) {
     for (int i = 0; i < 8; ++i) out_bits[i] = 0;
-    uint32_t bm[8];
-    for (int i = 0; i < 8; ++i) bm[i] = (uint32_t)rows[2 * i] | ((uint32_t)rows[2 * i + 1] << 16);
+    uint32_t rows[irbpp::ROWS_WORDS] = {0};                  // padded row form: rows[y + 1] = row y << 1
+    for (int y = 0; y < 16; ++y) rows[y + 1] = (uint32_t)rows16[y] << 1;
     auto emit = [&](int x, int y) { const int b = x * 16 + y; out_bits[b >> 5] |= 1u << (b & 31); };
-    if (use_big == 3) {   // component-first, serial, long buffers
-        static uint32_t w[16]; static uint8_t b[2 * 1024];
-        irbpp::FlatScratch<1024> sc; sc.w = w; sc.b = b;
-        return irbpp::process_level_image_cf(sc, bm, legacy != 0, emit) ? 0 : 1;
+    if (mode == 5) {   // one task per start pixel, long buffers (the kernel's overflow path)
+        static uint8_t b[2 * 1024];
+        irbpp::FlatScratch<1024> sc; sc.b = b;
+        return irbpp::process_level_image_mt(sc, rows, legacy != 0, emit) ? 0 : 1;
     }
-    if (use_big == 4) {   // component-first, lock-step routine with one lane
-        static uint32_t w[16]; static uint8_t b[64];
-        irbpp::StridedScratch<1, 32> sc; sc.w = w; sc.b = b; sc.kept = 0;
-        return irbpp::process_level_image_cf_lockstep(sc, bm, true, legacy != 0, emit) ? 0 : 1;
+    if (mode == 6) {   // one task per start pixel, 64-point fast buffers (the kernel's lane scratch)
+        static uint8_t b[64];
+        irbpp::StridedScratch<1, 64> sc; sc.b = b; sc.kept = 0;
+        return irbpp::process_level_image_mt(sc, rows, legacy != 0, emit) ? 0 : 1;
     }
-    if (use_big == 5) {   // micro-task formulation (no visited bits), long buffers
-        static uint32_t w[16]; static uint8_t b[2 * 1024];
-        irbpp::FlatScratch<1024> sc; sc.w = w; sc.b = b;
-        return irbpp::process_level_image_mt(sc, bm, legacy != 0, emit) ? 0 : 1;
-    }
-    if (use_big == 6) {   // micro-task formulation, 64-point fast buffers
-        static uint32_t w[16]; static uint8_t b[64];
-        irbpp::StridedScratch<1, 64> sc; sc.w = w; sc.b = b; sc.kept = 0;
-        return irbpp::process_level_image_mt(sc, bm, legacy != 0, emit) ? 0 : 1;
-    }
-    return -1;   // modes 3-6 only
+    return -1;   // modes 5 and 6 only
 }
 
 extern "C" void floor_div_many(const double* a, double b, int n, double* out) {

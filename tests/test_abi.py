@@ -115,15 +115,15 @@ def test_device_contour_routines_match_oracle(contour_harness):
             for c in cp.find_outer_contours(img):
                 maxlen = max(maxlen, len(c))
                 want |= {(int(p[0]), int(p[1])) for p in cp.convex_vertices(cp.approx_poly_dp_closed(c, 1.0, bool(legacy)))}
-            # component-first formulation (what the kernels run): serial long-buffer and lock-step variants
-            rc_cf, got_cf = _dev_bits(contour_harness, img, legacy, 3)
-            assert rc_cf == 0 and got_cf == want
-            rc_cfl, got_cfl = _dev_bits(contour_harness, img, legacy, 4)
-            if rc_cfl == 0:
-                assert got_cfl == want
+            # one task per start pixel (what the kernels run): long-buffer and 64-point lane-scratch variants
+            rc_big, got_big = _dev_bits(contour_harness, img, legacy, 5)
+            assert rc_big == 0 and got_big == want
+            rc_fast, got_fast = _dev_bits(contour_harness, img, legacy, 6)
+            if rc_fast == 0:
+                assert got_fast == want
             else:
-                assert maxlen > 32                        # overflow of the 32-point harness buffer only
-            n_ovf += rc_cfl
+                assert maxlen > 64                        # overflow of the 64-point buffer only
+            n_ovf += rc_fast
     assert n_ovf > 0                                         # the overflow path was exercised
 
 
