@@ -75,6 +75,38 @@ struct FlatScratch {
     }
 };
 
+// Explicit stack of the Douglas-Peucker ranges.  The larger half of a split is deferred, so the depth is
+// at most 2 + log2(n).  For <= 64-point contours the entries (two 6-bit indices) live in a 128-bit shift
+// register instead of local memory: pushes and pops are on the dependent chain of the recursion.
+template <bool SMALL>
+struct RangeStack;
+template <>
+struct RangeStack<true> {
+    uint64_t lo = 0, hi = 0;
+    int depth = 0;
+    __device__ __forceinline__ bool empty() const { return depth == 0; }
+    __device__ __forceinline__ void push(int s, int e) {
+        hi = (hi << 16) | (lo >> 48);
+        lo = (lo << 16) | (uint64_t)((s << 8) | e);
+        ++depth;
+    }
+    __device__ __forceinline__ void pop(int& s, int& e) {
+        const int v = (int)(lo & 0xFFFFu);
+        lo = (lo >> 16) | (hi << 48);
+        hi >>= 16;
+        --depth;
+        s = v >> 8; e = v & 0xFF;
+    }
+};
+template <>
+struct RangeStack<false> {
+    int st_s[14], st_e[14];
+    int depth = 0;
+    __device__ __forceinline__ bool empty() const { return depth == 0; }
+    __device__ __forceinline__ void push(int s, int e) { st_s[depth] = s; st_e[depth] = e; ++depth; }
+    __device__ __forceinline__ void pop(int& s, int& e) { --depth; s = st_s[depth]; e = st_e[depth]; }
+};
+
 // ---- approxPolyDP(eps = 1, closed) + convex-vertex filter ---------------------------------------
 // Emits the selected vertices through `emit(x, y)`.
 template <class S, class Emit>
@@ -98,7 +130,8 @@ __device__ void approx_and_emit(S& sc, int n, bool legacy, Emit emit) {
     int pos = 0, far = 0, maxd = 0;
     for (int it = 0; it < 3; ++it) {
         pos += far; if (pos >= n) pos -= n;
-        const int sx = PX(pos), sy = PY(pos);
+        const int pp = sc.pt(pos);
+        const int sx = pp >> 4, sy = pp & 15;
         maxd = 0; far = 0;
         int k = pos;
         for (int j = 1; j < n; ++j) {
@@ -117,18 +150,18 @@ __device__ void approx_and_emit(S& sc, int n, bool legacy, Emit emit) {
     // 2. Douglas-Peucker.  A leaf slice (s,e) keeps P[s]; the kept set is order independent, so the
     // larger half is deferred and the explicit stack stays logarithmic.
     sc.kept_clear(n);
-    int st_s[12], st_e[12];
-    int sp = 0;
-    st_s[sp] = fp; st_e[sp] = pos; ++sp;
-    st_s[sp] = pos; st_e[sp] = fp; ++sp;
-    while (sp > 0) {
-        --sp;
-        int s = st_s[sp], e = st_e[sp];
+    RangeStack<(S::CAP <= 64)> st;
+    st.push(fp, pos);
+    st.push(pos, fp);
+    while (!st.empty()) {
+        int s, e;
+        st.pop(s, e);
         for (;;) {
             int len = e - s; if (len <= 0) len += n;
             if (len == 1) { sc.kept_set(s); break; }
-            const int sx = PX(s), sy = PY(s);
-            const int dx = PX(e) - sx, dy = PY(e) - sy;
+            const int ps = sc.pt(s), pe = sc.pt(e);
+            const int sx = ps >> 4, sy = ps & 15;
+            const int dx = (pe >> 4) - sx, dy = (pe & 15) - sy;
             const int seg2 = dx * dx + dy * dy;
             int best = -1, bi = s;
             int k = s;
@@ -173,8 +206,8 @@ __device__ void approx_and_emit(S& sc, int n, bool legacy, Emit emit) {
             if (le) { sc.kept_set(s); break; }
             int ll = bi - s; if (ll <= 0) ll += n;
             const int lr = len - ll;
-            if (ll <= lr) { st_s[sp] = bi; st_e[sp] = e; ++sp; e = bi; }
-            else          { st_s[sp] = s;  st_e[sp] = bi; ++sp; s = bi; }
+            if (ll <= lr) { st.push(bi, e); e = bi; }
+            else          { st.push(s, bi); s = bi; }
         }
     }
     // 3. ring Q = kept points in contour order starting at pos; OpenCV's clean-up pass removes nearly

@@ -683,10 +683,10 @@ struct CandSmem {
 __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Params P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CandSmem& S = *reinterpret_cast<CandSmem*>(smem_raw);
-    asm volatile("griddepcontrol.wait;" ::: "memory");      // PDL: scan grid complete, its scratch writes visible
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int env0 = P.env_lo + blockIdx.x * ENVS_PER_CTA;
     const int nenv = min(ENVS_PER_CTA, P.env_hi - env0);
+    asm volatile("griddepcontrol.wait;" ::: "memory");      // PDL: scan grid complete, its scratch writes visible
     const int R = P.R;
     const int npairs = nenv * R;
     long long t_prev = P.phase_cycles ? clock64() : 0;
@@ -698,6 +698,19 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
         }
     };
     auto env_live = [&](int e) { return !(P.mode == MODE_RESET && P.which && !P.which[e]); };
+    // Zero the candidate rows [first, sel) of one bin's observation (one warp): scalar stores up to a 16-byte
+    // boundary, float4 after it.
+    auto zero_obs_rows = [&](int e, int first) {
+        float* z0 = P.obs + (int64_t)e * P.obs_stride + (P.mode == MODE_ALL_OBS ? P.slot * P.loc_len : 0) + first * 5;
+        const int count = (P.sel - first) * 5;
+        int head = (int)((16u - ((uint32_t)(uintptr_t)z0 & 15u)) & 15u) >> 2;
+        head = head < count ? head : count;
+        const int nvec = (count - head) >> 2;
+        if (lane < head) z0[lane] = 0.0f;
+        float4* zv = reinterpret_cast<float4*>(z0 + head);
+        for (int i = lane; i < nvec; i += 32) zv[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        for (int i = head + 4 * nvec + lane; i < count; i += 32) z0[i] = 0.0f;
+    };
 
     // dynamic tail: CAND_WARPS blocks of P.ws_bytes, then the 256-bit candidate sets per (bin, rotation)
     uint32_t* candbits = reinterpret_cast<uint32_t*>(smem_raw + ((sizeof(CandSmem) + 15) & ~(size_t)15) + (size_t)CAND_WARPS * P.ws_bytes);
@@ -728,7 +741,7 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
         // 1. thread t loads image t, counts its start candidates (background at W, NW, N, NE) and a cost key
         //    (foreground/background transitions ~ border length)
         int cnt = 0, bucket = 63, my_off = 0;
-        uint32_t wv[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};   // this thread's image, two 16-bit rows per word
+        uint32_t sm[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};   // start-pixel masks of this thread's image, two 16-bit rows per word
         if (tid < 64) S.hist[tid] = 0;
         __syncthreads();
         if (tid < nround) {
@@ -740,7 +753,7 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
             const uint4 a = src[0], b = src[1];
             uint32_t* rows = S.slots + tid * ROWS_WORDS;
             S.pair_of[tid] = (uint16_t)lo;
-            wv[0] = a.x; wv[1] = a.y; wv[2] = a.z; wv[3] = a.w; wv[4] = b.x; wv[5] = b.y; wv[6] = b.z; wv[7] = b.w;
+            const uint32_t wv[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
             rows[0] = 0u; rows[17] = 0u;
 #pragma unroll
             for (int k = 0; k < 8; ++k) { rows[1 + 2 * k] = (wv[k] & 0xFFFFu) << 1; rows[2 + 2 * k] = (wv[k] >> 16) << 1; }
@@ -749,7 +762,8 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 const uint32_t r0 = wv[k] & 0xFFFFu, r1 = wv[k] >> 16;
-                cnt += __popc(start_mask(r0, up)) + __popc(start_mask(r1, r0));
+                sm[k] = start_mask(r0, up) | (start_mask(r1, r0) << 16);
+                cnt += __popc(sm[k]);
                 key += __popc(r0 ^ (r0 << 1)) + __popc(r1 ^ (r1 << 1)) + __popc(r0 ^ up) + __popc(r1 ^ r0);
                 up = r1;
             }
@@ -797,15 +811,14 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
         // micro-task lane finds its pixel with one load
         if (tid < nround && cnt > 0) {
             int off = S.cand_off[my_pos];
-            uint32_t up = 0;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-                const uint32_t r0 = wv[k] & 0xFFFFu, r1 = wv[k] >> 16;
-                uint32_t c = start_mask(r0, up);
-                while (c && off < TASK_TAB) { S.task_tab[off++] = (uint16_t)((tid << 8) | ((__ffs((int)c) - 1) << 4) | (2 * k)); c &= c - 1; }
-                c = start_mask(r1, r0);
-                while (c && off < TASK_TAB) { S.task_tab[off++] = (uint16_t)((tid << 8) | ((__ffs((int)c) - 1) << 4) | (2 * k + 1)); c &= c - 1; }
-                up = r1;
+                uint32_t c = sm[k];
+                while (c && off < TASK_TAB) {
+                    const int b = __ffs((int)c) - 1;           // bit b: column b & 15 of row 2k + (b >> 4)
+                    c &= c - 1;
+                    S.task_tab[off++] = (uint16_t)((tid << 8) | ((b & 15) << 4) | (2 * k + (b >> 4)));
+                }
             }
         }
         __syncthreads();
@@ -957,7 +970,7 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
         if (dbg_cand) { double* qd = dbg_cand + row * 5; qd[0] = rot; qd[1] = x; qd[2] = y; qd[3] = H; qd[4] = V; }
     };
     auto zero_rows = [&](int first) {
-        for (int i = first * 5 + lane; i < sel * 5; i += 32) obs_g[i] = 0.0f;
+        zero_obs_rows(env, first);
         if (cand_g) for (int i = first + lane; i < sel; i += 32) cand_g[i] = 0;
         if (dbg_cand) for (int i = first * 5 + lane; i < sel * 5; i += 32) dbg_cand[i] = 0.0;
     };
