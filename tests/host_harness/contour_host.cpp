@@ -67,3 +67,28 @@ extern "C" int heuristic_pose_host(int method, int dir_idx, int R, const double*
     }
     return beste;
 }
+
+// All outer contours of an image as the device follower produces them: for every start pixel whose path
+// is kept (raster-first start of an outer border), n followed by n packed points (x << 4 | y), in
+// raster order of the start pixels.  Returns the number of words written, -1 on overflow of `cap`.
+extern "C" int outer_contours_host(const uint16_t* rows16, int32_t* out, int cap) {
+    uint32_t rows[irbpp::ROWS_WORDS] = {0};
+    for (int y = 0; y < 16; ++y) rows[y + 1] = (uint32_t)rows16[y] << 1;
+    static uint8_t b[2 * 1024];
+    irbpp::FlatScratch<1024> sc; sc.b = b;
+    int w = 0;
+    for (int y = 0; y < 16; ++y) {
+        uint32_t c = irbpp::start_candidates_rows(rows, y);
+        while (c) {
+            const int x = __builtin_ctz(c);
+            c &= c - 1;
+            int area2;
+            const int n = irbpp::follow_outer_rows(sc, rows, x, y, area2);
+            if (n == -2 || area2 > 0) continue;
+            if (n < 0 || w + 1 + n > cap) return -1;
+            out[w++] = n;
+            for (int i = 0; i < n; ++i) out[w++] = sc.pt(i);
+        }
+    }
+    return w;
+}

@@ -174,3 +174,41 @@ def test_device_heuristic_scores_match_oracle(contour_harness):
             r_, x_, y_ = e.heuristic_action(HEURISTICS[t % 4], t % 4)
             acts.append((r_ * 16 + x_) * 16 + y_)
         env.step(acts, poses=True)
+
+
+def test_device_border_follower_matches_oracle_contours(contour_harness):
+    """cv2.findContours(RETR_TREE, CHAIN_APPROX_SIMPLE) + find_out_contour (cvTools.py:7-38,86): the point
+    LISTS (order within a contour matters for approxPolyDP) of the device follower, compiled for the host,
+    against the oracle's restatement (itself fuzzed against cv2 in test_oracle_contours.py)."""
+    from oracle import contours_port as cp
+    rng = np.random.default_rng(3)
+    out = np.zeros(4096, np.int32)
+    for it in range(800):
+        kind = it % 4
+        if kind == 0:
+            img = (rng.random((16, 16)) < rng.uniform(0.05, 0.95)).astype(np.uint8)
+        elif kind == 1:
+            img = np.kron((rng.random((8, 8)) < rng.uniform(0.2, 0.9)).astype(np.uint8), np.ones((2, 2), np.uint8))
+        elif kind == 2:
+            img = np.ones((16, 16), np.uint8)
+            for _ in range(int(rng.integers(1, 9))):
+                x0, y0 = rng.integers(0, 15, 2); w, h = rng.integers(1, 5, 2)
+                img[x0:x0 + w, y0:y0 + h] = 0
+        else:
+            img = np.zeros((16, 16), np.uint8)
+            a = int(rng.integers(0, 3)); img[a:16 - a, a:16 - a] = 1
+            b = a + int(rng.integers(1, 3)); img[b:16 - b, b:16 - b] = 0
+            c = b + int(rng.integers(1, 3)); img[c:16 - c, c:16 - c] = 1
+            img ^= (rng.random((16, 16)) < 0.05).astype(np.uint8)
+        rows = np.zeros(16, np.uint16)
+        for y in range(16):
+            rows[y] = sum(1 << x for x in range(16) if img[y, x])
+        nw = contour_harness.outer_contours_host(rows.ctypes.data_as(ctypes.c_void_p),
+                                                 out.ctypes.data_as(ctypes.c_void_p), len(out))
+        assert nw >= 0
+        got, i = [], 0
+        while i < nw:
+            n = int(out[i]); pts = out[i + 1:i + 1 + n]; i += 1 + n
+            got.append(tuple((int(p) >> 4, int(p) & 15) for p in pts))
+        want = [tuple((int(p[0]), int(p[1])) for p in c_) for c_ in cp.find_outer_contours(img)]
+        assert sorted(got) == sorted(want), it
