@@ -10,19 +10,19 @@
 //        (space.py:98-129), one warp per rotation, lanes = poses; level quantisation with NumPy
 //        floor_divide semantics (cvTools.py:78-79); one 16x16 bitmap per (rotation, level) by warp
 //        ballots -> global scratch (L2 resident).  Tables that are constant on square blocks of cells
-//        (voxel shapes) are scanned from block maxima of the heightmap (scan_rotation_tiles)
+//        (voxel shapes) are scanned from block maxima of the heightmap (TileEntry lists)
 //   irbpp_candidates_kernel  one CTA (128 threads) per 4 bins
-//     C  candidate extraction (cvTools.py:61-103): every (bin, rotation, level) image of the CTA is one
-//        lane's task; tasks are ordered by a cost key so that the lanes of a warp carry images of
-//        similar size, and each warp advances in lock step, contour by contour: border following +
-//        approxPolyDP + convex filter (irbpp_contour.cuh), results OR-ed into a 256-bit set per
-//        (bin, rotation) in shared memory (np.unique == sorted set)
+//     C  candidate extraction (cvTools.py:61-103): the (bin, rotation, level) images of the CTA are
+//        ordered by a cost key; every (image, start pixel) pair is one lane's task, dealt in that order
+//        so that the lanes of a warp carry contours of similar length: border following, then (after
+//        re-dealing the contours by length) approxPolyDP + convex filter (irbpp_contour.cuh), results
+//        OR-ed into a 256-bit set per (bin, rotation) in shared memory (np.unique == sorted set)
 //     D  select / pad (binPhy.py:205-225): one warp per bin ranks the set bits and writes the
 //        candidate rows of the observation (float32, envs.py:151,163 cast) and the packed candidate
 //        table the next step decodes its action from
 // (paths relative to the reference root)
 //
-// Why two kernels: phase C is one serial task per lane with ~16 tasks per bin; inside a one-bin CTA it
+// Why two kernels: phase C is one serial task per lane with ~40 tasks per bin; inside a one-bin CTA it
 // ran at ~3 active lanes per instruction and left the other warps waiting at a barrier (profiles/).
 // Splitting lets phase C pack tasks of several bins into full warps and lets phase B run with 12 KB of
 // shared memory per CTA.  The hand-over (float64 drop heights, masks, level bitmaps: ~9 KB per bin) is
@@ -55,11 +55,6 @@ constexpr int ENVS_PER_CTA = IRBPP_ENVS_PER_CTA;   // bins (= warps) per CTA of 
 constexpr int CAND_WARPS = IRBPP_CAND_WARPS;          // warps per CTA of the candidates kernel (>= ENVS_PER_CTA)
 constexpr int CAND_THREADS = 32 * CAND_WARPS;
 static_assert(CAND_WARPS >= ENVS_PER_CTA, "phase D needs one warp per bin");
-#ifndef IRBPP_TASK_LANES
-#define IRBPP_TASK_LANES 32
-#endif
-constexpr int TASK_LANES = IRBPP_TASK_LANES;          // lanes of a warp that carry a level image in phase C
-constexpr int ROUND_TASKS = ENVS_PER_CTA * TASK_LANES; // level images a CTA processes per round
 constexpr int MAX_LEVELS = 64;           // level-image slots per (bin, rotation) in the scratch
 constexpr int TASK_TAB = 256;            // start pixels of a round listed explicitly (the rest are found by search)
 constexpr int FAST_CAP = 64;             // contour points on the fast path (32 was measured slower: every overflow redo stalls a warp)
@@ -155,7 +150,7 @@ struct Params {
     int32_t heur_method, heur_dir;       // heuristic kernel: Heuristic, dirIdx 0..3 (space.py:162-166)
     int32_t* heur_pose;                  // [N][3] rot, lx, ly
     int64_t* heur_index;                 // [N] row of that pose in the candidate table, -1 if absent
-    int32_t env_lo, env_hi;              // bins [env_lo, env_hi) handled by this launch (chunked pipeline)
+    int32_t env_lo, env_hi;              // bins [env_lo, env_hi) handled by this launch (the full range [0, N))
     // outputs
     float* obs;                          // [N][obs_stride] (+ slot offset in MODE_ALL_OBS)
     float* r_reward; uint8_t* r_done; uint8_t* r_valid; uint8_t* r_error;
