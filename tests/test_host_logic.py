@@ -1,0 +1,55 @@
+"""Host-side logic of GpuVecEnv that needs no GPU: the single-copy result block, its typed views and
+the lazily built info dicts (the reference's per-env dicts: binPhy.py:306-309, monitor.py:58-75)."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from irbpp_b200 import _lib
+from irbpp_b200.vec_env import GpuVecEnv, LazyInfos
+
+
+def _fake_result(n):
+    """A host buffer laid out like the library's pinned result block (include/irbpp.h, irbpp_step_result)."""
+    sizes = (("ratio", 8), ("ep_reward", 8), ("reward", 4), ("counter", 4), ("ep_len", 4), ("done", 1),
+             ("valid", 1), ("error", 1))
+    offs, o = {}, 0
+    for k, sz in sizes:
+        offs[k] = o
+        o += sz * n
+    buf = np.zeros(o + 16, np.uint8)
+    res = _lib.IrbppStepResult()
+    for k in offs:
+        setattr(res, k, buf.ctypes.data + offs[k])
+    return buf, offs, res
+
+
+@pytest.mark.parametrize("n", [1, 37, 4096])
+def test_result_block_views_and_lazy_infos(n):
+    buf, offs, res = _fake_result(n)
+    buf[offs["ratio"]:offs["ratio"] + 8 * n].view(np.float64)[:] = np.arange(n) * 0.5
+    buf[offs["ep_reward"]:offs["ep_reward"] + 8 * n].view(np.float64)[:] = np.arange(n) * 1.2345678
+    buf[offs["reward"]:offs["reward"] + 4 * n].view(np.float32)[:] = np.arange(n)
+    buf[offs["counter"]:offs["counter"] + 4 * n].view(np.int32)[:] = np.arange(n) + 100
+    buf[offs["ep_len"]:offs["ep_len"] + 4 * n].view(np.int32)[:] = np.arange(n) + 7
+    buf[offs["done"]:offs["done"] + n] = np.arange(n) % 2
+    buf[offs["valid"]:offs["valid"] + n] = 1
+    env = object.__new__(GpuVecEnv)          # no handle: only the pure-host helpers are exercised
+    env.num_envs = n
+    src, got_offs = env._result_block(res)
+    assert got_offs == offs and src.ctypes.data == buf.ctypes.data
+    assert env._result_block(res)[0] is src                       # built once per handle
+    block = src.copy()
+    done = block[offs["done"]:offs["done"] + n].view(np.bool_)
+    infos = LazyInfos(n, block, offs, done, 1.5)
+    buf[:] = 0                                                    # the step's copy is private
+    assert len(infos) == n
+    assert infos[0] == {"Valid": True}
+    if n > 1:
+        i = n - 1 if (n - 1) % 2 else n - 2
+        assert infos[i] == {"Valid": True, "counter": 100 + i, "ratio": 0.5 * i,
+                            "episode": {"r": round(1.2345678 * i, 6), "l": 7 + i, "t": 1.5}}
+        assert infos[-1] == infos[n - 1]
+        assert [d["Valid"] for d in infos[0:2]] == [True, True]
+    with pytest.raises(IndexError):
+        infos[n]
