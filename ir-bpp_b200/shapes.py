@@ -113,6 +113,79 @@ class ShapeLibrary:
 
 
 # ---------------------------------------------------------------------------
+# the reference's on-disk table cache (tools.shotInfoPre, tools.py:248-279)
+# ---------------------------------------------------------------------------
+
+SHOTINFO_META = "irbpp_info.pt"     # not part of the reference layout: extents / volume of a saved library
+
+
+def shotinfo_dir_name(data_name, dict_name, resolutionH, mesh_scale=1):
+    """``dataset/shotInfo/<data>_<dict>_<resH>[_<scale>]`` as ``tools.py:255-260`` composes it."""
+    if mesh_scale != 1:
+        return "{}_{}_{}_{}".format(data_name, dict_name, resolutionH, mesh_scale)
+    return "{}_{}_{}".format(data_name, dict_name, resolutionH)
+
+
+def save_shotinfo_dir(lib, path):
+    """Write ``lib`` in the reference's cache layout: one ``<id>_<rotIdx>.pt`` per (shape, rotation)
+    holding ``[heightMapT, heightMapB, maskH, maskB]`` (``tools.py:270-276``; ``torch.save`` of NumPy
+    arrays), so that the reference's ``shotInfoPre`` finds and loads them.  Extents and volumes, which
+    the reference takes from the meshes (``tools.py:236-241``), go to ``irbpp_info.pt`` beside them."""
+    import os
+    import torch
+    os.makedirs(path, exist_ok=True)
+    for s in range(lib.num_shapes):
+        for r in range(lib.num_rotations):
+            torch.save([np.array(m) for m in lib.tables[s][r]], os.path.join(path, "{}_{}.pt".format(s, r)))
+    torch.save({"extents": lib.extents, "volume": lib.volume, "resolutionH": lib.resolutionH,
+                "resolutionAct": lib.resolutionAct}, os.path.join(path, SHOTINFO_META))
+
+
+def load_shotinfo_dir(path, extents=None, volume=None, resolutionH=None, resolutionAct=None, name=None):
+    """Read a ``dataset/shotInfo/...`` directory written by the reference's ``shotInfoPre``
+    (``tools.py:248-279``) or by ``save_shotinfo_dir`` into a ``ShapeLibrary``.
+
+    The cache holds only the four maps per (id, rotIdx).  ``extents`` ``[S, R, 3]`` (``mesh.extents`` of
+    every rotation, ``space.py:104``) and ``volume`` ``[S]`` (``infoDict[id][0]['volume']``,
+    ``binPhy.py:151``) come from the caller -- ``args.infoDict`` in the reference -- unless the
+    directory carries ``irbpp_info.pt``.  Ids must be ``0..S-1`` with the same rotation count each."""
+    import os
+    import re
+    import torch
+    found = {}
+    for fn in os.listdir(path):
+        m = re.fullmatch(r"(\d+)_(\d+)\.pt", fn)
+        if m:
+            found[(int(m.group(1)), int(m.group(2)))] = fn
+    if not found:
+        raise FileNotFoundError("no <id>_<rotIdx>.pt files in %s" % path)
+    S = max(k for k, _ in found) + 1
+    R = max(r for _, r in found) + 1
+    missing = [(k, r) for k in range(S) for r in range(R) if (k, r) not in found]
+    if missing:
+        raise ValueError("incomplete shotInfo cache, missing %s" % missing[:8])
+    meta_path = os.path.join(path, SHOTINFO_META)
+    if os.path.exists(meta_path):
+        meta = torch.load(meta_path, weights_only=False)
+        extents = meta["extents"] if extents is None else extents
+        volume = meta["volume"] if volume is None else volume
+        resolutionH = meta["resolutionH"] if resolutionH is None else resolutionH
+        resolutionAct = meta["resolutionAct"] if resolutionAct is None else resolutionAct
+    if extents is None or volume is None or resolutionH is None or resolutionAct is None:
+        raise ValueError("extents / volume / resolutions are not in the cache: pass them (args.infoDict, args.resolutionH/A)")
+    tables = []
+    for k in range(S):
+        rows = []
+        for r in range(R):
+            maps = torch.load(os.path.join(path, found[(k, r)]), weights_only=False)      # tools.py:271
+            rows.append(tuple(np.ascontiguousarray(np.asarray(m), dtype=np.float64) for m in maps))
+        tables.append(rows)
+    return ShapeLibrary(float(resolutionH), float(resolutionAct), np.asarray(extents, dtype=np.float64),
+                        np.asarray(volume, dtype=np.float64), tables,
+                        name=name or os.path.basename(os.path.normpath(path)))
+
+
+# ---------------------------------------------------------------------------
 # voxel models -> tables (shot_item sampling rule)
 # ---------------------------------------------------------------------------
 
