@@ -58,7 +58,7 @@ def test_hull_actions_legacy_switch_matches_oracle():
     """approx_legacy=1 selects the point-to-line rule (unpinned against the reference's cv2 4.4.0.46;
     checked against the oracle's restatement of that rule)."""
     from irbpp_b200 import shapes
-    from oracle.oracle_env import select_candidates, OracleConfig
+    from oracle.oracle_env import OracleConfig
     from oracle import contours_port
     d = load_golden("hulls")
     n = len(d["counts"])

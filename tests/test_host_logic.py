@@ -1,6 +1,5 @@
 """Host-side logic of GpuVecEnv that needs no GPU: the single-copy result block, its typed views and
 the lazily built info dicts (the reference's per-env dicts: binPhy.py:306-309, monitor.py:58-75)."""
-import ctypes
 
 import numpy as np
 import pytest

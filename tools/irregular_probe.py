@@ -2,7 +2,7 @@
 """Kernel time split for the irregular R=8 configuration (per-cell scan path).  GPU only; run under ncu."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch
+import torch
 from irbpp_b200 import shapes
 from irbpp_b200.vec_env import GpuVecEnv
 R = int(sys.argv[1]) if len(sys.argv) > 1 else 8

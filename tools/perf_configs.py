@@ -3,7 +3,7 @@
 (parity cases, timed here only to know where they stand).  GPU only."""
 import os, sys, json
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-import numpy as np, torch
+import torch
 from irbpp_b200 import shapes
 from irbpp_b200.vec_env import GpuVecEnv
 
