@@ -107,6 +107,97 @@ struct RangeStack<false> {
     __device__ __forceinline__ void pop(int& s, int& e) { --depth; s = st_s[depth]; e = st_e[depth]; }
 };
 
+// Part 2 of approxPolyDP + the convex filter, given the Douglas-Peucker kept set in `sc` and the start
+// index `pos`: OpenCV's clean-up pass over the kept ring, then find_convex_vetex (cvTools.py:40-59).
+template <class S, class Emit>
+__device__ void finish_polygon(S& sc, int n, int pos, Emit emit) {
+    // 3. ring Q = kept points in contour order starting at pos; OpenCV's clean-up pass removes nearly
+    // collinear points on diagonal chords.  It writes into a copy of Q and returns the first
+    // `new_count` entries; that sequence is regenerated on the fly here instead of being stored.
+    const int c = sc.kept_count(n);
+    int last = pos;                                   // Q[c-1]
+    for (int k = 0; k + 1 < c; ++k) last = sc.kept_next(last, n);
+    // generator of the written values: calls sink(value) for each write, returns the final new_count
+    auto cleanup = [&](auto sink, int max_writes) -> int {
+        int new_count = c;
+        int start = sc.pt(last);
+        int ci = pos;
+        int pt = sc.pt(ci); ci = sc.kept_next(ci, n);
+        int i = 0, writes = 0;
+        while (i < c && new_count > 2) {
+            const int end = sc.pt(ci); ci = sc.kept_next(ci, n);
+            const int dx = (end >> 4) - (start >> 4), dy = (end & 15) - (start & 15);
+            const int px = (pt >> 4) - (start >> 4), py = (pt & 15) - (start & 15);
+            int dist = px * dy - py * dx; if (dist < 0) dist = -dist;
+            const int ip = px * ((end >> 4) - (pt >> 4)) + py * ((end & 15) - (pt & 15));
+            if (2 * dist * dist <= dx * dx + dy * dy && dx != 0 && dy != 0 && ip >= 0) {
+                --new_count;
+                start = end;
+                if (writes < max_writes) sink(end);
+                ++writes;
+                pt = sc.pt(ci); ci = sc.kept_next(ci, n);
+                i += 2;
+                continue;
+            }
+            start = pt;
+            if (writes < max_writes) sink(pt);
+            ++writes;
+            pt = end;
+            ++i;
+        }
+        return new_count | (writes << 16);
+    };
+    int nc = c, writes = c;
+    if (c > 2) {
+        const int r = cleanup([](int) {}, 0);
+        nc = r & 0xFFFF; writes = r >> 16;
+    }
+    if (nc == c) {
+        // nothing dropped: the polygon is Q itself
+        if (c <= 3) {
+            int ci = pos;
+            for (int k = 0; k < c; ++k) { const int p = sc.pt(ci); emit(p >> 4, p & 15); ci = sc.kept_next(ci, n); }
+        } else {
+            int a = sc.pt(last), ci = pos, bpt = sc.pt(ci);
+            for (int k = 0; k < c; ++k) {
+                ci = sc.kept_next(ci, n);
+                const int cpt = sc.pt(ci);
+                const int abx = (bpt >> 4) - (a >> 4), aby = (bpt & 15) - (a & 15);
+                const int acx = (cpt >> 4) - (a >> 4), acy = (cpt & 15) - (a & 15);
+                if (abx * acy - aby * acx < 0) emit(bpt >> 4, bpt & 15);      // find_convex_vetex: cross < 0
+                a = bpt; bpt = cpt;
+            }
+        }
+        return;
+    }
+    if (nc <= 3) {
+        // result = dst[0..nc): written values first, untouched copies of Q beyond them
+        int k = 0;
+        cleanup([&](int v) { emit(v >> 4, v & 15); ++k; }, nc);
+        int ci = pos;
+        for (int q = 0; q < nc; ++q) { if (q >= k) { const int p = sc.pt(ci); emit(p >> 4, p & 15); } ci = sc.kept_next(ci, n); }
+        (void)writes;
+        return;
+    }
+    // nc > 3: all nc entries were written; streaming convex filter over the ring w_0 .. w_{nc-1}
+    {
+        int w0 = -1, w1 = -1, a = -1, bpt = -1, k = 0;
+        auto test = [&](int A, int B, int C) {
+            const int abx = (B >> 4) - (A >> 4), aby = (B & 15) - (A & 15);
+            const int acx = (C >> 4) - (A >> 4), acy = (C & 15) - (A & 15);
+            if (abx * acy - aby * acx < 0) emit(B >> 4, B & 15);
+        };
+        cleanup([&](int v) {
+            if (k == 0) { w0 = v; a = v; }
+            else if (k == 1) { w1 = v; bpt = v; }
+            else { test(a, bpt, v); a = bpt; bpt = v; }
+            ++k;
+        }, nc);
+        test(a, bpt, w0);      // (w_{nc-2}, w_{nc-1}, w_0)
+        test(bpt, w0, w1);     // (w_{nc-1}, w_0, w_1)
+    }
+}
+
 // ---- approxPolyDP(eps = 1, closed) + convex-vertex filter ---------------------------------------
 // Emits the selected vertices through `emit(x, y)`.
 template <class S, class Emit>
@@ -210,91 +301,99 @@ __device__ void approx_and_emit(S& sc, int n, bool legacy, Emit emit) {
             else          { st.push(s, bi); s = bi; }
         }
     }
-    // 3. ring Q = kept points in contour order starting at pos; OpenCV's clean-up pass removes nearly
-    // collinear points on diagonal chords.  It writes into a copy of Q and returns the first
-    // `new_count` entries; that sequence is regenerated on the fly here instead of being stored.
-    const int c = sc.kept_count(n);
-    int last = pos;                                   // Q[c-1]
-    for (int k = 0; k + 1 < c; ++k) last = sc.kept_next(last, n);
-    // generator of the written values: calls sink(value) for each write, returns the final new_count
-    auto cleanup = [&](auto sink, int max_writes) -> int {
-        int new_count = c;
-        int start = sc.pt(last);
-        int ci = pos;
-        int pt = sc.pt(ci); ci = sc.kept_next(ci, n);
-        int i = 0, writes = 0;
-        while (i < c && new_count > 2) {
-            const int end = sc.pt(ci); ci = sc.kept_next(ci, n);
-            const int dx = (end >> 4) - (start >> 4), dy = (end & 15) - (start & 15);
-            const int px = (pt >> 4) - (start >> 4), py = (pt & 15) - (start & 15);
-            int dist = px * dy - py * dx; if (dist < 0) dist = -dist;
-            const int ip = px * ((end >> 4) - (pt >> 4)) + py * ((end & 15) - (pt & 15));
-            if (2 * dist * dist <= dx * dx + dy * dy && dx != 0 && dy != 0 && ip >= 0) {
-                --new_count;
-                start = end;
-                if (writes < max_writes) sink(end);
-                ++writes;
-                pt = sc.pt(ci); ci = sc.kept_next(ci, n);
-                i += 2;
-                continue;
-            }
-            start = pt;
-            if (writes < max_writes) sink(pt);
-            ++writes;
-            pt = end;
-            ++i;
+    finish_polygon(sc, n, pos, emit);
+}
+
+// ---- warp-cooperative seeding + Douglas-Peucker (long contours) ---------------------------------------------
+// Same result as the first part of approx_and_emit, computed by the 32 lanes of a warp for ONE contour
+// of n <= 64 points (lane l holds points l and l + 32): every farthest-point search is one maximum over
+// the lanes of the packed key  value << 6 | (63 - offset)  -- the largest value, and among equal values
+// the smallest offset from the range start, which is the point the serial scan (strict >) keeps.  Control
+// flow is uniform; every lane ends with the same kept set in `sc` and the same return value: the start
+// index pos, or -1 when the contour collapsed to one point (which `emit` received).  The caller continues
+// with finish_polygon().  IRBPP_WARP_MAX(v): maximum of an unsigned value over the warp.
+#ifndef IRBPP_WARP_MAX
+#define IRBPP_WARP_MAX(v) __reduce_max_sync(0xffffffffu, (v))
+#endif
+template <class S, class Emit>
+__device__ int dp_keep_warp(S& sc, int n, bool legacy, int lane, Emit emit) {
+    static_assert(S::CAP <= 64, "two points per lane");
+    const int i0 = lane, i1 = lane + 32;
+    const int q0 = (i0 < n) ? sc.pt(i0) : 0, q1 = (i1 < n) ? sc.pt(i1) : 0;
+    // 1. seed: three rounds of "farthest point from the current one"
+    int pos = 0, far = 0, maxd = 0;
+    for (int it = 0; it < 3; ++it) {
+        pos += far; if (pos >= n) pos -= n;
+        const int pp = sc.pt(pos);
+        const int sx = pp >> 4, sy = pp & 15;
+        unsigned key = 0;
+        if (i0 < n) {
+            int j = i0 - pos; if (j < 0) j += n;
+            const int ex = (q0 >> 4) - sx, ey = (q0 & 15) - sy;
+            if (j >= 1) key = ((unsigned)(ex * ex + ey * ey) << 6) | (unsigned)(63 - j);
         }
-        return new_count | (writes << 16);
-    };
-    int nc = c, writes = c;
-    if (c > 2) {
-        const int r = cleanup([](int) {}, 0);
-        nc = r & 0xFFFF; writes = r >> 16;
-    }
-    if (nc == c) {
-        // nothing dropped: the polygon is Q itself
-        if (c <= 3) {
-            int ci = pos;
-            for (int k = 0; k < c; ++k) { const int p = sc.pt(ci); emit(p >> 4, p & 15); ci = sc.kept_next(ci, n); }
-        } else {
-            int a = sc.pt(last), ci = pos, bpt = sc.pt(ci);
-            for (int k = 0; k < c; ++k) {
-                ci = sc.kept_next(ci, n);
-                const int cpt = sc.pt(ci);
-                const int abx = (bpt >> 4) - (a >> 4), aby = (bpt & 15) - (a & 15);
-                const int acx = (cpt >> 4) - (a >> 4), acy = (cpt & 15) - (a & 15);
-                if (abx * acy - aby * acx < 0) emit(bpt >> 4, bpt & 15);      // find_convex_vetex: cross < 0
-                a = bpt; bpt = cpt;
-            }
+        if (i1 < n) {
+            int j = i1 - pos; if (j < 0) j += n;
+            const int ex = (q1 >> 4) - sx, ey = (q1 & 15) - sy;
+            const unsigned k1 = ((unsigned)(ex * ex + ey * ey) << 6) | (unsigned)(63 - j);
+            if (j >= 1 && k1 > key) key = k1;
         }
-        return;
+        const unsigned km = IRBPP_WARP_MAX(key);
+        maxd = (int)(km >> 6);
+        far = maxd > 0 ? 63 - (int)(km & 63u) : 0;
     }
-    if (nc <= 3) {
-        // result = dst[0..nc): written values first, untouched copies of Q beyond them
-        int k = 0;
-        cleanup([&](int v) { emit(v >> 4, v & 15); ++k; }, nc);
-        int ci = pos;
-        for (int q = 0; q < nc; ++q) { if (q >= k) { const int p = sc.pt(ci); emit(p >> 4, p & 15); } ci = sc.kept_next(ci, n); }
-        (void)writes;
-        return;
+    if (maxd <= 1) {  // whole contour within eps of one point
+        const int pp = sc.pt(pos);
+        emit(pp >> 4, pp & 15);
+        return -1;
     }
-    // nc > 3: all nc entries were written; streaming convex filter over the ring w_0 .. w_{nc-1}
-    {
-        int w0 = -1, w1 = -1, a = -1, bpt = -1, k = 0;
-        auto test = [&](int A, int B, int C) {
-            const int abx = (B >> 4) - (A >> 4), aby = (B & 15) - (A & 15);
-            const int acx = (C >> 4) - (A >> 4), acy = (C & 15) - (A & 15);
-            if (abx * acy - aby * acx < 0) emit(B >> 4, B & 15);
-        };
-        cleanup([&](int v) {
-            if (k == 0) { w0 = v; a = v; }
-            else if (k == 1) { w1 = v; bpt = v; }
-            else { test(a, bpt, v); a = bpt; bpt = v; }
-            ++k;
-        }, nc);
-        test(a, bpt, w0);      // (w_{nc-2}, w_{nc-1}, w_0)
-        test(bpt, w0, w1);     // (w_{nc-1}, w_0, w_1)
+    int fp = pos + far; if (fp >= n) fp -= n;
+    // 2. Douglas-Peucker, one range at a time, the farthest point of a range by one warp maximum
+    sc.kept_clear(n);
+    RangeStack<true> st;
+    st.push(fp, pos);
+    st.push(pos, fp);
+    while (!st.empty()) {
+        int s, e;
+        st.pop(s, e);
+        for (;;) {
+            int len = e - s; if (len <= 0) len += n;
+            if (len == 1) { sc.kept_set(s); break; }
+            const int ps = sc.pt(s), pe = sc.pt(e);
+            const int sx = ps >> 4, sy = ps & 15;
+            const int dx = (pe >> 4) - sx, dy = (pe & 15) - sy;
+            const int seg2 = dx * dx + dy * dy;
+            auto key_of = [&](int idx, int q) -> unsigned {
+                int t = idx - s; if (t < 0) t += n;
+                if (idx >= n || t < 1 || t >= len) return 0u;
+                const int vx = (q >> 4) - sx, vy = (q & 15) - sy;
+                const int cr = vy * dx - vx * dy;
+                int num;
+                if (legacy) num = cr < 0 ? -cr : cr;
+                else if (seg2 == 0) num = vx * vx + vy * vy;
+                else {
+                    const int dot = vx * dx + vy * dy;
+                    const int cl = dot < 0 ? 0 : (dot > seg2 ? seg2 : dot);
+                    const int tt = dot - cl;
+                    num = cr * cr + tt * tt;
+                }
+                return ((unsigned)num << 6) | (unsigned)(63 - t);       // t <= 62: a real key is never 0
+            };
+            const unsigned k0 = key_of(i0, q0), k1 = key_of(i1, q1);
+            const unsigned km = IRBPP_WARP_MAX(k0 > k1 ? k0 : k1);
+            const int best = (int)(km >> 6);
+            int bi = s + 63 - (int)(km & 63u); if (bi >= n) bi -= n;
+            bool le;
+            if (legacy) le = (best * best <= seg2);
+            else le = (seg2 == 0) ? (best <= 1) : (best <= seg2);
+            if (le) { sc.kept_set(s); break; }
+            int ll = bi - s; if (ll <= 0) ll += n;
+            const int lr = len - ll;
+            if (ll <= lr) { st.push(bi, e); e = bi; }
+            else          { st.push(s, bi); s = bi; }
+        }
     }
+    return pos;
 }
 
 // ---- start pixels ------------------------------------------------------------------------------------------

@@ -888,8 +888,29 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
             phase_mark(6);   // length sort
 #endif
             // (c) lane i approximates the i-th longest contour (points live in its owner's scratch)
-            {
-                const int owner = S.order2[tid];
+#ifdef IRBPP_COOP_APPROX
+            // Experimental (not the default build): contours of COOP_MIN points or more -- the tail that
+            // decides when the CTA, and with it the kernel, ends -- are taken one per WARP (dp_keep_warp:
+            // lanes = points), the rest one per lane as before.
+            constexpr int COOP_MIN = 17;
+            const int ncoop = S.hbase[64 - COOP_MIN];          // entries of the buckets with npts >= COOP_MIN
+            for (int c = warp; c < ncoop; c += CAND_WARPS) {
+                const int owner = S.order2[c];
+                const int on = S.n_of[owner];
+                StridedScratch<32, FAST_CAP> sc;
+                sc.b = ws_base + (size_t)(owner >> 5) * P.ws_bytes + (owner & 31);
+                sc.kept = 0;
+                uint32_t* cb = candbits + (int)S.q_of[owner] * 8;
+                auto emit0 = [&](int ex, int ey) { if (lane == 0) { const int b = ex * 16 + ey; atomicOr(cb + (b >> 5), 1u << (b & 31)); } };
+                const int pos = dp_keep_warp(sc, on, P.legacy != 0, lane, emit0);
+                if (pos >= 0) finish_polygon(sc, on, pos, emit0);
+            }
+            const int my_rank = ncoop + tid;
+#else
+            const int my_rank = tid;
+#endif
+            if (my_rank < CAND_THREADS) {
+                const int owner = S.order2[my_rank];
                 const int on = S.n_of[owner];
                 if (on > 0) {
                     StridedScratch<32, FAST_CAP> sc;
