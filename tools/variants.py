@@ -1,0 +1,49 @@
+#!/usr/bin/env python
+"""Build experiment variants of the library next to the default one and (on a GPU box) compare them.
+
+    python tools/variants.py build coop=-DIRBPP_COOP_APPROX fine=-DIRBPP_PROBE_FINE
+        -> ir-bpp_b200/lib/libirbpp_coop.so, libirbpp_fine.so   (they travel with gpurun like the default .so)
+    python tools/variants.py bench coop            # GPU: parity tests of the episode goldens + bench.py per variant
+
+Known switches (csrc/): IRBPP_COOP_APPROX  contours of >= 17 points by a whole warp (dp_keep_warp)
+                        IRBPP_PROBE_FINE   slots 4-7 of the phase counters time the sub-phases of phase C
+                        IRBPP_ENVS_PER_CTA / IRBPP_CAND_WARPS / IRBPP_SCAN_MIN_CTAS   CTA shapes
+"""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+LIB_DIR = os.path.join(ROOT, "ir-bpp_b200", "lib")
+
+
+def lib_path(name):
+    return os.path.join(LIB_DIR, "libirbpp.so" if name == "default" else "libirbpp_%s.so" % name)
+
+
+def main():
+    cmd, args = sys.argv[1], sys.argv[2:]
+    if cmd == "build":
+        from irbpp_b200 import build as b
+        for spec in args:
+            name, defs = spec.split("=", 1)
+            print(b.build(out=lib_path(name), defs=defs.split(",")))
+        return 0
+    if cmd == "bench":
+        for name in ["default"] + args:
+            env = dict(os.environ, IRBPP_LIB=lib_path(name))
+            t = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-q", "-x",
+                                "-m", "gpu", "-k", "episode or random or hull"], env=env, capture_output=True, text=True)
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "100", "--warmup", "5",
+                                "--no-cpu-baseline"], env=env, capture_output=True, text=True)
+            line = json.loads(r.stdout.strip().splitlines()[-1])
+            print(json.dumps({"variant": name, "tests": t.stdout.strip().splitlines()[-1], "ms_per_step": line["ms_per_step"],
+                              "e2e_ms": line["e2e"]["ms_per_step"]}))
+        return 0
+    raise SystemExit(__doc__)
+
+
+if __name__ == "__main__":
+    sys.exit(main())
