@@ -244,6 +244,8 @@ def main():
                                         selectedAction=40),
         "episode_buffered": gen_episode("buffered", shapes.make_blockout_library(16, seed=5), 4, 3, 50, 25,
                                         bufferSize=5),
+        # 24 rotations (BASELINE.json config 3): > 1024 candidates per bin, truncation is the normal case
+        "episode_rot24": gen_episode("rot24", shapes.make_irregular_library(8, seed=9, num_rotations=24), 24, 2, 24, 28),
     }
     for k, d in eps.items():
         np.savez_compressed(os.path.join(HERE, k + ".npz"), **d)

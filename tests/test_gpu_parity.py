@@ -92,7 +92,8 @@ def _check_step(out, d, t, tag):
             assert "episode" not in info
 
 
-@pytest.mark.parametrize("name", ["episode_blockout", "episode_irregular", "episode_cube", "episode_truncate"])
+@pytest.mark.parametrize("name", ["episode_blockout", "episode_irregular", "episode_cube", "episode_truncate",
+                                  "episode_rot24"])
 def test_episode_matches_reference_golden(name):
     d = load_golden(name)
     lib = lib_from_fixture(d)
