@@ -30,6 +30,8 @@ struct irbpp_env {
     bool scan_current = false;        // the scan scratch holds the drop heights of every bin's cur_item
     int32_t* heur_pose_dev = nullptr; int64_t* heur_index_dev = nullptr;
     bool results_on_host = false;           // the pending step wrote its results straight to the host mirror
+    int host_results_mode = 0;              // IRBPP_HOST_RESULTS: 0 per-bin stores over PCIe (default), 1 copy kernel, 2 cudaMemcpyAsync in step_wait
+    int host_actions_mode = 0;              // IRBPP_HOST_ACTIONS: 0 read over PCIe by the kernel (default), 1 cudaMemcpyAsync in front of it
     cudaStream_t pending_stream = nullptr;
     int64_t launches = 0;
     // device allocations
@@ -120,6 +122,8 @@ int irbpp_create(const irbpp_config* cfg, irbpp_handle* out) {
 
     irbpp_env* h = new irbpp_env();
     h->cfg = *cfg;
+    if (const char* m = getenv("IRBPP_HOST_RESULTS")) h->host_results_mode = !strcmp(m, "kernel") ? 1 : (!strcmp(m, "memcpy") ? 2 : 0);
+    if (const char* m = getenv("IRBPP_HOST_ACTIONS")) h->host_actions_mode = !strcmp(m, "memcpy") ? 1 : 0;
     Params& P = h->P;
     memset(&P, 0, sizeof(P));
     const int N = cfg->num_envs;
@@ -357,6 +361,12 @@ int irbpp_set_sequences(irbpp_handle h, const int32_t* ids, int32_t length) {
 // candidates kernel when the observation carries candidate rows.  (Running bin ranges on separate
 // streams so that one range's candidates kernel overlaps the next range's scan kernel was measured:
 // no gain -- the scan kernel owns the whole register file, the two cannot co-reside.)
+// Experiment knob (IRBPP_HOST_RESULTS=kernel): the 31 B/bin result block device -> host-mapped memory
+// as one coalesced copy after the step's kernels, instead of eight small stores per bin over PCIe.
+__global__ void irbpp_copy_block_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src, int n16) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
 static int launch(irbpp_env* h, Params& P, cudaStream_t s) {
     P.env_lo = 0;
     P.env_hi = P.N;
@@ -426,19 +436,31 @@ static int step_async_impl(irbpp_env* h, const int64_t* actions, int32_t on_devi
         // bin) -- no separate copy node in front of the kernel; results go back the same way (posted stores)
         memcpy(h->actions_pinned, actions, (size_t)P.N * sizeof(int64_t));
         P.actions = h->actions_mapped;
+        if (h->host_actions_mode == 1) {
+            CUDA_TRY(h, cudaMemcpyAsync(h->actions_dev, h->actions_pinned, (size_t)P.N * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+            P.actions = h->actions_dev;
+        }
         char* b = h->results_mapped;
         const size_t N = P.N;
-        P.h_ratio = reinterpret_cast<double*>(b); b += N * 8;
-        P.h_eprew = reinterpret_cast<double*>(b); b += N * 8;
-        P.h_reward = reinterpret_cast<float*>(b); b += N * 4;
-        P.h_counter = reinterpret_cast<int32_t*>(b); b += N * 4;
-        P.h_eplen = reinterpret_cast<int32_t*>(b); b += N * 4;
-        P.h_done = reinterpret_cast<uint8_t*>(b); b += N;
-        P.h_valid = reinterpret_cast<uint8_t*>(b); b += N;
-        P.h_error = reinterpret_cast<uint8_t*>(b);
+        if (h->host_results_mode == 0) {
+            P.h_ratio = reinterpret_cast<double*>(b); b += N * 8;
+            P.h_eprew = reinterpret_cast<double*>(b); b += N * 8;
+            P.h_reward = reinterpret_cast<float*>(b); b += N * 4;
+            P.h_counter = reinterpret_cast<int32_t*>(b); b += N * 4;
+            P.h_eplen = reinterpret_cast<int32_t*>(b); b += N * 4;
+            P.h_done = reinterpret_cast<uint8_t*>(b); b += N;
+            P.h_valid = reinterpret_cast<uint8_t*>(b); b += N;
+            P.h_error = reinterpret_cast<uint8_t*>(b);
+        }
     }
-    h->results_on_host = !on_device;
+    h->results_on_host = !on_device && h->host_results_mode != 2;
     rc = launch(h, P, s); if (rc) return rc;
+    if (!on_device && h->host_results_mode == 1) {
+        const int n16 = (int)((h->results_bytes + 15) / 16);           // both blocks are allocated with 64 bytes of slack
+        irbpp_copy_block_kernel<<<8, 256, 0, s>>>(reinterpret_cast<uint4*>(h->results_mapped),
+                                                 reinterpret_cast<const uint4*>(h->results_dev), n16);
+        h->launches += 1;
+    }
     h->waiting_step = true; h->pending_stream = s;
     return IRBPP_OK;
 }
