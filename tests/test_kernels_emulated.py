@@ -1,0 +1,152 @@
+"""The CUDA kernels of ir-bpp_b200/csrc/ executed on host threads (tests/host_harness/cuda_emu.h: one
+thread per CUDA thread of one block at a time, real barriers, warp collectives as slot exchanges) and
+compared with the golden episodes of the unmodified reference.  TEST INFRASTRUCTURE ONLY: it checks the
+kernel-level logic (barrier structure, hand-overs, warp collectives) where no GPU exists; the emulated
+library exports ``emu_irbpp_*`` symbols, which ``irbpp_b200._lib`` cannot bind, and lives in a temp dir.
+The parity tests proper are the ``-m gpu`` tests, which run the real kernels on a B200."""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import lib_from_fixture, load_golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "ir-bpp_b200", "csrc")
+HARNESS = os.path.join(ROOT, "tests", "host_harness")
+
+
+def _host_source(text):
+    """Storage qualifiers and launch syntax of the device source rewritten for g++."""
+    text = re.sub(r"extern __shared__ __align__\((\d+)\)", r"alignas(\1) extern", text)
+    text = re.sub(r"__shared__ __align__\((\d+)\)", r"alignas(\1) static", text)
+    text = text.replace("extern __shared__", "extern").replace("__shared__", "static")
+    text = re.sub(r'^\s*asm volatile\("griddepcontrol.*$', ";", text, flags=re.M)
+    text = text.replace("#include <cuda_runtime.h>", '#include "cuda_emu.h"')
+    text = re.sub(r"(\w+)<<<([^;]*?)>>>\(", lambda m: "CUDA_EMU_LAUNCH(%s, %s, " % (m.group(1), m.group(2)), text, flags=re.S)
+    return text
+
+
+def build_emulated(tmp, defs=()):
+    names = re.findall(r"\b(irbpp_[a-z_]+)\(", open(os.path.join(ROOT, "include", "irbpp.h")).read())
+    csrc = os.path.join(tmp, "pkg", "csrc")               # irbpp.cu includes "../../include/irbpp.h"
+    os.makedirs(csrc, exist_ok=True)
+    os.makedirs(os.path.join(tmp, "include"), exist_ok=True)
+    for fn in os.listdir(CSRC):
+        with open(os.path.join(csrc, fn), "w") as f:
+            f.write(_host_source(open(os.path.join(CSRC, fn)).read()))
+    for src, dst in ((os.path.join(ROOT, "include", "irbpp.h"), os.path.join(tmp, "include", "irbpp.h")),
+                     (os.path.join(HARNESS, "cuda_emu.h"), os.path.join(csrc, "cuda_emu.h"))):
+        open(dst, "w").write(open(src).read())
+    main = os.path.join(csrc, "emu_main.cpp")
+    with open(main, "w") as f:
+        f.write('#include "cuda_emu.h"\n#include "irbpp.cu"\n'
+                "namespace irbpp { alignas(16) unsigned char smem_raw[512 * 1024]; alignas(16) TileEntry estage[1 << 16]; }\n")
+    # the C-ABI entry points get emu_ names: this library can never stand in for the product's
+    rename = ["-D%s=emu_%s" % (n, n) for n in sorted(set(names))]
+    out = os.path.join(tmp, "libirbpp_emulated.so")
+    cmd = ["g++", "-O1", "-std=c++17", "-pthread", "-ffp-contract=off", "-Wno-unknown-pragmas", "-shared", "-fPIC",
+           "-I", csrc] + rename + list(defs) + ["-o", out, main]
+    subprocess.run(cmd, check=True)
+    return ctypes.CDLL(out)
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    return build_emulated(str(tmp_path_factory.mktemp("emu")))
+
+
+class _Cfg(ctypes.Structure):
+    _fields_ = [("num_envs", ctypes.c_int32), ("num_rotations", ctypes.c_int32), ("selected_action", ctypes.c_int32),
+                ("buffer_size", ctypes.c_int32), ("bin_dimension", ctypes.c_double * 3), ("resolution_act", ctypes.c_double),
+                ("resolution_h", ctypes.c_double), ("resolution_z", ctypes.c_double), ("device", ctypes.c_int32),
+                ("approx_legacy", ctypes.c_int32)]
+
+
+class _Res(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_void_p) for n in ("reward", "done", "valid", "error", "counter", "ep_len", "ratio", "ep_reward")]
+
+
+class EmuEnv(object):
+    """The C ABI of include/irbpp.h driven with NumPy buffers (device == host under the emulation)."""
+
+    def __init__(self, lib, library, sequences, selected_action=500, buffer_size=1):
+        self.lib, self.n = lib, len(sequences)
+        cfg = _Cfg(self.n, library.num_rotations, selected_action, buffer_size, (ctypes.c_double * 3)(0.32, 0.32, 0.30),
+                   0.02, 0.01, 0.01, 0, 0)
+        self.h = ctypes.c_void_p()
+        assert lib.emu_irbpp_create(ctypes.byref(cfg), ctypes.byref(self.h)) == 0
+        dims, ext, vol, maps, offsets = library.flat()
+        P = ctypes.c_void_p
+        assert lib.emu_irbpp_load_shapes(self.h, library.num_shapes, library.num_rotations, P(dims.ctypes.data),
+                                         P(ext.ctypes.data), P(vol.ctypes.data), P(maps.ctypes.data),
+                                         P(offsets.ctypes.data), ctypes.c_int64(maps.size)) == 0
+        seqs = np.ascontiguousarray(sequences, dtype=np.int32)
+        assert lib.emu_irbpp_set_sequences(self.h, P(seqs.ctypes.data), seqs.shape[1]) == 0
+        o, l, k = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int32()
+        lib.emu_irbpp_obs_len(self.h, ctypes.byref(o), ctypes.byref(l), ctypes.byref(k))
+        self.obs_len, self.loc_len = o.value, l.value
+
+    def reset(self):
+        obs = np.zeros((self.n, self.obs_len), np.float32)
+        assert self.lib.emu_irbpp_reset(self.h, None, ctypes.c_void_p(obs.ctypes.data), None) == 0
+        return obs
+
+    def step(self, actions):
+        acts = np.ascontiguousarray(actions, dtype=np.int64)
+        obs = np.zeros((self.n, self.obs_len), np.float32)
+        assert self.lib.emu_irbpp_step_async(self.h, ctypes.c_void_p(acts.ctypes.data), 0, ctypes.c_void_p(obs.ctypes.data), None) == 0
+        res = _Res()
+        assert self.lib.emu_irbpp_step_wait(self.h, ctypes.byref(res)) == 0, self.lib.emu_irbpp_last_error(self.h)
+        view = lambda p, ct, dt: np.frombuffer((ct * self.n).from_address(p), dtype=dt).copy()
+        return (obs, view(res.reward, ctypes.c_float, np.float32), view(res.done, ctypes.c_uint8, np.bool_),
+                view(res.counter, ctypes.c_int32, np.int32), view(res.ratio, ctypes.c_double, np.float64))
+
+    def get_action_candidates(self, order):
+        order = np.ascontiguousarray(order, dtype=np.int64)
+        loc = np.zeros((self.n, self.loc_len), np.float32)
+        assert self.lib.emu_irbpp_get_action_candidates(self.h, ctypes.c_void_p(order.ctypes.data), 0,
+                                                        ctypes.c_void_p(loc.ctypes.data), None) == 0
+        return loc
+
+    def close(self):
+        self.lib.emu_irbpp_destroy(self.h)
+
+
+def _replay(lib, name, steps):
+    d = load_golden(name)
+    env = EmuEnv(lib, lib_from_fixture(d), d["sequences"], selected_action=int(d["selectedAction"]),
+                 buffer_size=int(d["bufferSize"]))
+    obs = env.reset()
+    assert np.array_equal(obs, d["obs"][0].astype(np.float32))
+    for t in range(min(steps, len(d["actions"]))):
+        if int(d["bufferSize"]) > 1:
+            assert np.array_equal(env.get_action_candidates(d["order"][t]), d["loc_obs"][t].astype(np.float32)), t
+        obs, rew, done, counter, ratio = env.step(d["actions"][t])
+        assert np.array_equal(obs, d["obs"][t + 1].astype(np.float32)), (name, t)
+        assert np.array_equal(rew, d["reward"][t].astype(np.float32)) and np.array_equal(done, d["done"][t])
+        for i in np.nonzero(done)[0]:
+            assert counter[i] == d["counter"][t][i] and ratio[i] == d["ratio"][t][i]
+    env.close()
+
+
+@pytest.mark.parametrize("name,steps", [("episode_blockout", 12), ("episode_irregular", 5), ("episode_truncate", 6),
+                                        ("episode_buffered", 6)])
+def test_emulated_kernels_replay_reference_episodes(emu, name, steps):
+    _replay(emu, name, steps)
+
+
+@pytest.fixture(scope="module")
+def emu_coop(tmp_path_factory):
+    # threshold lowered from 17 to 6 points so that most contours of these short episodes take the warp path
+    return build_emulated(str(tmp_path_factory.mktemp("emu_coop")), defs=["-DIRBPP_COOP_APPROX", "-DIRBPP_COOP_MIN=6"])
+
+
+@pytest.mark.parametrize("name,steps", [("episode_irregular", 5), ("episode_blockout", 8), ("episode_truncate", 4)])
+def test_emulated_cooperative_variant_replays_reference_episodes(emu_coop, name, steps):
+    """The experimental build switch IRBPP_COOP_APPROX (long contours by a whole warp, off in the default
+    build) through the same episodes."""
+    _replay(emu_coop, name, steps)
