@@ -150,3 +150,81 @@ def test_emulated_cooperative_variant_replays_reference_episodes(emu_coop, name,
     """The experimental build switch IRBPP_COOP_APPROX (long contours by a whole warp, off in the default
     build) through the same episodes."""
     _replay(emu_coop, name, steps)
+
+
+def _P(a):
+    return ctypes.c_void_p(a.ctypes.data)
+
+
+@pytest.mark.parametrize("tag", ["blockout", "irregular", "cube"])
+def test_emulated_scan_matches_reference_golden(emu, tag):
+    """Verbatim Space.get_possible_position outputs (scan goldens) through irbpp_debug_scan."""
+    d = load_golden("scan_" + tag)
+    lib = lib_from_fixture(d)
+    n, R = len(d["item_ids"]), lib.num_rotations
+    env = EmuEnv(emu, lib, np.zeros((n, 8), np.int32))
+    hm = np.ascontiguousarray(d["heightmaps"], dtype=np.float64)
+    assert emu.emu_irbpp_debug_set_heightmap(env.h, _P(hm)) == 0
+    items = np.ascontiguousarray(d["item_ids"], dtype=np.int32)
+    pz, pv, mk = np.zeros((n, R, 16, 16)), np.zeros((n, R, 16, 16)), np.zeros((n, R, 16, 16))
+    cand, nh = np.zeros((n, 500, 5)), np.zeros(n, np.int32)
+    assert emu.emu_irbpp_debug_scan(env.h, _P(items), _P(pz), _P(pv), _P(mk), _P(cand), _P(nh)) == 0
+    assert np.array_equal(pz, d["posZmap"]) and np.array_equal(pv, d["posZValid"]) and np.array_equal(mk, d["naiveMask"])
+    env.close()
+
+
+def test_emulated_hull_actions_match_reference_golden(emu):
+    """Verbatim cvTools.getConvexHullActions outputs (hull goldens) through irbpp_debug_hulls."""
+    from irbpp_b200 import shapes
+    d = load_golden("hulls")
+    n = len(d["counts"])
+    env = EmuEnv(emu, shapes.make_cube_library(seed=1, num_rotations=1, num_shapes=4), np.zeros((n, 8), np.int32),
+                 selected_action=256)
+    pv = np.ascontiguousarray(d["posZValid"][:, None], dtype=np.float64)
+    mk = np.ascontiguousarray(d["mask"][:, None], dtype=np.float64)
+    cand, nh = np.zeros((n, 256, 5)), np.zeros(n, np.int32)
+    assert emu.emu_irbpp_debug_hulls(env.h, _P(pv), _P(mk), _P(cand), _P(nh)) == 0
+    off = 0
+    for k in range(n):
+        c = int(d["counts"][k])
+        assert nh[k] == c, k
+        if c:
+            assert np.array_equal(cand[k, :c], d["rows"][off:off + c]), k
+        off += c
+    env.close()
+
+
+def test_emulated_heuristics_match_reference_golden(emu):
+    """Verbatim Space.get_heuristic_action (4 scores x 4 directions) and the pose step, first steps of the
+    irregular heuristic episode."""
+    d = load_golden("heuristic_irregular")
+    lib = lib_from_fixture(d)
+    env = EmuEnv(emu, lib, d["sequences"])
+    n = env.n
+    assert np.array_equal(env.reset(), d["obs"][0])
+    for t in range(4):
+        for mi in range(4):
+            for k in range(4):
+                poses, index = np.zeros((n, 3), np.int32), np.zeros(n, np.int64)
+                assert emu.emu_irbpp_heuristic_actions(env.h, mi, k, _P(poses), _P(index), 0, None) == 0
+                assert np.array_equal(poses, d["poses"][t, mi, k]) and np.array_equal(index, d["index"][t, mi, k]), (t, mi, k)
+        acts = np.ascontiguousarray(d["actions"][t], dtype=np.int64)
+        obs = np.zeros((n, env.obs_len), np.float32)
+        assert emu.emu_irbpp_step_poses_async(env.h, _P(acts), 0, _P(obs), None) == 0
+        assert emu.emu_irbpp_step_wait(env.h, None) == 0
+        assert np.array_equal(obs, d["obs"][t + 1]), t
+    env.close()
+
+
+def test_emulated_24_rotations(emu):
+    """R = 24: run-time sized scratch, > 1024 candidates per bin, exact bucketed ranking."""
+    _replay(emu, "episode_rot24", 3)
+
+
+@pytest.mark.parametrize("results,actions", [("kernel", "memcpy"), ("memcpy", "mapped")])
+def test_emulated_host_transport_knobs(emu, monkeypatch, results, actions):
+    """IRBPP_HOST_RESULTS / IRBPP_HOST_ACTIONS (experiment knobs of the host path, read at irbpp_create):
+    the alternative transports deliver the same step results."""
+    monkeypatch.setenv("IRBPP_HOST_RESULTS", results)
+    monkeypatch.setenv("IRBPP_HOST_ACTIONS", actions)
+    _replay(emu, "episode_blockout", 6)
