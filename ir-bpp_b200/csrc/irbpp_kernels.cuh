@@ -891,13 +891,15 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
 #ifdef IRBPP_COOP_APPROX
             // Experimental (not the default build): contours of COOP_MIN points or more -- the tail that
             // decides when the CTA, and with it the kernel, ends -- are taken one per WARP (dp_keep_warp:
-            // lanes = points), the rest one per lane as before.
+            // lanes = points), the rest one per lane as before.  The long contours go to the LAST warps
+            // first: in the per-lane part below those carry the shortest contours of the batch, so the
+            // warp-level and the lane-level work overlap instead of queueing up in warp 0.
 #ifndef IRBPP_COOP_MIN
 #define IRBPP_COOP_MIN 17
 #endif
             constexpr int COOP_MIN = IRBPP_COOP_MIN;
             const int ncoop = S.hbase[64 - COOP_MIN];          // entries of the buckets with npts >= COOP_MIN
-            for (int c = warp; c < ncoop; c += CAND_WARPS) {
+            for (int c = CAND_WARPS - 1 - warp; c < ncoop; c += CAND_WARPS) {
                 const int owner = S.order2[c];
                 const int on = S.n_of[owner];
                 StridedScratch<32, FAST_CAP> sc;
