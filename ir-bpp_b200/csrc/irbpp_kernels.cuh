@@ -331,6 +331,20 @@ __global__ void __launch_bounds__(CTA_THREADS, IRBPP_SCAN_MIN_CTAS) irbpp_scan_k
         if (warp == 0) reinterpret_cast<uint32_t*>(&st_s)[lane] = stw;
     }
     if (tid == 0) { err_sh = 0; any_sh = 0; }
+#ifdef IRBPP_PREFETCH_NEXT
+    // Experimental (not the default build): the grid runs in waves of IRBPP_PREFETCH_NEXT resident CTAs; pull
+    // the heightmap, state and action of the bin a later wave will handle into L2 (no semantic effect), so
+    // that wave's dependent chain starts from L2 instead of DRAM.
+    {
+        const int nxt = env + IRBPP_PREFETCH_NEXT;
+        if (mode == MODE_STEP && nxt < P.env_hi) {
+            const char* hp = reinterpret_cast<const char*>(P.hm + (int64_t)nxt * (HX * HY));
+            if (tid < 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(hp + tid * 128));
+            if (tid == 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.state + nxt));
+            if (tid == 65) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.actions + nxt));
+        }
+    }
+#endif
     __syncthreads();
 
     int32_t* queue_g = st_s.queue;
