@@ -24,7 +24,7 @@ def _host_source(text):
     text = re.sub(r"extern __shared__ __align__\((\d+)\)", r"alignas(\1) extern", text)
     text = re.sub(r"__shared__ __align__\((\d+)\)", r"alignas(\1) static", text)
     text = text.replace("extern __shared__", "extern").replace("__shared__", "static")
-    text = re.sub(r'^\s*asm volatile\("griddepcontrol.*$', ";", text, flags=re.M)
+    text = re.sub(r'asm volatile\("(griddepcontrol|prefetch)[^\n]*\);', ";", text)
     text = text.replace("#include <cuda_runtime.h>", '#include "cuda_emu.h"')
     text = re.sub(r"(\w+)<<<([^;]*?)>>>\(", lambda m: "CUDA_EMU_LAUNCH(%s, %s, " % (m.group(1), m.group(2)), text, flags=re.S)
     return text
