@@ -509,3 +509,18 @@ def test_heuristic_policy_matches_oracle_at_scale():
     po, io = orab.heuristic_actions("DBLF", 1)
     assert np.array_equal(pg, po) and np.array_equal(ig, io)
     envb.close()
+
+
+@pytest.mark.gpu
+def test_survey_known_answers_on_device():
+    """the known-answer level sets of the unmodified cvTools (rectangle, pixel, line, L
+    with a collapsing notch, ring + island, diagonals, the two-level map) through irbpp_debug_hulls."""
+    from irbpp_b200 import shapes
+    from test_kernels_emulated import check_kats
+    env = _env(shapes.make_cube_library(seed=1, num_rotations=1, num_shapes=4), _dummy_seqs(8, None), selected_action=256)
+
+    def run(pv, mk):
+        out = env.debug_hulls(pv, mk)
+        return out["cand"], out["num_hull"]
+    check_kats(run)
+    env.close()

@@ -228,3 +228,43 @@ def test_emulated_host_transport_knobs(emu, monkeypatch, results, actions):
     monkeypatch.setenv("IRBPP_HOST_RESULTS", results)
     monkeypatch.setenv("IRBPP_HOST_ACTIONS", actions)
     _replay(emu, "episode_blockout", 6)
+
+
+def _kat_inputs():
+    """The SURVEY section 4 known-answer maps (8 x 8) embedded in the 16 x 16 action grid, masked outside."""
+    d = load_golden("kats")
+    names = ["rect", "pixel", "hline", "L", "ring_island", "diag", "diag_squares", "twolevel"]
+    pv = np.full((len(names), 1, 16, 16), 1e3)
+    mk = np.zeros((len(names), 1, 16, 16))
+    for i, k in enumerate(names):
+        pv[i, 0, :8, :8] = d["kat_%s_posz" % k]
+        mk[i, 0, :8, :8] = d["kat_%s_mask" % k]
+    pv[mk == 0] = 1e3
+    return d, names, pv, mk
+
+
+def check_kats(run_hulls):
+    """``run_hulls(posZValid[n,1,16,16], mask) -> (cand[n,sel,5], num_hull[n])``; shared with the GPU test."""
+    from test_oracle_golden import SURVEY_KATS
+    d, names, pv, mk = _kat_inputs()
+    cand, nh = run_hulls(pv, mk)
+    for i, k in enumerate(names[:-1]):
+        rows = cand[i, :int(nh[i])]
+        assert [[int(r[2]), int(r[1])] for r in rows] == SURVEY_KATS[k], k          # (col, row), np.unique order
+        assert np.all(rows[:, 4] == 1) and np.all(rows[:, 3] == 0.05)
+    assert cand[-1, :int(nh[-1])].tolist() == d["kat_twolevel_rows"].tolist()
+
+
+def test_emulated_survey_known_answers(emu):
+    from irbpp_b200 import shapes
+    n = 8
+    env = EmuEnv(emu, shapes.make_cube_library(seed=1, num_rotations=1, num_shapes=4), np.zeros((n, 8), np.int32),
+                 selected_action=256)
+
+    def run(pv, mk):
+        cand, nh = np.zeros((n, 256, 5)), np.zeros(n, np.int32)
+        pv, mk = np.ascontiguousarray(pv), np.ascontiguousarray(mk)
+        assert emu.emu_irbpp_debug_hulls(env.h, _P(pv), _P(mk), _P(cand), _P(nh)) == 0
+        return cand, nh
+    check_kats(run)
+    env.close()
