@@ -524,3 +524,17 @@ def test_survey_known_answers_on_device():
         return out["cand"], out["num_hull"]
     check_kats(run)
     env.close()
+
+
+@pytest.mark.gpu
+def test_many_start_pixels_on_device():
+    """More start pixels in a round than the task table lists (search fallback, several batches)."""
+    from irbpp_b200 import shapes
+    from test_kernels_emulated import check_many_start_pixels
+    env = _env(shapes.make_cube_library(seed=1, num_rotations=1, num_shapes=4), _dummy_seqs(4, None), selected_action=256)
+
+    def run(pv, mk):
+        out = env.debug_hulls(pv, mk)
+        return out["cand"], out["num_hull"]
+    check_many_start_pixels(run)
+    env.close()

@@ -268,3 +268,40 @@ def test_emulated_survey_known_answers(emu):
         return cand, nh
     check_kats(run)
     env.close()
+
+
+def check_many_start_pixels(run_hulls):
+    """Level sets with > 100 start pixels per image (isolated pixels, sparse noise): more micro-tasks in a
+    round than the task table lists (the search fallback) and several batches per round; vs the oracle."""
+    from oracle.oracle_env import convex_hull_actions
+    rng = np.random.default_rng(5)
+    n = 4
+    pv = np.full((n, 1, 16, 16), 1e3)
+    mk = np.zeros((n, 1, 16, 16))
+    xs, ys = np.meshgrid(np.arange(16), np.arange(16), indexing="ij")
+    # bins 0, 1: every pixel feasible, neighbours always on different levels -> four level images of 64
+    # isolated pixels each (256 start pixels per bin, 512 in the CTA's round: beyond the 256-entry table)
+    for i in (0, 1):
+        mk[i, 0] = 1
+        pv[i, 0] = 0.015 + 0.01 * ((xs % 2) + 2 * (ys % 2)) + 0.04 * i
+    for i, pat in ((2, rng.random((16, 16)) < 0.35), (3, (xs % 2 == 0) & (ys % 2 == 0))):
+        mk[i, 0][pat] = 1
+        pv[i, 0][pat] = 0.03 * (i - 1)
+    cand, nh = run_hulls(pv, mk)
+    for i in range(n):
+        want = convex_hull_actions(pv[i], mk[i], 0.01, "port")
+        assert nh[i] == len(want) and np.array_equal(cand[i, :len(want)], want), i
+
+
+def test_emulated_many_start_pixels(emu):
+    from irbpp_b200 import shapes
+    env = EmuEnv(emu, shapes.make_cube_library(seed=1, num_rotations=1, num_shapes=4), np.zeros((4, 8), np.int32),
+                 selected_action=256)
+
+    def run(pv, mk):
+        cand, nh = np.zeros((4, 256, 5)), np.zeros(4, np.int32)
+        pv, mk = np.ascontiguousarray(pv), np.ascontiguousarray(mk)
+        assert emu.emu_irbpp_debug_hulls(env.h, _P(pv), _P(mk), _P(cand), _P(nh)) == 0
+        return cand, nh
+    check_many_start_pixels(run)
+    env.close()
