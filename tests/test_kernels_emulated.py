@@ -305,3 +305,15 @@ def test_emulated_many_start_pixels(emu):
         return cand, nh
     check_many_start_pixels(run)
     env.close()
+
+
+@pytest.fixture(scope="module")
+def emu_split(tmp_path_factory):
+    return build_emulated(str(tmp_path_factory.mktemp("emu_split")), defs=["-DIRBPP_SPLIT_APPLY"])
+
+
+@pytest.mark.parametrize("name,steps", [("episode_blockout", 70), ("episode_buffered", 12), ("episode_truncate", 5)])
+def test_emulated_split_apply_variant_replays_reference_episodes(emu_split, name, steps):
+    """The experimental build switch IRBPP_SPLIT_APPLY (phase A as its own one-warp-per-bin kernel, off in
+    the default build): the full BlockOut episode incl. terminal steps, the buffered protocol, truncation."""
+    _replay(emu_split, name, steps)

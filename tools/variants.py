@@ -7,6 +7,7 @@
 
 Known switches (csrc/): IRBPP_COOP_APPROX  contours of >= 17 points by a whole warp (dp_keep_warp)
                         IRBPP_PROBE_FINE   slots 4-7 of the phase counters time the sub-phases of phase C
+                        IRBPP_SPLIT_APPLY  phase A (apply the action) as its own one-warp-per-bin kernel in front of the scan
                         IRBPP_PREFETCH_NEXT=1184   scan CTAs prefetch the inputs of the bin a later wave handles into L2
                         IRBPP_ENVS_PER_CTA / IRBPP_CAND_WARPS / IRBPP_SCAN_MIN_CTAS   CTA shapes
 Run-time knobs of the host path (environment, read at irbpp_create; defaults = what bench.py's e2e measures):
