@@ -56,6 +56,7 @@ struct Barrier {
 };
 
 constexpr int MAX_WARPS = 32;
+static unsigned char* dyn_smem = nullptr;      // the launch's dynamic shared memory, exactly as many bytes as requested
 static Barrier cta_bar;
 static Barrier warp_bar[MAX_WARPS];
 static uint64_t slots[MAX_WARPS][32];
@@ -76,8 +77,12 @@ template <class T> static inline uint64_t pack(T v) { uint64_t u = 0; memcpy(&u,
 template <class T> static inline T unpack(uint64_t u) { T v; memcpy(&v, &u, sizeof(T)); return v; }
 
 template <class K, class... A>
-static void launch(K kernel, int grid, int block, A... args) {
+static void launch(K kernel, int grid, int block, size_t smem_bytes, A... args) {
     gridDim.x = (unsigned)grid; blockDim.x = (unsigned)block; cta_threads = block;
+    // a heap block of exactly the requested size: an address sanitizer then sees any access beyond it
+    void* mem = nullptr;
+    if (posix_memalign(&mem, 16, smem_bytes ? smem_bytes : 16)) abort();
+    dyn_smem = static_cast<unsigned char*>(mem);
     for (int b = 0; b < grid; ++b) {
         std::vector<std::thread> th;
         th.reserve(block);
@@ -85,6 +90,8 @@ static void launch(K kernel, int grid, int block, A... args) {
             th.emplace_back([=] { threadIdx.x = (unsigned)t; blockIdx.x = (unsigned)b; kernel(args...); });
         for (auto& x : th) x.join();
     }
+    dyn_smem = nullptr;
+    free(mem);
 }
 
 }  // namespace cuda_emu
@@ -171,7 +178,7 @@ static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cuda
 template <class K> static inline cudaError_t cudaFuncSetAttribute(K, cudaFuncAttribute, int) { return cudaSuccess; }
 template <class K, class... A>
 static inline cudaError_t cudaLaunchKernelEx(const cudaLaunchConfig_t* c, K kernel, A... args) {
-    cuda_emu::launch(kernel, (int)c->gridDim.x, (int)c->blockDim.x, args...);
+    cuda_emu::launch(kernel, (int)c->gridDim.x, (int)c->blockDim.x, c->dynamicSmemBytes, args...);
     return cudaSuccess;
 }
-#define CUDA_EMU_LAUNCH(kernel, grid, block, smem, stream, ...) cuda_emu::launch(kernel, (int)(grid), (int)(block), __VA_ARGS__)
+#define CUDA_EMU_LAUNCH(kernel, grid, block, smem, stream, ...) cuda_emu::launch(kernel, (int)(grid), (int)(block), (size_t)(smem), __VA_ARGS__)

@@ -21,7 +21,9 @@ HARNESS = os.path.join(ROOT, "tests", "host_harness")
 
 def _host_source(text):
     """Storage qualifiers and launch syntax of the device source rewritten for g++."""
-    text = re.sub(r"extern __shared__ __align__\((\d+)\)", r"alignas(\1) extern", text)
+    # dynamic shared memory: a pointer to the launch's heap block (sized as requested) instead of an unsized array
+    text = re.sub(r"extern __shared__ __align__\(\d+\) ([\w ]+?) (\w+)\[\];",
+                  r"\1* \2 = reinterpret_cast<\1*>(cuda_emu::dyn_smem);", text)
     text = re.sub(r"__shared__ __align__\((\d+)\)", r"alignas(\1) static", text)
     text = text.replace("extern __shared__", "extern").replace("__shared__", "static")
     text = re.sub(r'asm volatile\("(griddepcontrol|prefetch)[^\n]*\);', ";", text)
@@ -43,8 +45,7 @@ def build_emulated(tmp, defs=()):
         open(dst, "w").write(open(src).read())
     main = os.path.join(csrc, "emu_main.cpp")
     with open(main, "w") as f:
-        f.write('#include "cuda_emu.h"\n#include "irbpp.cu"\n'
-                "namespace irbpp { alignas(16) unsigned char smem_raw[512 * 1024]; alignas(16) TileEntry estage[1 << 16]; }\n")
+        f.write('#include "cuda_emu.h"\n#include "irbpp.cu"\n')
     # the C-ABI entry points get emu_ names: this library can never stand in for the product's
     rename = ["-D%s=emu_%s" % (n, n) for n in sorted(set(names))]
     out = os.path.join(tmp, "libirbpp_emulated.so")
