@@ -5,6 +5,12 @@
         -> ir-bpp_b200/lib/libirbpp_coop.so, libirbpp_fine.so   (they travel with gpurun like the default .so)
     python tools/variants.py bench coop            # GPU: parity tests of the episode goldens + bench.py per variant
 
+First GPU call of a round (everything below is checked under the CUDA emulator, none of it is timed yet):
+    python tools/variants.py build coop=-DIRBPP_COOP_APPROX split=-DIRBPP_SPLIT_APPLY \\
+        split10=-DIRBPP_SPLIT_APPLY,-DIRBPP_SCAN_MIN_CTAS=10 both=-DIRBPP_COOP_APPROX,-DIRBPP_SPLIT_APPLY \\
+        pf=-DIRBPP_PREFETCH_NEXT=1184
+    python tools/variants.py bench coop split split10 both pf
+
 Known switches (csrc/): IRBPP_COOP_APPROX  contours of >= 17 points by a whole warp (dp_keep_warp)
                         IRBPP_PROBE_FINE   slots 4-7 of the phase counters time the sub-phases of phase C
                         IRBPP_SPLIT_APPLY  phase A (apply the action) as its own one-warp-per-bin kernel in front of the scan
