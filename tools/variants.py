@@ -35,6 +35,8 @@ def lib_path(name):
 
 
 def main():
+    if len(sys.argv) < 2:
+        raise SystemExit(__doc__)
     cmd, args = sys.argv[1], sys.argv[2:]
     if cmd == "build":
         from irbpp_b200 import build as b
