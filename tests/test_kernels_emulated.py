@@ -14,6 +14,8 @@ import pytest
 
 from conftest import lib_from_fixture, load_golden
 
+pytestmark = pytest.mark.timeout(900)          # a deadlocked emulated barrier must not hang the suite
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CSRC = os.path.join(ROOT, "ir-bpp_b200", "csrc")
 HARNESS = os.path.join(ROOT, "tests", "host_harness")
