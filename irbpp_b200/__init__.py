@@ -1,8 +1,7 @@
-"""Import alias: the package directory is ``ir-bpp_b200/`` (not a valid Python
-identifier), so ``import irbpp_b200`` resolves its submodules from there."""
-import os as _os
+"""irbpp_b200: B200-native packing-environment hot path of IR-BPP.
 
-_real = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "ir-bpp_b200")
-__path__ = [_real]
-with open(_os.path.join(_real, "__init__.py")) as _f:
-    exec(compile(_f.read(), _os.path.join(_real, "__init__.py"), "exec"))
+Submodules (imported lazily so CPU-only tooling can use ``shapes`` without the
+CUDA library): ``shapes`` (shape tables), ``_lib`` (ctypes binding of the C-ABI
+in ``include/irbpp.h``), ``vec_env`` (the reference's VecEnv surface on the GPU),
+``envs`` (``make_vec_envs`` mirror), ``sharding`` (multi-GPU)."""
+__version__ = "0.1.0"

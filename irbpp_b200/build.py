@@ -6,8 +6,10 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "csrc", "irbpp.cu")
-DEPS = [SRC, os.path.join(HERE, "csrc", "irbpp_kernels.cuh"), os.path.join(HERE, "csrc", "irbpp_contour.cuh"),
-        os.path.join(ROOT, "include", "irbpp.h")]
+import glob  # noqa: E402
+# every source the library is compiled from (all of csrc/ + the public header) + this file's flags
+DEPS = sorted(glob.glob(os.path.join(HERE, "csrc", "*.cu")) + glob.glob(os.path.join(HERE, "csrc", "*.cuh"))) + \
+    [os.path.join(ROOT, "include", "irbpp.h"), os.path.abspath(__file__)]
 OUT_DIR = os.path.join(HERE, "lib")
 OUT = os.path.join(OUT_DIR, "libirbpp.so")
 # experiment hook: extra -D flags and an alternative output name (IRBPP_LIB selects it at load time)

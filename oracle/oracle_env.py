@@ -2,7 +2,7 @@
 
 TEST INFRASTRUCTURE ONLY.  Only ``tests/``, ``__graft_entry__.smoke()`` and the
 ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import this
-module; the product (``ir-bpp_b200/``) never does and has no CPU fallback.
+module; the product (``irbpp_b200/``) never does and has no CPU fallback.
 
 What is restated, and where it comes from in the reference
 (paths relative to ``/root/reference``):

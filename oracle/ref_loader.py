@@ -1,6 +1,6 @@
 """Load the UNMODIFIED reference geometry modules for golden-vector generation.
 
-TEST INFRASTRUCTURE ONLY.  Nothing in the product path (``ir-bpp_b200/``) may
+TEST INFRASTRUCTURE ONLY.  Nothing in the product path (``irbpp_b200/``) may
 import this module.  It only works where ``/root/reference`` is mounted (the
 build container); the GPU box has no reference tree, which is why the vectors
 it produces are committed under ``tests/golden/``.

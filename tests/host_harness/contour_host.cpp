@@ -1,7 +1,7 @@
 // TEST-ONLY harness: compiles the per-thread device routines of
-// ir-bpp_b200/csrc/irbpp_contour.cuh (and the exact floor-divide of irbpp_math.cuh) as plain host
+// irbpp_b200/csrc/irbpp_contour.cuh (and the exact floor-divide of irbpp_math.cuh) as plain host
 // C++ so their logic can be checked against the oracle without a GPU.  It is never linked into the
-// product library and is not a CPU fallback: nothing under ir-bpp_b200/ references it.
+// product library and is not a CPU fallback: nothing under irbpp_b200/ references it.
 #include <math.h>
 #include <stdint.h>
 #define __device__
@@ -42,8 +42,8 @@ static unsigned reduce_max(unsigned v) {
 }
 }  // namespace warp_emu
 #define IRBPP_WARP_MAX(v) warp_emu::reduce_max(v)
-#include "../../ir-bpp_b200/csrc/irbpp_contour.cuh"
-#include "../../ir-bpp_b200/csrc/irbpp_math.cuh"
+#include "../../irbpp_b200/csrc/irbpp_contour.cuh"
+#include "../../irbpp_b200/csrc/irbpp_math.cuh"
 
 extern "C" int hull_bits(const uint16_t* rows16, int legacy, int mode, uint32_t* out_bits) {
     for (int i = 0; i < 8; ++i) out_bits[i] = 0;
@@ -68,7 +68,7 @@ extern "C" void floor_div_many(const double* a, double b, int n, double* out) {
     for (int i = 0; i < n; ++i) out[i] = irbpp::floor_divide_exact(a[i], b, inv);
 }
 
-#include "../../ir-bpp_b200/csrc/irbpp_heuristic.cuh"
+#include "../../irbpp_b200/csrc/irbpp_heuristic.cuh"
 
 // np.sum of n contiguous doubles as irbpp_math.cuh restates it (checked against NumPy itself)
 extern "C" double pairwise_sum_host(const double* a, int n) {

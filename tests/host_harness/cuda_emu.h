@@ -1,5 +1,5 @@
 // cuda_emu.h -- TEST-ONLY.  Just enough of the CUDA execution model to run the kernels of
-// ir-bpp_b200/csrc/ on host threads, so that kernel-level logic (barrier structure, warp collectives,
+// irbpp_b200/csrc/ on host threads, so that kernel-level logic (barrier structure, warp collectives,
 // shared-memory hand-overs) can be checked against the oracle in a container without a GPU:
 //   * one host thread per CUDA thread of ONE thread block at a time (blocks run one after another);
 //   * __shared__ variables become function-local statics (one block alive at a time);
@@ -7,7 +7,7 @@
 //     32-entry slot array between two warp barriers (full masks only, as the kernels use them);
 //   * the runtime API is mapped onto the host heap; "device" and "host" pointers are the same.
 // It is slow (thousands of thread switches per launch) and is never linked into the product: the
-// library built from it exports emu_irbpp_* names that ir-bpp_b200/_lib.py cannot bind.
+// library built from it exports emu_irbpp_* names that irbpp_b200/_lib.py cannot bind.
 #pragma once
 #include <math.h>
 #include <stdint.h>

@@ -1,4 +1,4 @@
-"""The CUDA kernels of ir-bpp_b200/csrc/ executed on host threads (tests/host_harness/cuda_emu.h: one
+"""The CUDA kernels of irbpp_b200/csrc/ executed on host threads (tests/host_harness/cuda_emu.h: one
 thread per CUDA thread of one block at a time, real barriers, warp collectives as slot exchanges) and
 compared with the golden episodes of the unmodified reference.  TEST INFRASTRUCTURE ONLY: it checks the
 kernel-level logic (barrier structure, hand-overs, warp collectives) where no GPU exists; the emulated
@@ -17,7 +17,7 @@ from conftest import lib_from_fixture, load_golden
 pytestmark = pytest.mark.timeout(900)          # a deadlocked emulated barrier must not hang the suite
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-CSRC = os.path.join(ROOT, "ir-bpp_b200", "csrc")
+CSRC = os.path.join(ROOT, "irbpp_b200", "csrc")
 HARNESS = os.path.join(ROOT, "tests", "host_harness")
 
 

@@ -2,7 +2,7 @@
 """Build experiment variants of the library next to the default one and (on a GPU box) compare them.
 
     python tools/variants.py build coop=-DIRBPP_COOP_APPROX fine=-DIRBPP_PROBE_FINE
-        -> ir-bpp_b200/lib/libirbpp_coop.so, libirbpp_fine.so   (they travel with gpurun like the default .so)
+        -> irbpp_b200/lib/libirbpp_coop.so, libirbpp_fine.so   (they travel with gpurun like the default .so)
     python tools/variants.py bench coop            # GPU: parity tests of the episode goldens + bench.py per variant
 
 First GPU call of a round (everything below is checked under the CUDA emulator, none of it is timed yet):
@@ -27,7 +27,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-LIB_DIR = os.path.join(ROOT, "ir-bpp_b200", "lib")
+LIB_DIR = os.path.join(ROOT, "irbpp_b200", "lib")
 
 
 def lib_path(name):
