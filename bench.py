@@ -1,19 +1,30 @@
 #!/usr/bin/env python
 """bench.py -- env-steps/s of the packing-environment hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W]            # B200 arm, one JSON line on rank 0
-    python bench.py --impl reference [--gpus N] --steps K --warmup W  # reference CPU arm (oracle port)
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config NAME]          # B200 arm, one JSON line on rank 0
+    python bench.py --impl reference [--gpus N] --steps K --warmup W [--config NAME]   # reference CPU arm (oracle port)
 
-A "step" is one batched ``step()`` of 4096 BlockOut bins per GPU (BASELINE.json configs[1]: online,
-selectedAction=500, R=4; synthetic polycube shapes and sequences).  For N > 1 the
-driver launches one rank per GPU with torch.distributed.run; bins are sharded by index (weak scaling:
-4096 per GPU), no collective inside a step, one NCCL all-gather of the observations at rollout end
-(inside the timed region).
+``--config`` selects one of BASELINE.json's configurations (default ``blockout`` = configs[1], the one the
+metric is quoted on):
 
-Timing: every timed step is bracketed by CUDA events on the launching stream; between timed steps
-the L2 is flushed by writing a 256 MiB buffer (outside the event pairs).  ``value`` uses actions that
-are already on the device; ``e2e`` calls the public ``GpuVecEnv.step`` with HOST actions (pinned H2D
-copy, kernel, D2H of reward/done/info arrays) and is timed with the host clock around the call.
+    blockout    BlockOut polycubes, 4096 bins/GPU, online, selectedAction=500, R=4           (configs[1], headline)
+    cube1       Cube boxes, 1 bin, R=2, online                                                 (configs[0])
+    general     irregular height-field shapes, 4096 bins/GPU, R=8 (arguments.py default for General)  (configs[2])
+    general24   the same with 24 rotations per shape (configs[2] as BASELINE.json words it)
+    buffered10  BlockOut, buffered k=10: one step = get_action_candidates(order) + step(location)     (configs[3])
+    abc32k      irregular R=8, 4096 bins/GPU -- meant for --gpus 8 (32768 bins, rollout-end gather)    (configs[4])
+
+A "step" is one batched ``step()`` over all bins of a GPU.  For N > 1 the driver launches one rank per GPU
+with torch.distributed.run; bins are sharded by index (weak scaling), there is no collective inside a step,
+and ONE NCCL all-gather of the observations per rollout.  That gather is pipelined: the
+gather of the previous rollout's observations runs on a side stream while this rollout's steps execute; the
+timed total counts every part of the gather's duration that did NOT run concurrently with a timed step
+interval (`gather_exposed_ms`), so gather time hidden behind L2 flushes or the stand-in policy is charged.
+
+Timing: every timed step is bracketed by CUDA events on the launching stream; between timed steps the L2 is
+flushed by writing a 256 MiB buffer (outside the event pairs).  ``value`` uses actions that are already on the
+device; ``e2e`` calls the public ``GpuVecEnv.step`` with HOST actions (pinned H2D copy, kernels, D2H of
+reward/done/info arrays) and is timed with the host clock around the call.
 """
 import argparse
 import json
@@ -29,29 +40,62 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-N_ENVS = 4096            # bins per GPU (BASELINE.json metric)
 SEL = 500
 SEQ_LEN = 128
-CPU_BURN_IN = 40         # untimed batched steps of the CPU arm before its timed sample
+CPU_BURN_IN = 40         # untimed batched steps of the CPU arm before its timed samples
 BURN_IN = 150            # untimed steps before the W warm-up steps so episodes are in steady state
-METRIC = "env steps/sec (4096 bins, BlockOut)"
 UNIT = "env-steps/s"
+CPU_ENVS_PER_CORE = 2    # bins per worker process of the CPU arm (same in cpu_baseline and --impl reference)
+CPU_SAMPLES = 3          # the CPU arm reports the median of this many timed samples
+
+CONFIGS = {
+    "blockout": dict(bins=4096, k=1, R=4, metric="env steps/sec (4096 bins, BlockOut)",
+                     workload="BlockOut-like polycubes (32 shapes, 2-5 cells of 0.04 m), 4096 bins per GPU, online "
+                              "(bufferSize=1), selectedAction=500, R=4, bin 0.32x0.32x0.30, random-valid policy"),
+    "cube1": dict(bins=1, k=1, R=2, metric="env steps/sec (1 bin, Cube)",
+                  workload="Cube boxes (125 shapes, edges 0.03-0.15 m), 1 bin, online, selectedAction=500, R=2, "
+                           "random-valid policy (BASELINE.json configs[0])"),
+    "general": dict(bins=4096, k=1, R=8, metric="env steps/sec (4096 bins, General irregular R=8)",
+                    workload="irregular height-field shapes (32 shapes, non-flat bottoms, holes, off-grid extents), 4096 "
+                             "bins per GPU, online, selectedAction=500, R=8, random-valid policy (BASELINE.json configs[2])"),
+    "general24": dict(bins=4096, k=1, R=24, metric="env steps/sec (4096 bins, General irregular R=24)",
+                      workload="irregular height-field shapes (32 shapes), 4096 bins per GPU, online, selectedAction=500, "
+                               "24 rotations per shape, random-valid policy (BASELINE.json configs[2], 24-rotation wording)"),
+    "buffered10": dict(bins=4096, k=10, R=4, metric="env steps/sec (4096 bins, BlockOut buffered k=10)",
+                       workload="BlockOut-like polycubes, 4096 bins per GPU, buffered k=10 (--hierachical): one step = "
+                                "get_action_candidates(random order action) + step(random-valid location action), "
+                                "selectedAction=500, R=4 (BASELINE.json configs[3])"),
+    "abc32k": dict(bins=4096, k=1, R=8, metric="env steps/sec (4096 bins per GPU, ABC-like irregular R=8)",
+                   workload="irregular height-field shapes (ABC stand-in, 32 shapes), 4096 bins per GPU (32768 at --gpus 8), "
+                            "online, selectedAction=500, R=8, rollout-end all-gather (BASELINE.json configs[4])"),
+}
 
 
-def workload():
+def make_library(config):
     from irbpp_b200 import shapes
-    lib = shapes.make_blockout_library(32, seed=1, num_rotations=4)
-    return lib
+    if config in ("blockout", "buffered10"):
+        return shapes.make_blockout_library(32, seed=1, num_rotations=4)
+    if config == "cube1":
+        return shapes.make_cube_library(seed=3)
+    if config in ("general", "abc32k"):
+        return shapes.make_irregular_library(32, seed=2, num_rotations=8)
+    if config == "general24":
+        return shapes.make_irregular_library(32, seed=2, num_rotations=24)
+    raise SystemExit("unknown config %r" % config)
 
 
-def algorithmic_bytes_per_env_step(lib, sel=SEL):
+def algorithmic_bytes_per_env_step(lib, k=1, sel=SEL):
     """2*Hx*Hy*8 [hm r+w] + R*Ax*Ay*16 [posZ+mask] + sum_r 2*w_r*h_r*8 [B, maskB of the
     next item] + 2*w*h*8 [T, maskT of the placed rotation] + obs_len*4 [float32 observation], averaged
-    over the shape library (ids are uniform)."""
+    over the shape library (ids are uniform).  Buffered (k > 1): the candidate pass reads the heightmap
+    once more and writes the location observation; the step writes the order observation [k + 1024]."""
     R = lib.num_rotations
     wh = (lib.dims[:, :, 0].astype(np.float64) * lib.dims[:, :, 1])
-    obs_len = sel * 5 + 9 + 1024
-    return 2 * 32 * 32 * 8 + R * 16 * 16 * 16 + float(wh.sum(axis=1).mean()) * 16 + float(wh.mean()) * 16 + obs_len * 4
+    loc_len = sel * 5 + 9 + 1024
+    base = 2 * 32 * 32 * 8 + R * 16 * 16 * 16 + float(wh.sum(axis=1).mean()) * 16 + float(wh.mean()) * 16 + loc_len * 4
+    if k > 1:
+        base += 32 * 32 * 8 + (k + 1024) * 4
+    return base
 
 
 class ClockSampler(object):
@@ -122,33 +166,138 @@ def host_policy(rng, obs):
 # it imports trimesh / gym / pybullet which are absent)
 # ---------------------------------------------------------------------------------------------------
 
-def run_cpu_arm(steps, warmup, envs_per_core=2, max_seconds=None):
+def _spin(q, seconds):
+    t_end = time.perf_counter() + seconds
+    n = 0
+    x = 1.0
+    while time.perf_counter() < t_end:
+        for _ in range(20000):
+            x = x * 1.0000001 + 1e-9
+        n += 1
+    q.put(n)
+
+
+def host_cores():
+    """How many host cores this process may really use.  ``os.cpu_count()`` is the machine's count; a
+    container is usually limited by the affinity mask and / or a cgroup CPU quota (round 1's 1-GPU lease
+    ran 128 workers on a fraction of the 128 advertised cores).  Besides reading those limits the
+    parallel speed-up of a spin loop is measured, which also catches limits that are not visible here."""
+    import multiprocessing as mp
+    info = {"cpu_count": os.cpu_count() or 1}
+    try:
+        info["affinity"] = len(os.sched_getaffinity(0))
+    except Exception:
+        info["affinity"] = info["cpu_count"]
+    quota = None
+    for path in ("/sys/fs/cgroup/cpu.max",):
+        try:
+            q, p = open(path).read().split()[:2]
+            if q != "max":
+                quota = float(q) / float(p)
+        except Exception:
+            pass
+    if quota is None:
+        try:
+            q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            p = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / p
+        except Exception:
+            pass
+    info["cgroup_quota"] = quota
+    declared = info["affinity"]
+    if quota is not None:
+        declared = max(1, min(declared, int(quota + 0.5)))
+    # measured: throughput of `declared` concurrent spinners relative to one spinner
+    ctx = mp.get_context("fork")
+
+    def rate(nproc, seconds=0.8):
+        q = ctx.Queue()
+        ps = [ctx.Process(target=_spin, args=(q, seconds)) for _ in range(nproc)]
+        for p in ps:
+            p.start()
+        tot = sum(q.get() for _ in ps)
+        for p in ps:
+            p.join()
+        return tot / seconds
+    try:
+        one = max(rate(1), rate(1))                  # best of two: a busy neighbour must not look like a quota
+        many = max(rate(declared), rate(declared))
+        info["measured_parallelism"] = round(many / one, 1)
+    except Exception:
+        info["measured_parallelism"] = None
+    cores = declared
+    mp_ = info["measured_parallelism"]
+    if mp_ is not None and mp_ < 0.6 * declared:           # far fewer real cores than declared: do not oversubscribe
+        cores = max(1, int(mp_ + 0.5))
+    info["cores_used"] = cores
+    return info
+
+
+def run_cpu_arm(config, steps, warmup, max_seconds=None):
+    """The reference-style CPU vector env on this box's host cores: one worker process per usable core
+    (ShmemVecEnv shape), CPU_ENVS_PER_CORE bins each, CPU_SAMPLES timed samples of `steps` batched steps
+    (or until max_seconds per sample); the median sample is reported."""
     from irbpp_b200 import shapes
     from oracle.cpu_vec_env import SubprocOracleVecEnv
-    lib = workload()
-    cores = os.cpu_count() or 1
-    n = cores * envs_per_core
+    spec = CONFIGS[config]
+    lib = make_library(config)
+    hc = host_cores()
+    cores = hc["cores_used"]
+    k = spec["k"]
+    if spec["bins"] == 1:
+        cores = 1
+        n = 1
+    else:
+        n = cores * CPU_ENVS_PER_CORE
     seqs = shapes.make_sequences(n, SEQ_LEN, lib.num_shapes, seed=0)
-    vec = SubprocOracleVecEnv(dict(ZRotNum=4, selectedAction=SEL), lib, seqs, num_procs=cores)
+    vec = SubprocOracleVecEnv(dict(ZRotNum=spec["R"], selectedAction=SEL, bufferSize=k), lib, seqs, num_procs=cores)
     rng = np.random.default_rng(0)
     obs = vec.reset()
-    for _ in range(CPU_BURN_IN + warmup):            # untimed: reach a steady mix of episode phases
-        obs, _, _, _ = vec.step(host_policy(rng, obs))
-    t_total, done_steps = 0.0, 0
-    for _ in range(steps):
-        acts = host_policy(rng, obs)
-        t0 = time.perf_counter()
-        obs, _, _, _ = vec.step(acts)
-        t_total += time.perf_counter() - t0
-        done_steps += 1
-        if max_seconds is not None and t_total > max_seconds:
+
+    def one(obs):
+        if k > 1:
+            loc = vec.get_action_candidates(rng.integers(0, k, size=n))
+            acts = host_policy(rng, loc)
+        else:
+            acts = host_policy(rng, obs)
+        return vec.step(acts)[0]
+
+    t_burn = time.perf_counter()
+    for i in range(CPU_BURN_IN + warmup):            # untimed: reach a steady mix of episode phases
+        obs = one(obs)
+        if max_seconds is not None and time.perf_counter() - t_burn > max_seconds and i >= 5:
             break
+    samples = []
+    for _ in range(CPU_SAMPLES):
+        t_total, done_steps = 0.0, 0
+        for _ in range(steps):
+            if k > 1:
+                order = rng.integers(0, k, size=n)
+                t0 = time.perf_counter()
+                loc = vec.get_action_candidates(order)
+                t_total += time.perf_counter() - t0
+                acts = host_policy(rng, loc)
+            else:
+                acts = host_policy(rng, obs)
+            t0 = time.perf_counter()
+            obs = vec.step(acts)[0]
+            t_total += time.perf_counter() - t0
+            done_steps += 1
+            if max_seconds is not None and t_total > max_seconds:
+                break
+        samples.append((n * done_steps / t_total, done_steps, t_total))
     vec.close()
-    value = n * done_steps / t_total
+    samples.sort()
+    value, done_steps, t_total = samples[len(samples) // 2]
     return {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%d bins (%d per core) x %d batched steps of the same BlockOut workload, one worker process "
-                      "per core over pipes (ShmemVecEnv shape), oracle port with reference-style loops + cv2, "
-                      "no PyBullet" % (n, envs_per_core, done_steps),
+            "sample": "%d bins (%d per worker) x %d batched steps per sample, median of %d samples (%s env-steps/s), one worker "
+                      "process per usable core over pipes (ShmemVecEnv shape), oracle port with reference-style loops + cv2, "
+                      "no PyBullet; host cores: cpu_count %s, affinity %s, cgroup quota %s, measured parallel speed-up %s -> %d "
+                      "workers (round 1 spawned cpu_count workers, which oversubscribed quota-limited boxes)"
+                      % (n, n // cores, done_steps, len(samples), "/".join("%.0f" % s[0] for s in samples), hc["cpu_count"],
+                         hc["affinity"], hc["cgroup_quota"], hc["measured_parallelism"], cores),
+            "per_core": value / cores, "host": hc,
             "steps": done_steps, "ms_per_step": 1e3 * t_total / done_steps, "n_envs": n}
 
 
@@ -156,14 +305,15 @@ def main_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    res = run_cpu_arm(args.steps, max(args.warmup, 1))
-    line = {"impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
+    spec = CONFIGS[args.config]
+    res = run_cpu_arm(args.config, max(args.steps, 1), max(args.warmup, 1), max_seconds=args.cpu_seconds * 4)
+    line = {"impl": "reference", "metric": spec["metric"], "value": res["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": res["steps"], "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "BlockOut-like polycubes, online, selectedAction=500, R=4 (bounded sample: "
-                                   "%d bins on %d host cores)" % (res["n_envs"], res["cores"])},
+            "config": {"workload": spec["workload"] + " [CPU arm: bounded sample of %d bins on %d host cores]"
+                                   % (res["n_envs"], res["cores"]), "name": args.config},
             "cpu_baseline": {"value": res["value"], "unit": UNIT, "cores": res["cores"], "kind": res["kind"],
-                             "sample": res["sample"]},
+                             "sample": res["sample"], "per_core": res["per_core"]},
             "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line))
@@ -174,20 +324,34 @@ def main_reference(args):
 # B200 arm
 # ---------------------------------------------------------------------------------------------------
 
+def overlap_ms(origin, a0, a1, spans):
+    """Milliseconds of [a0, a1] that ran concurrently with any of `spans` (pairs of CUDA events);
+    all positions measured from `origin`."""
+    g0, g1 = origin.elapsed_time(a0), origin.elapsed_time(a1)
+    tot = 0.0
+    for s0, s1 in spans:
+        x0, x1 = origin.elapsed_time(s0), origin.elapsed_time(s1)
+        tot += max(0.0, min(g1, x1) - max(g0, x0))
+    return tot, g1 - g0
+
+
 def main_gpu(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    spec = CONFIGS[args.config]
+    n_envs, k = spec["bins"], spec["k"]
 
     cpu_base = None
     if world == 1 and rank == 0 and not args.no_cpu_baseline:
         # before CUDA is initialised in this process (workers are forked)
-        cpu_base = run_cpu_arm(steps=10 ** 9, warmup=2, max_seconds=args.cpu_seconds)
-        for k in ("steps", "ms_per_step", "n_envs"):
-            cpu_base.pop(k, None)
+        cpu_base = run_cpu_arm(args.config, steps=10 ** 9, warmup=2, max_seconds=args.cpu_seconds / CPU_SAMPLES)
+        for key in ("steps", "ms_per_step", "n_envs", "host"):
+            cpu_base.pop(key, None)
 
     import torch
     import torch.distributed as dist
+    import irbpp_b200
     from irbpp_b200 import shapes, sharding
     from irbpp_b200.vec_env import GpuVecEnv
 
@@ -199,11 +363,11 @@ def main_gpu(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    lib = workload()
-    n_total = N_ENVS * world
+    lib = make_library(args.config)
+    n_total = n_envs * world
     seqs_all = shapes.make_sequences(n_total, SEQ_LEN, lib.num_shapes, seed=0)
     seqs = sharding.shard_sequences(seqs_all, rank, world)
-    env = GpuVecEnv(lib, seqs, device=dev, selected_action=SEL)
+    env = GpuVecEnv(lib, seqs, device=dev, selected_action=SEL, buffer_size=k)
     gen = torch.Generator(device=dev); gen.manual_seed(1234 + rank)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
 
@@ -212,33 +376,62 @@ def main_gpu(args):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    state = {"obs": None}
+
+    def choose():
+        """the stand-in agent (outside the timed intervals): -> what one_step consumes"""
+        if k > 1:
+            return torch.randint(0, k, (n_envs,), device=dev, generator=gen)
+        return device_policy(torch, state["obs"], gen)
+
+    def one_step(choice, ev=None):
+        """one batched env step on the device-resident path; `ev` brackets the library's work"""
+        if k > 1:
+            if ev is not None:
+                ev[0].record()
+            loc = env.get_action_candidates(choice, as_tensor=True)
+            acts = device_policy(torch, loc, gen)       # the location agent needs the candidates: inside the interval
+            state["obs"], _ = env.step_device(acts)
+        else:
+            if ev is not None:
+                ev[0].record()
+            state["obs"], _ = env.step_device(choice)
+        if ev is not None:
+            ev[1].record()
+
     # ---- device-resident loop ("value") ----
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()                             # sampled from burn-in through the timed steps (same load)
-    obs = env.reset()
+    state["obs"] = env.reset()
     for _ in range(BURN_IN + args.warmup):          # burn-in: bins spread over all episode phases
-        acts = device_policy(torch, obs, gen)
-        obs, _ = env.step_device(acts)
-    if world > 1:                                   # warm-up of the rollout-end collective (NCCL channel setup)
-        sharding.gather_rollout(obs, world)
+        one_step(choose())
+    gatherer = sharding.AsyncRolloutGather(world) if world > 1 else None
+    gather_alone_ms = 0.0
+    if world > 1:                                   # warm-up of the rollout-end collective (NCCL channel setup) + its stand-alone time
+        for _ in range(2):
+            gatherer.start(state["obs"]); gatherer.finish()
+        torch.cuda.synchronize(dev)
+        gather_alone_ms = gatherer.events[0].elapsed_time(gatherer.events[1])
     torch.cuda.synchronize(dev)
     launches0 = env.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    origin = torch.cuda.Event(enable_timing=True)
+    tail0, tail1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_wall0 = time.perf_counter()
-    for k in range(args.steps):
-        acts = device_policy(torch, obs, gen)
-        flush.fill_(float(k))                       # L2 flush, outside the event pair
-        ev[k][0].record()
-        obs, _ = env.step_device(acts)
-        ev[k][1].record()
-    gather_ms = 0.0
-    if world > 1:                                  # end-of-rollout gather of observations (NCCL all-gather)
-        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        g0.record()
-        gathered = sharding.gather_rollout(obs, world)
-        g1.record()
+    origin.record()
+    if world > 1:                                   # the previous rollout's observations go out while this rollout steps
+        gatherer.start(state["obs"])
+    for i in range(args.steps):
+        choice = choose()
+        flush.fill_(float(i))                       # L2 flush, outside the event pair
+        one_step(choice, ev[i])
+    gathered = None
+    if world > 1:
+        tail0.record()
+        gathered = gatherer.finish()
+        tail1.record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
     launches_timed = env.launch_count() - launches0
@@ -249,46 +442,76 @@ def main_gpu(args):
         t_end = time.perf_counter() + 1.5
         while len(sampler.rows) < 25 and time.perf_counter() < t_end:
             for _ in range(20):
-                acts = device_policy(torch, obs, gen)
-                obs, _ = env.step_device(acts)
+                one_step(choose())
             torch.cuda.synchronize(dev)
             extra_steps += 20
     clocks = sampler.stop() if rank == 0 else None
     if clocks is not None:
         clocks["window"] = "burn-in + timed steps + %d further untimed steps of the same loop" % extra_steps
-    launches = launches_timed
     step_ms = [a.elapsed_time(b) for a, b in ev]
+    gather_ms = gather_exposed = gather_hidden = 0.0
     if world > 1:
-        gather_ms = g0.elapsed_time(g1)
         assert gathered.shape[0] == n_total
-    t_dev_ms = float(sum(step_ms)) + gather_ms
-    t = torch.tensor([t_dev_ms, float(np.mean(step_ms)), gather_ms], dtype=torch.float64, device=dev)
+        hidden, gather_ms = overlap_ms(origin, gatherer.events[0], gatherer.events[1], ev)
+        gather_hidden = min(hidden, gather_ms)
+        gather_exposed = gather_ms - gather_hidden
+    t_dev_ms = float(sum(step_ms)) + gather_exposed
+    t = torch.tensor([t_dev_ms, float(np.mean(step_ms)), gather_ms, gather_exposed, gather_alone_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    t_dev_ms, kern_ms, gather_ms = [float(v) for v in t.tolist()]
+    t_dev_ms, kern_ms, gather_ms, gather_exposed, gather_alone_ms = [float(v) for v in t.tolist()]
     value = n_total * args.steps / (t_dev_ms * 1e-3)
 
     # ---- end-to-end loop through the public API with host actions ----
     e2e_steps = args.steps
     t_e2e = 0.0
-    for k in range(min(args.warmup, 3)):
-        acts = device_policy(torch, obs, gen).cpu().numpy()
-        obs, rew, done, infos = env.step(acts)
-    for k in range(e2e_steps):
-        acts = device_policy(torch, obs, gen).cpu().numpy()        # agent -> action.cpu().numpy() (trainer.py:165)
-        flush.fill_(float(k))
-        torch.cuda.synchronize(dev)
+
+    def e2e_step(timed):
+        if k > 1:
+            order = torch.randint(0, k, (n_envs,), device=dev, generator=gen).cpu().numpy()
+        else:
+            acts = device_policy(torch, state["obs"], gen).cpu().numpy()   # agent -> action.cpu().numpy() (trainer.py:165)
+        if timed is not None:
+            flush.fill_(1.0)
+            torch.cuda.synchronize(dev)
+            timed[0].record()
         t0 = time.perf_counter()
-        obs, rew, done, infos = env.step(acts)                      # H2D actions, kernel, D2H results
+        if k > 1:
+            loc = env.get_action_candidates(order, as_tensor=True)       # H2D order actions, kernels; stays on device
+            acts = device_policy(torch, loc, gen).cpu().numpy()            # location agent -> host actions (trainer.py:272-281)
+        out = env.step(acts)                                               # H2D actions, kernels, D2H results
         torch.cuda.synchronize(dev)
-        t_e2e += time.perf_counter() - t0
-    te = torch.tensor([t_e2e], dtype=torch.float64, device=dev)
+        dt = time.perf_counter() - t0
+        if timed is not None:
+            timed[1].record()
+        state["obs"] = out[0]
+        return dt
+
+    for _ in range(min(args.warmup, 3)):
+        e2e_step(None)
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(e2e_steps)]
+    origin2 = torch.cuda.Event(enable_timing=True)
+    barrier()
+    origin2.record()
+    if world > 1:
+        gatherer.start(state["obs"])
+    for i in range(e2e_steps):
+        t_e2e += e2e_step(ev2[i])
+    e2e_gather_exposed = 0.0
+    if world > 1:
+        gatherer.finish()
+        torch.cuda.synchronize(dev)
+        hidden, gms = overlap_ms(origin2, gatherer.events[0], gatherer.events[1], ev2)
+        e2e_gather_exposed = gms - min(hidden, gms)
+    te = torch.tensor([t_e2e + e2e_gather_exposed * 1e-3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     t_e2e = float(te.item())
     e2e_value = n_total * e2e_steps / t_e2e
-    h2d = N_ENVS * 8                                                # int64 actions
-    d2h = N_ENVS * (8 + 8 + 4 + 4 + 4 + 1 + 1 + 1)                  # ratio, ep_reward, reward, counter, ep_len, done, valid, error
+    h2d = n_envs * 8 * (2 if k > 1 else 1)                          # int64 actions (+ order actions when buffered)
+    d2h = n_envs * (8 + 8 + 4 + 4 + 4 + 1 + 1 + 1)                  # ratio, ep_reward, reward, counter, ep_len, done, valid, error
+    if k > 1:
+        d2h += n_envs * 8                                           # the location agent's actions come back to the host
 
     if rank == 0:
         peaks = {}
@@ -298,35 +521,45 @@ def main_gpu(args):
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-        bytes_step = algorithmic_bytes_per_env_step(lib) * N_ENVS
+        bytes_step = algorithmic_bytes_per_env_step(lib, k) * n_envs
         achieved = bytes_step / (kern_ms * 1e-3) / 1e9
-        traffic = None
+        traffic, traffic_note = None, "no ncu capture of this kernel version / config committed"
         try:
             prof = json.load(open(os.path.join(ROOT, "profiles", "step_kernel_traffic.json")))
-            traffic = prof.get("dram_bytes_per_launch")
+            entry = prof.get(args.config)
+            if entry and entry.get("kernel_version") == irbpp_b200.KERNEL_VERSION:
+                traffic = entry.get("dram_bytes_per_launch")
+                traffic_note = "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of the step's kernels, %s (%s)" % (
+                    entry.get("source", "profiles/"), entry.get("kernel_version"))
+            elif entry:
+                traffic_note = "committed capture is of kernel version %s, this is %s" % (entry.get("kernel_version"), irbpp_b200.KERNEL_VERSION)
         except Exception:
             pass
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        line = {"metric": spec["metric"], "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": t_dev_ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "BlockOut-like polycubes (32 shapes, 2-5 cells of 0.04 m), 4096 bins per GPU, "
-                                       "online (bufferSize=1), selectedAction=500, R=4, bin 0.32x0.32x0.30, "
-                                       "random-valid policy", "bins_per_gpu": N_ENVS, "burn_in_steps": BURN_IN, "parallelism": "env-shard x%d" % world,
+                "config": {"workload": spec["workload"], "name": args.config, "bins_per_gpu": n_envs, "burn_in_steps": BURN_IN,
+                           "parallelism": "env-shard x%d" % world, "kernel_version": irbpp_b200.KERNEL_VERSION,
                            "l2": "flushed between timed steps by a 256 MiB write outside the event pairs",
                            "timing": "sum of per-step CUDA-event intervals on the launching stream"
-                                     + (" + end-of-rollout all-gather" if world > 1 else "") + ", max over ranks"},
+                                     + (" + the part of the pipelined rollout all-gather that did not overlap a timed step" if world > 1 else "")
+                                     + ", max over ranks"},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                             "traffic": traffic, "peak_source": peak_src,
-                             "kernel": "irbpp_scan_kernel + irbpp_candidates_kernel (one step = both launches)",
+                             "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,
+                             "kernel": "irbpp_scan_kernel + irbpp_candidates_kernel (one step = both launches"
+                                       + ("; buffered: a candidates pass + the order-level step" if k > 1 else "") + ")",
                              "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": bytes_step},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "ms_per_step": 1e3 * t_e2e / e2e_steps,
-                        "note": "GpuVecEnv.step(host int64 actions): actions staged in pinned memory and read by the kernel over "
-                                "PCIe, both kernels, reward/done/info arrays written back over PCIe, stream sync; observations "
-                                "stay on the device as in the reference (envs.py:163)"},
-                "gpu_launches": int(launches), "clocks": clocks, "wall_s_timed_region": t_wall}
+                        "note": "GpuVecEnv.step(host int64 actions): pinned staging, kernels, reward/done/info arrays back to the "
+                                "host, stream sync; observations stay on the device as in the reference (envs.py:163)"
+                                + ("; includes the exposed part of the rollout all-gather" if world > 1 else "")},
+                "gpu_launches": int(launches_timed), "clocks": clocks, "wall_s_timed_region": t_wall}
         if world > 1:
             line["gather_ms"] = gather_ms
+            line["gather_exposed_ms"] = gather_exposed
+            line["gather_hidden_ms"] = gather_ms - gather_exposed
+            line["gather_alone_ms"] = gather_alone_ms
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
         print(json.dumps(line))
@@ -342,7 +575,8 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="bound of the cpu_baseline sample (wall seconds)")
+    ap.add_argument("--config", default="blockout", choices=sorted(CONFIGS))
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="bound of the cpu_baseline timed samples (wall seconds, all samples)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

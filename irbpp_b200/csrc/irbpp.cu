@@ -370,13 +370,6 @@ __global__ void irbpp_copy_block_kernel(uint4* __restrict__ dst, const uint4* __
 static int launch(irbpp_env* h, Params& P, cudaStream_t s) {
     P.env_lo = 0;
     P.env_hi = P.N;
-#ifdef IRBPP_SPLIT_APPLY
-    if (P.mode == MODE_STEP) {          // experiment: phase A as its own one-warp-per-bin kernel
-        irbpp_apply_kernel<<<(P.N + CTA_WARPS - 1) / CTA_WARPS, CTA_THREADS, 0, s>>>(P);
-        h->launches += 1;
-        P.skip_apply = 1;
-    }
-#endif
     if (P.mode == MODE_DEBUG_HULLS) irbpp_levels_kernel<<<P.N, CTA_THREADS, 0, s>>>(P);
     else irbpp_scan_kernel<<<P.N, CTA_THREADS, h->scan_smem, s>>>(P);
     h->launches += 1;

@@ -304,96 +304,195 @@ __device__ void approx_and_emit(S& sc, int n, bool legacy, Emit emit) {
     finish_polygon(sc, n, pos, emit);
 }
 
-// ---- warp-cooperative seeding + Douglas-Peucker (long contours) ---------------------------------------------
-// Same result as the first part of approx_and_emit, computed by the 32 lanes of a warp for ONE contour
-// of n <= 64 points (lane l holds points l and l + 32): every farthest-point search is one maximum over
-// the lanes of the packed key  value << 6 | (63 - offset)  -- the largest value, and among equal values
-// the smallest offset from the range start, which is the point the serial scan (strict >) keeps.  Control
-// flow is uniform; every lane ends with the same kept set in `sc` and the same return value: the start
-// index pos, or -1 when the contour collapsed to one point (which `emit` received).  The caller continues
-// with finish_polygon().  IRBPP_WARP_MAX(v): maximum of an unsigned value over the warp.
-#ifndef IRBPP_WARP_MAX
-#define IRBPP_WARP_MAX(v) __reduce_max_sync(0xffffffffu, (v))
+// ---- register-resident approxPolyDP (contours of <= 32 points) ---------------------------------------------
+// Same result as approx_and_emit, organised for the SIMT machine instead of for one thread: the contour lives
+// in NW registers (four packed points per word), and every "farthest point" search -- the three seeding rounds
+// and every Douglas-Peucker range -- is ONE statically unrolled pass over all 4*NW positions with the range as a
+// bit mask.  No loads, no loop-carried addresses, no data-dependent trip counts: the lanes of a warp, each on
+// its own contour, stay converged, and the visits of a pass are independent (instruction-level parallelism
+// instead of one dependent chain per point).  The serial form spent ~1.6 k cycles per contour point in the
+// lock-stepped warp (profiles/); see DESIGN.md.
+// The first maximum in traversal order (what the serial scan's strict `>` keeps) is recovered from two running
+// maxima of the key  num << 6 | (63 - i):  positions above the range start come first in traversal order,
+// positions below it after the wrap; inside each group a smaller index is an earlier visit.
+template <int NW>
+struct PackedContour {
+    static constexpr int CAP = 4 * NW;
+    static_assert(NW <= 8, "kept set is one 32-bit register");
+    uint32_t w[NW];
+    uint32_t kept;
+    __device__ __forceinline__ int pt(int i) const {          // dynamic index: select the word, then the byte
+        uint32_t v = w[0];
+#pragma unroll
+        for (int k = 1; k < NW; ++k) v = ((i >> 2) == k) ? w[k] : v;
+        return (int)((v >> ((i & 3) * 8)) & 0xFFu);
+    }
+    __device__ __forceinline__ void kept_clear(int) { kept = 0; }
+    __device__ __forceinline__ void kept_set(int i) { kept |= 1u << i; }
+    __device__ __forceinline__ int kept_count(int) const { return __popc(kept); }
+    __device__ __forceinline__ int kept_next(int i, int) const {
+        const uint32_t hi = (i >= 31) ? 0u : (kept & ~((2u << i) - 1u));
+        return hi ? (__ffs((int)hi) - 1) : (__ffs((int)kept) - 1);
+    }
+};
+
+// One pass: among the ring positions i = s + t (mod n), 1 <= t < len, the first one maximising
+//   LEGACY: |cr|          else: cr^2 + (dot - clamp(dot, 0, hi))^2
+// with cr = (p - a) x d, dot = (p - a) . d.  The caller passes d = (1, 0), hi = 0 for "squared distance to the
+// point a" (seeding; degenerate segment).  Returns num << 6 | (63 - i); never 0 when len >= 2.
+template <int NW, bool LEGACY>
+__device__ __forceinline__ uint32_t packed_farthest(const uint32_t (&w)[NW], int n, int s, int len, int ax, int ay,
+                                                    int dx, int dy, int hi) {
+    // bit i set <=> position i is inside the range: the low (len - 1) bits rotated left by s + 1 within n bits
+    const uint32_t m = (uint32_t)((1ull << (len - 1)) - 1ull);
+    const int sh = (s + 1 == n) ? 0 : s + 1;
+    const uint64_t mm = (uint64_t)m << sh;
+    const uint32_t in = (uint32_t)(mm | (mm >> n));           // bits >= n are never tested below (i < n is static-free: see `live`)
+    const uint32_t live = (n >= 32) ? 0xFFFFFFFFu : ((1u << n) - 1u);
+    const uint32_t above = (s >= 31) ? 0u : ~((2u << s) - 1u);
+    const uint32_t in_hi = in & live & above, in_lo = in & live & ~above;
+    const int c0 = ay * dx - ax * dy, d0 = ax * dx + ay * dy;
+    uint32_t kh = 0, kl = 0;
+#pragma unroll
+    for (int i = 0; i < 4 * NW; ++i) {
+        const int px = (int)((w[i >> 2] >> (8 * (i & 3) + 4)) & 15u), py = (int)((w[i >> 2] >> (8 * (i & 3))) & 15u);
+        const int cr = py * dx - px * dy - c0;
+        int num;
+        if (LEGACY) num = cr < 0 ? -cr : cr;
+        else {
+            const int dot = px * dx + py * dy - d0;
+            const int cl = dot < 0 ? 0 : (dot > hi ? hi : dot);
+            const int tt = dot - cl;
+            num = cr * cr + tt * tt;
+        }
+        const uint32_t key = ((uint32_t)num << 6) | (uint32_t)(63 - i);
+        const uint32_t a = ((in_hi >> i) & 1u) ? key : 0u, b = ((in_lo >> i) & 1u) ? key : 0u;
+        kh = a > kh ? a : kh;
+        kl = b > kl ? b : kl;
+    }
+    return (kh != 0u && (kh >> 6) >= (kl >> 6)) ? kh : kl;
+}
+
+// approxPolyDP(eps = 1, closed) + convex filter of the packed contour `pc` (n points, 2 <= ... handled below).
+// `active` lanes do real work; the loop structure is uniform over the warp (IRBPP_ANY: warp vote).
+#ifndef IRBPP_ANY
+#define IRBPP_ANY(p) __any_sync(0xffffffffu, (p))
 #endif
-template <class S, class Emit>
-__device__ int dp_keep_warp(S& sc, int n, bool legacy, int lane, Emit emit) {
-    static_assert(S::CAP <= 64, "two points per lane");
-    const int i0 = lane, i1 = lane + 32;
-    const int q0 = (i0 < n) ? sc.pt(i0) : 0, q1 = (i1 < n) ? sc.pt(i1) : 0;
-    // 1. seed: three rounds of "farthest point from the current one"
+template <int NW, bool LEGACY, class Emit>
+__device__ void approx_packed(PackedContour<NW>& pc, int n, bool active, Emit emit) {
+    bool run = active && n > 0;
+    if (run && n == 4) {       // filled axis-aligned rectangle with both sides >= 2: its four corners (see approx_and_emit)
+        const int p0 = pc.w[0] & 0xFF, p1 = (pc.w[0] >> 8) & 0xFF, p2 = (pc.w[0] >> 16) & 0xFF, p3 = pc.w[0] >> 24;
+        if ((p0 >> 4) == (p1 >> 4) && (p1 & 15) == (p2 & 15) && (p2 >> 4) == (p3 >> 4) && (p3 & 15) == (p0 & 15) &&
+            (p1 & 15) - (p0 & 15) >= 2 && (p2 >> 4) - (p1 >> 4) >= 2) {
+            emit(p0 >> 4, p0 & 15); emit(p1 >> 4, p1 & 15); emit(p2 >> 4, p2 & 15); emit(p3 >> 4, p3 & 15);
+            run = false;
+        }
+    }
+    if (run && n == 1) { const int p = pc.w[0] & 0xFF; emit(p >> 4, p & 15); run = false; }
+    // 1. seed: three rounds of "farthest point from the current one" (a point-distance pass each)
     int pos = 0, far = 0, maxd = 0;
+#pragma unroll 1
     for (int it = 0; it < 3; ++it) {
-        pos += far; if (pos >= n) pos -= n;
-        const int pp = sc.pt(pos);
-        const int sx = pp >> 4, sy = pp & 15;
-        unsigned key = 0;
-        if (i0 < n) {
-            int j = i0 - pos; if (j < 0) j += n;
-            const int ex = (q0 >> 4) - sx, ey = (q0 & 15) - sy;
-            if (j >= 1) key = ((unsigned)(ex * ex + ey * ey) << 6) | (unsigned)(63 - j);
+        if (!IRBPP_ANY(run)) break;
+        if (run) {
+            pos += far; if (pos >= n) pos -= n;
+            const int pp = pc.pt(pos);
+            const uint32_t k = packed_farthest<NW, false>(pc.w, n, pos, n, pp >> 4, pp & 15, 1, 0, 0);
+            maxd = (int)(k >> 6);
+            int fi = 63 - (int)(k & 63u);                          // index of the farthest point
+            fi -= pos; if (fi < 0) fi += n;
+            far = maxd > 0 ? fi : 0;
         }
-        if (i1 < n) {
-            int j = i1 - pos; if (j < 0) j += n;
-            const int ex = (q1 >> 4) - sx, ey = (q1 & 15) - sy;
-            const unsigned k1 = ((unsigned)(ex * ex + ey * ey) << 6) | (unsigned)(63 - j);
-            if (j >= 1 && k1 > key) key = k1;
-        }
-        const unsigned km = IRBPP_WARP_MAX(key);
-        maxd = (int)(km >> 6);
-        far = maxd > 0 ? 63 - (int)(km & 63u) : 0;
     }
-    if (maxd <= 1) {  // whole contour within eps of one point
-        const int pp = sc.pt(pos);
+    if (run && maxd <= 1) {  // whole contour within eps of one point
+        const int pp = pc.pt(pos);
         emit(pp >> 4, pp & 15);
-        return -1;
+        run = false;
     }
-    int fp = pos + far; if (fp >= n) fp -= n;
-    // 2. Douglas-Peucker, one range at a time, the farthest point of a range by one warp maximum
-    sc.kept_clear(n);
+    // 2. Douglas-Peucker: one range per lane and iteration; one-step ranges are resolved when they are created
+    pc.kept_clear(n);
     RangeStack<true> st;
-    st.push(fp, pos);
-    st.push(pos, fp);
-    while (!st.empty()) {
-        int s, e;
-        st.pop(s, e);
-        for (;;) {
-            int len = e - s; if (len <= 0) len += n;
-            if (len == 1) { sc.kept_set(s); break; }
-            const int ps = sc.pt(s), pe = sc.pt(e);
+    int s = 0, e = 0;
+    bool have = false;
+    if (run) {
+        int fp = pos + far; if (fp >= n) fp -= n;
+        // the two arcs pos -> fp and fp -> pos; an arc of one step keeps its start
+        int l1 = fp - pos; if (l1 <= 0) l1 += n;
+        int l2 = pos - fp; if (l2 <= 0) l2 += n;
+        if (l2 == 1) pc.kept_set(fp); else st.push(fp, pos);
+        if (l1 == 1) pc.kept_set(pos); else st.push(pos, fp);
+    }
+#pragma unroll 1
+    for (;;) {
+        if (run && !have) {
+            if (st.empty()) run = false;
+            else { st.pop(s, e); have = true; }
+        }
+        if (!IRBPP_ANY(run)) break;
+        if (run) {
+            int len = e - s; if (len <= 0) len += n;             // >= 2 by construction
+            const int ps = pc.pt(s), pe = pc.pt(e);
             const int sx = ps >> 4, sy = ps & 15;
-            const int dx = (pe >> 4) - sx, dy = (pe & 15) - sy;
+            int dx = (pe >> 4) - sx, dy = (pe & 15) - sy;
             const int seg2 = dx * dx + dy * dy;
-            auto key_of = [&](int idx, int q) -> unsigned {
-                int t = idx - s; if (t < 0) t += n;
-                if (idx >= n || t < 1 || t >= len) return 0u;
-                const int vx = (q >> 4) - sx, vy = (q & 15) - sy;
-                const int cr = vy * dx - vx * dy;
-                int num;
-                if (legacy) num = cr < 0 ? -cr : cr;
-                else if (seg2 == 0) num = vx * vx + vy * vy;
-                else {
-                    const int dot = vx * dx + vy * dy;
-                    const int cl = dot < 0 ? 0 : (dot > seg2 ? seg2 : dot);
-                    const int tt = dot - cl;
-                    num = cr * cr + tt * tt;
-                }
-                return ((unsigned)num << 6) | (unsigned)(63 - t);       // t <= 62: a real key is never 0
-            };
-            const unsigned k0 = key_of(i0, q0), k1 = key_of(i1, q1);
-            const unsigned km = IRBPP_WARP_MAX(k0 > k1 ? k0 : k1);
-            const int best = (int)(km >> 6);
-            int bi = s + 63 - (int)(km & 63u); if (bi >= n) bi -= n;
+            int hi = seg2;
+            if (!LEGACY && seg2 == 0) { dx = 1; dy = 0; hi = 0; }     // squared distance to the point
+            const uint32_t k = packed_farthest<NW, LEGACY>(pc.w, n, s, len, sx, sy, dx, dy, hi);
+            const int best = (int)(k >> 6);
+            const int bi = 63 - (int)(k & 63u);
             bool le;
-            if (legacy) le = (best * best <= seg2);
+            if (LEGACY) le = (best * best <= seg2);
             else le = (seg2 == 0) ? (best <= 1) : (best <= seg2);
-            if (le) { sc.kept_set(s); break; }
-            int ll = bi - s; if (ll <= 0) ll += n;
-            const int lr = len - ll;
-            if (ll <= lr) { st.push(bi, e); e = bi; }
-            else          { st.push(s, bi); s = bi; }
+            if (le) { pc.kept_set(s); have = false; }
+            else {
+                int ll = bi - s; if (ll <= 0) ll += n;
+                const int lr = len - ll;
+                // children (s, bi) and (bi, e); a one-step child keeps its start at once; the larger one is deferred
+                const bool left_leaf = (ll == 1), right_leaf = (lr == 1);
+                if (left_leaf) pc.kept_set(s);
+                if (right_leaf) pc.kept_set(bi);
+                if (left_leaf && right_leaf) have = false;
+                else if (left_leaf) { s = bi; }
+                else if (right_leaf) { e = bi; }
+                else if (ll <= lr) { st.push(bi, e); e = bi; }
+                else { st.push(s, bi); s = bi; }
+            }
         }
     }
-    return pos;
+    if (active && n > 0 && pc.kept != 0u) finish_polygon(pc, n, pos, emit);
+}
+
+// Load the first n (<= 4 * NW) points of a scratch accessor into the packed form.
+template <int NW, class S>
+__device__ __forceinline__ void load_packed(PackedContour<NW>& pc, const S& sc, int n) {
+#pragma unroll
+    for (int k = 0; k < NW; ++k) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (4 * k + j < n) v |= (uint32_t)sc.pt(4 * k + j) << (8 * j);
+        pc.w[k] = v;
+    }
+    pc.kept = 0;
+}
+
+// One warp-uniform call: every lane brings a contour of n points (0: none) in `sc`; `cls` is the smallest of
+// 1, 2, 4, 8 with 4 * cls >= the largest n of the warp (<= 32; longer contours take approx_and_emit).
+template <class S, class Emit>
+__device__ __forceinline__ void approx_packed_dispatch(const S& sc, int n, int cls, bool legacy, bool active, Emit emit) {
+#define IRBPP_APPROX_CASE(NW)                                                                     \
+    {                                                                                              \
+        PackedContour<NW> pc;                                                                      \
+        load_packed(pc, sc, active ? n : 0);                                                       \
+        if (legacy) approx_packed<NW, true>(pc, n, active, emit);                                  \
+        else approx_packed<NW, false>(pc, n, active, emit);                                        \
+    }
+    if (cls <= 1) IRBPP_APPROX_CASE(1)
+    else if (cls == 2) IRBPP_APPROX_CASE(2)
+    else if (cls <= 4) IRBPP_APPROX_CASE(4)
+    else IRBPP_APPROX_CASE(8)
+#undef IRBPP_APPROX_CASE
 }
 
 // ---- start pixels ------------------------------------------------------------------------------------------

@@ -147,9 +147,6 @@ struct Params {
     int32_t slot;                        // MODE_ALL_OBS: queue slot of this pass
     int32_t ws_bytes;                    // per-warp scratch of the candidates kernel (ws_bytes_for(R))
     int32_t pose_actions;                // MODE_STEP: actions are flat poses (rot*256 + lx*16 + ly), not candidate rows
-#ifdef IRBPP_SPLIT_APPLY
-    int32_t skip_apply;                  // MODE_STEP: phase A was done by irbpp_apply_kernel (experiment)
-#endif
     int32_t heur_method, heur_dir;       // heuristic kernel: Heuristic, dirIdx 0..3 (space.py:162-166)
     int32_t* heur_pose;                  // [N][3] rot, lx, ly
     int64_t* heur_index;                 // [N] row of that pose in the candidate table, -1 if absent
@@ -276,11 +273,6 @@ __device__ __forceinline__ bool scan_rotation(const Params& P, const double* arr
 }
 
 // ---- scan kernel ------------------------------------------------------------------------------------------
-#ifdef IRBPP_SPLIT_APPLY
-#define IRBPP_SKIP_APPLY(P) ((P).skip_apply != 0)      // phase A ran in irbpp_apply_kernel (experiment)
-#else
-#define IRBPP_SKIP_APPLY(P) false
-#endif
 #ifndef IRBPP_SCAN_MIN_CTAS
 #define IRBPP_SCAN_MIN_CTAS 8
 #endif
@@ -316,12 +308,7 @@ __global__ void __launch_bounds__(CTA_THREADS, IRBPP_SCAN_MIN_CTAS) irbpp_scan_k
     int seq_pf = -1;             // thread 0: the sequence entry at the bin's cursor (first draw of this call)
     {
         uint32_t stw = 0;
-#ifdef IRBPP_SPLIT_APPLY
-        const bool apply_here = (mode == MODE_STEP) && !IRBPP_SKIP_APPLY(P);
-#define IRBPP_APPLY_HERE apply_here
-#else
 #define IRBPP_APPLY_HERE (mode == MODE_STEP)
-#endif
         if (warp == 0) {
             stw = reinterpret_cast<const uint32_t*>(P.state + env)[lane];
             if (IRBPP_APPLY_HERE) a_pf = P.actions[env];
@@ -344,25 +331,7 @@ __global__ void __launch_bounds__(CTA_THREADS, IRBPP_SCAN_MIN_CTAS) irbpp_scan_k
         for (int k = 0; k < 4; ++k) dst[tid + k * CTA_THREADS] = hreg[k];
         if (warp == 0) reinterpret_cast<uint32_t*>(&st_s)[lane] = stw;
     }
-#ifdef IRBPP_SPLIT_APPLY
-    if (tid == 0) { err_sh = (mode == MODE_STEP && IRBPP_SKIP_APPLY(P)) ? (int)P.r_error[env] : 0; any_sh = 0; }
-#else
     if (tid == 0) { err_sh = 0; any_sh = 0; }
-#endif
-#ifdef IRBPP_PREFETCH_NEXT
-    // Experimental (not the default build): the grid runs in waves of IRBPP_PREFETCH_NEXT resident CTAs; pull
-    // the heightmap, state and action of the bin a later wave will handle into L2 (no semantic effect), so
-    // that wave's dependent chain starts from L2 instead of DRAM.
-    {
-        const int nxt = env + IRBPP_PREFETCH_NEXT;
-        if (mode == MODE_STEP && nxt < P.env_hi) {
-            const char* hp = reinterpret_cast<const char*>(P.hm + (int64_t)nxt * (HX * HY));
-            if (tid < 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(hp + tid * 128));
-            if (tid == 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.state + nxt));
-            if (tid == 65) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.actions + nxt));
-        }
-    }
-#endif
     __syncthreads();
 
     int32_t* queue_g = st_s.queue;
@@ -386,12 +355,6 @@ __global__ void __launch_bounds__(CTA_THREADS, IRBPP_SCAN_MIN_CTAS) irbpp_scan_k
         }
         hm_changed = true; st_dirty = true;
         __syncthreads();
-#ifdef IRBPP_SPLIT_APPLY
-    } else if (mode == MODE_STEP && IRBPP_SKIP_APPLY(P)) {
-        // the apply kernel already placed the item and advanced the queue: only the next item is needed
-        if (tid == 0) item_sh = queue_g[0];
-        __syncthreads();
-#endif
     } else if (mode == MODE_STEP) {
         // decode the action (warp 0 computes the drop height of that single pose)
         if (warp == 0) {
@@ -587,112 +550,6 @@ __global__ void __launch_bounds__(CTA_THREADS, IRBPP_SCAN_MIN_CTAS) irbpp_scan_k
     phase_mark(1);   // observation heightmap, write-back, scan, level bitmaps
 }
 
-#ifdef IRBPP_SPLIT_APPLY
-// ---- apply kernel (experimental, not the default build) -----------------------------------------------------
-// Phase A of the step alone, one WARP per bin: decode the action, prejudge, drop height of the chosen pose,
-// placement test, heightmap window update (read-modify-write in global memory), bookkeeping, auto-reset.
-// Its dependent chain  action -> candidate row -> tables -> heightmap window  is first-touch DRAM latency;
-// inside the scan kernel every CTA holds a full register budget while warp 0 walks it (3.5 waves of it),
-// here all bins walk it at once in one wave of light warps.  The scan kernel then runs with skip_apply.
-__global__ void __launch_bounds__(CTA_THREADS) irbpp_apply_kernel(const Params P) {
-    __shared__ __align__(16) EnvState st4[CTA_WARPS];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int env = P.env_lo + blockIdx.x * CTA_WARPS + warp;
-    if (env >= P.env_hi) return;
-    EnvState& st_s = st4[warp];
-    const uint32_t stw = reinterpret_cast<const uint32_t*>(P.state + env)[lane];
-    const int64_t a = P.actions[env];
-    reinterpret_cast<uint32_t*>(&st_s)[lane] = stw;
-    int seq_pf = -1;
-    if (lane == 0) seq_pf = P.seq[(int64_t)env * P.L + ((int)stw % P.L)];
-    __syncwarp();
-    double* hm_g = P.hm + (int64_t)env * (HX * HY);
-    int32_t* queue_g = st_s.queue;
-    const int item = st_s.cur_item;
-    int rot = 0, lx = 0, ly = 0, err = 0;
-    bool ok = true;
-    if (a < 0 || a >= (P.pose_actions ? P.R * NPOSE : P.sel)) { ok = false; err = 2; }
-    else {
-        const uint32_t c = P.pose_actions ? (uint32_t)a : P.cand[(int64_t)env * P.sel + a];
-        rot = c >> 8; lx = (c >> 4) & 15; ly = c & 15;
-    }
-    const ShapeRot* sr = P.srot + (int64_t)item * P.R + rot;
-    if (!((sr->okx >> lx) & 1u) || !((sr->oky >> ly) & 1u)) ok = false;      // prejudge (binPhy.py:238-245)
-    if (!st_s.mask_any) ok = false;
-    const int w = sr->w, h = sr->h;
-    const int x0 = STEP * lx, y0 = STEP * ly;
-    double z = POSZ_INVALID;                                                   // space.py:101
-    if (lx < sr->nX && ly < sr->nY) {
-        const double* __restrict__ B = P.Bs + sr->off;
-        double acc = sr->any_zero ? 0.0 : -INFINITY;
-        for (int c = lane; c < w * h; c += 32) {
-            const int i = c / h, j = c - i * h;
-            const double v = hm_g[hm_index(x0 + i, y0 + j)] - B[c];
-            acc = (v > acc) ? v : acc;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double t = __shfl_xor_sync(0xffffffffu, acc, o);
-            acc = (t > acc) ? t : acc;
-        }
-        z = acc;
-    }
-    if (ok && !round6_le0(z + sr->ez - P.binz)) ok = false;                    // Interface.py:365-369
-    if (ok) {
-        const double* __restrict__ T = P.Ts + sr->off;                         // space.py:213
-        for (int c = lane; c < w * h; c += 32) {
-            const int i = c / h, j = c - i * h;
-            const double v = T[c] + z;
-            double* cell = hm_g + hm_index(x0 + i, y0 + j);
-            if (v > *cell) *cell = v;
-        }
-    } else {
-        double2* dst = reinterpret_cast<double2*>(hm_g);                       // auto-reset
-        for (int i = lane; i < HX * HY / 2; i += 32) dst[i] = make_double2(0.0, 0.0);
-    }
-    if (lane == 0) {
-        auto draw = [&](int& cursor) {
-            if (seq_pf >= 0) { const int id = seq_pf; seq_pf = -1; ++cursor; return id; }
-            return draw_item(P, env, cursor);
-        };
-        int cursor = st_s.cursor;
-        const int nfill = P.K > 1 ? P.K : 1;
-        if (ok) {
-            const double rew = P.reward_tab[item];
-            P.r_reward[env] = (float)rew; P.r_done[env] = 0; P.r_valid[env] = 1;
-            P.r_counter[env] = -1; P.r_eplen[env] = 0; P.r_ratio[env] = -1.0; P.r_eprew[env] = 0.0;
-            if (P.h_reward) {
-                P.h_reward[env] = (float)rew; P.h_done[env] = 0; P.h_valid[env] = 1;
-                P.h_counter[env] = -1; P.h_eplen[env] = 0; P.h_ratio[env] = -1.0; P.h_eprew[env] = 0.0;
-            }
-            st_s.packed += 1; st_s.ep_len += 1;
-            st_s.vol_sum += P.vol[item];
-            st_s.ep_rew += rew;
-            const int oa = st_s.order_act;
-            for (int q = oa; q + 1 < nfill; ++q) queue_g[q] = queue_g[q + 1];
-            queue_g[nfill - 1] = draw(cursor);
-        } else {
-            P.r_reward[env] = 0.0f; P.r_done[env] = 1; P.r_valid[env] = 1;
-            P.r_counter[env] = st_s.packed;
-            P.r_ratio[env] = st_s.vol_sum / P.binvol;
-            P.r_eplen[env] = st_s.ep_len + 1;
-            P.r_eprew[env] = st_s.ep_rew + 0.0;
-            if (P.h_reward) {
-                P.h_reward[env] = 0.0f; P.h_done[env] = 1; P.h_valid[env] = 1;
-                P.h_counter[env] = st_s.packed; P.h_ratio[env] = st_s.vol_sum / P.binvol;
-                P.h_eplen[env] = st_s.ep_len + 1; P.h_eprew[env] = st_s.ep_rew + 0.0;
-            }
-            st_s.packed = 0; st_s.ep_len = 0; st_s.vol_sum = 0.0; st_s.ep_rew = 0.0;
-            st_s.order_act = 0;
-            for (int q = 0; q < nfill; ++q) queue_g[q] = draw(cursor);
-        }
-        st_s.cursor = cursor;
-        P.r_error[env] = (uint8_t)err;                  // the scan kernel starts from this code (skip_apply)
-    }
-    __syncwarp();
-    reinterpret_cast<uint32_t*>(P.state + env)[lane] = reinterpret_cast<const uint32_t*>(&st_s)[lane];
-}
-#endif
 
 // ---- levels kernel (MODE_DEBUG_HULLS): level bitmaps from caller-supplied posZValid / mask ------------------
 __global__ void __launch_bounds__(CTA_THREADS) irbpp_levels_kernel(const Params P) {
@@ -1033,42 +890,21 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
             phase_mark(6);   // length sort
 #endif
             // (c) lane i approximates the i-th longest contour (points live in its owner's scratch)
-#ifdef IRBPP_COOP_APPROX
-            // Experimental (not the default build): contours of COOP_MIN points or more -- the tail that
-            // decides when the CTA, and with it the kernel, ends -- are taken one per WARP (dp_keep_warp:
-            // lanes = points), the rest one per lane as before.  The long contours go to the LAST warps
-            // first: in the per-lane part below those carry the shortest contours of the batch, so the
-            // warp-level and the lane-level work overlap instead of queueing up in warp 0.
-#ifndef IRBPP_COOP_MIN
-#define IRBPP_COOP_MIN 17
-#endif
-            constexpr int COOP_MIN = IRBPP_COOP_MIN;
-            const int ncoop = S.hbase[64 - COOP_MIN];          // entries of the buckets with npts >= COOP_MIN
-            for (int c = CAND_WARPS - 1 - warp; c < ncoop; c += CAND_WARPS) {
-                const int owner = S.order2[c];
-                const int on = S.n_of[owner];
+            //     in the register-resident form (approx_packed): the warp runs the class of its longest contour
+            {
+                const int owner = S.order2[tid];
+                const int on = S.n_of[owner];                       // 0: nothing to approximate
                 StridedScratch<32, FAST_CAP> sc;
                 sc.b = ws_base + (size_t)(owner >> 5) * P.ws_bytes + (owner & 31);
                 sc.kept = 0;
                 uint32_t* cb = candbits + (int)S.q_of[owner] * 8;
-                auto emit0 = [&](int ex, int ey) { if (lane == 0) { const int b = ex * 16 + ey; atomicOr(cb + (b >> 5), 1u << (b & 31)); } };
-                const int pos = dp_keep_warp(sc, on, P.legacy != 0, lane, emit0);
-                if (pos >= 0) finish_polygon(sc, on, pos, emit0);
-            }
-            const int my_rank = ncoop + tid;
-#else
-            const int my_rank = tid;
-#endif
-            if (my_rank < CAND_THREADS) {
-                const int owner = S.order2[my_rank];
-                const int on = S.n_of[owner];
-                if (on > 0) {
-                    StridedScratch<32, FAST_CAP> sc;
-                    sc.b = ws_base + (size_t)(owner >> 5) * P.ws_bytes + (owner & 31);
-                    sc.kept = 0;
-                    uint32_t* cb = candbits + (int)S.q_of[owner] * 8;
-                    approx_and_emit(sc, on, P.legacy != 0,
-                                    [&](int ex, int ey) { const int b = ex * 16 + ey; atomicOr(cb + (b >> 5), 1u << (b & 31)); });
+                auto emit = [&](int ex, int ey) { const int b = ex * 16 + ey; atomicOr(cb + (b >> 5), 1u << (b & 31)); };
+                const int nmax = (int)__reduce_max_sync(0xffffffffu, (unsigned)on);
+                if (nmax > 0) {
+                    if (on > 32) approx_and_emit(sc, on, P.legacy != 0, emit);          // rare: longer than the register form holds
+                    const int m32 = nmax < 32 ? nmax : 32;
+                    const int cls = m32 <= 4 ? 1 : (m32 <= 8 ? 2 : (m32 <= 16 ? 4 : 8));
+                    approx_packed_dispatch(sc, on, cls, P.legacy != 0, on > 0 && on <= 32, emit);
                 }
             }
             __syncthreads();           // scratch of every lane is free again

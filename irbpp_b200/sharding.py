@@ -41,6 +41,69 @@ def gather_rollout(local, world_size=None, group=None):
     return out
 
 
+class AsyncRolloutGather(object):
+    """The rollout-end gather taken off the critical path ("overlap with the next step's
+    scan"): ``start(local)`` enqueues the all-gather of a finished rollout's tensor on a side stream
+    (after everything already enqueued on the caller's current stream), the caller goes on stepping the
+    next rollout, ``finish()`` makes the current stream wait for the gather and returns the gathered
+    tensor.  Two output buffers alternate, so a gathered tensor stays valid while the next gather is in
+    flight.  On CPU tensors (gloo, the tests) the collective simply runs asynchronously."""
+
+    def __init__(self, world_size=None, group=None):
+        import torch.distributed as dist
+        self.world = dist.get_world_size(group) if world_size is None else world_size
+        self.group = group
+        self._bufs = [None, None]
+        self._turn = 0
+        self._work = None
+        self._out = None
+        self._side = None
+        self.events = None                      # (start, end) CUDA events of the last gather on the side stream
+
+    def start(self, local):
+        import torch
+        import torch.distributed as dist
+        if self._work is not None:
+            raise RuntimeError("a gather is already in flight")
+        local = local.contiguous()
+        if self.world == 1:
+            self._out, self._work = local, False
+            return
+        shape = (self.world * local.shape[0],) + tuple(local.shape[1:])
+        buf = self._bufs[self._turn]
+        if buf is None or buf.shape != shape or buf.dtype != local.dtype or buf.device != local.device:
+            buf = torch.empty(shape, dtype=local.dtype, device=local.device)
+            self._bufs[self._turn] = buf
+        self._turn ^= 1
+        if local.is_cuda:
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=local.device)
+            cur = torch.cuda.current_stream(local.device)
+            self._side.wait_stream(cur)                       # `local` is complete in stream order
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(self._side):
+                e0.record()
+                dist.all_gather_into_tensor(buf, local, group=self.group)
+                e1.record()
+            local.record_stream(self._side)
+            self.events = (e0, e1)
+            self._work = True
+        else:
+            self._work = dist.all_gather_into_tensor(buf, local, group=self.group, async_op=True)
+        self._out = buf
+
+    def finish(self):
+        import torch
+        if self._work is None:
+            raise RuntimeError("no gather in flight")
+        if self._work is True:
+            torch.cuda.current_stream(self._out.device).wait_stream(self._side)
+        elif self._work is not False:
+            self._work.wait()
+        out, self._out, self._work = self._out, None, None
+        return out
+
+
 def scatter_actions(global_actions, rank, world_size):
     """Slice of a global action vector (ordered by global env index) that belongs to ``rank``."""
     lo, hi = shard_range(global_actions.shape[0], rank, world_size)

@@ -32,6 +32,8 @@ def _worker(pipe, cfg_kwargs, lib, sequences):
                         obs = e.reset()
                     out.append((obs, rew, done, info))
                 pipe.send(out)
+            elif cmd == "get_action_candidates":          # shmem_vec_env.py:99-102,149-150
+                pipe.send([e.get_action_candidates(int(a)) for e, a in zip(envs, data)])
             elif cmd == "close":
                 pipe.send(None)
                 break
@@ -74,6 +76,14 @@ class SubprocOracleVecEnv(object):
             outs.extend(p.recv())
         obs, rews, dones, infos = zip(*outs)
         return np.stack(obs), np.array(rews), np.array(dones), infos
+
+    def get_action_candidates(self, order_actions):
+        for p, (lo, hi) in zip(self.pipes, self.slices):
+            p.send(("get_action_candidates", list(order_actions[lo:hi])))
+        out = []
+        for p in self.pipes:
+            out.extend(p.recv())
+        return np.stack(out)
 
     def close(self):
         for p in self.pipes:

@@ -15,33 +15,6 @@ static inline int __clz(int x) { return x ? __builtin_clz((unsigned)x) : 32; }
 static inline int __any_sync(unsigned, int p) { return p; }   // one "lane": the lock-step variant degenerates to serial
 static inline long long clock64() { return 0; }
 static inline void __syncwarp() {}
-// ---- a 32-thread warp for the cooperative routines: every collective is an exchange through a slot array
-// between two barriers, so the SPMD source runs unchanged, one host thread per lane ----
-#include <atomic>
-#include <thread>
-#include <vector>
-namespace warp_emu {
-struct Barrier {
-    std::atomic<int> count{0}, sense{0};
-    void wait(int n) {
-        const int my = sense.load(std::memory_order_acquire);
-        if (count.fetch_add(1, std::memory_order_acq_rel) == n - 1) { count.store(0, std::memory_order_relaxed); sense.store(my ^ 1, std::memory_order_release); }
-        else while (sense.load(std::memory_order_acquire) == my) std::this_thread::yield();
-    }
-};
-static Barrier bar;
-static unsigned slot[32];
-static thread_local int lane = 0;
-static unsigned reduce_max(unsigned v) {
-    slot[lane] = v;
-    bar.wait(32);
-    unsigned m = 0;
-    for (int i = 0; i < 32; ++i) m = slot[i] > m ? slot[i] : m;
-    bar.wait(32);
-    return m;
-}
-}  // namespace warp_emu
-#define IRBPP_WARP_MAX(v) warp_emu::reduce_max(v)
 #include "../../irbpp_b200/csrc/irbpp_contour.cuh"
 #include "../../irbpp_b200/csrc/irbpp_math.cuh"
 
@@ -60,7 +33,29 @@ extern "C" int hull_bits(const uint16_t* rows16, int legacy, int mode, uint32_t*
         irbpp::StridedScratch<1, 64> sc; sc.b = b; sc.kept = 0;
         return irbpp::process_level_image_mt(sc, rows, legacy != 0, emit) ? 0 : 1;
     }
-    return -1;   // modes 5 and 6 only
+    if (mode == 7 || mode == 8) {
+        // the register-resident form the kernel runs (approx_packed): contours of <= 32 points in the smallest
+        // class that holds them (7) or always in the 32-point class (8); longer ones take the serial routine
+        static uint8_t b[64];
+        bool ok = true;
+        for (int y = 0; y < 16; ++y) {
+            uint32_t c = irbpp::start_candidates_rows(rows, y);
+            while (c) {
+                const int x = __builtin_ctz(c);
+                c &= c - 1;
+                irbpp::StridedScratch<1, 64> sc; sc.b = b; sc.kept = 0;
+                int area2;
+                const int n = irbpp::follow_outer_rows(sc, rows, x, y, area2);
+                if (n == -2 || area2 > 0) continue;
+                if (n < 0) { ok = false; continue; }
+                if (n > 32) { irbpp::approx_and_emit(sc, n, legacy != 0, emit); continue; }
+                const int cls = (mode == 8) ? 8 : (n <= 4 ? 1 : n <= 8 ? 2 : n <= 16 ? 4 : 8);
+                irbpp::approx_packed_dispatch(sc, n, cls, legacy != 0, true, emit);
+            }
+        }
+        return ok ? 0 : 1;
+    }
+    return -1;   // modes 5 to 8 only
 }
 
 extern "C" void floor_div_many(const double* a, double b, int n, double* out) {
@@ -118,44 +113,4 @@ extern "C" int outer_contours_host(const uint16_t* rows16, int32_t* out, int cap
         }
     }
     return w;
-}
-
-
-// The warp-cooperative seeding + Douglas-Peucker (dp_keep_warp) on every outer contour of an image, 32 host
-// threads as the lanes; the result set must equal hull_bits() / the oracle.  Contours are followed by the
-// main thread first (<= 64 points each, else return 1).
-extern "C" int hull_bits_coop(const uint16_t* rows16, int legacy, uint32_t* out_bits) {
-    for (int i = 0; i < 8; ++i) out_bits[i] = 0;
-    uint32_t rows[irbpp::ROWS_WORDS] = {0};
-    for (int y = 0; y < 16; ++y) rows[y + 1] = (uint32_t)rows16[y] << 1;
-    std::vector<std::vector<uint8_t>> contours;
-    for (int y = 0; y < 16; ++y) {
-        uint32_t c = irbpp::start_candidates_rows(rows, y);
-        while (c) {
-            const int x = __builtin_ctz(c);
-            c &= c - 1;
-            uint8_t buf[64];
-            irbpp::StridedScratch<1, 64> sc; sc.b = buf; sc.kept = 0;
-            int area2;
-            const int n = irbpp::follow_outer_rows(sc, rows, x, y, area2);
-            if (n == -2 || area2 > 0) continue;
-            if (n < 0) return 1;
-            contours.emplace_back(buf, buf + n);
-        }
-    }
-    auto lane_main = [&](int lane) {
-        warp_emu::lane = lane;
-        for (auto& pts : contours) {
-            irbpp::StridedScratch<1, 64> sc; sc.b = pts.data(); sc.kept = 0;
-            auto emit = [&](int x, int y) { if (lane == 0) { const int b = x * 16 + y; out_bits[b >> 5] |= 1u << (b & 31); } };
-            const int n = (int)pts.size();
-            const int pos = irbpp::dp_keep_warp(sc, n, legacy != 0, lane, emit);
-            if (pos >= 0) irbpp::finish_polygon(sc, n, pos, emit);
-        }
-    };
-    std::vector<std::thread> th;
-    for (int l = 1; l < 32; ++l) th.emplace_back(lane_main, l);
-    lane_main(0);
-    for (auto& t : th) t.join();
-    return 0;
 }

@@ -124,6 +124,14 @@ def test_device_contour_routines_match_oracle(contour_harness):
             else:
                 assert maxlen > 64                        # overflow of the 64-point buffer only
             n_ovf += rc_fast
+            # the register-resident approxPolyDP the kernel runs on contours of <= 32 points (smallest class /
+            # always the 32-point class)
+            for mode in (7, 8):
+                rc_p, got_p = _dev_bits(contour_harness, img, legacy, mode)
+                if rc_p == 0:
+                    assert got_p == want, (it, legacy, mode)
+                else:
+                    assert maxlen > 64
     assert n_ovf > 0                                         # the overflow path was exercised
 
 
@@ -214,44 +222,3 @@ def test_device_border_follower_matches_oracle_contours(contour_harness):
         assert sorted(got) == sorted(want), it
 
 
-def test_warp_cooperative_douglas_peucker_matches_oracle(contour_harness):
-    """dp_keep_warp (32 lanes on one contour, farthest points by packed-key warp maxima) run by 32 host
-    threads against the oracle; the serial routine it stands in for is checked above."""
-    from oracle import contours_port as cp
-    rng = np.random.default_rng(11)
-    checked = 0
-    for it in range(240):
-        kind = it % 4
-        if kind == 0:
-            img = (rng.random((16, 16)) < rng.uniform(0.3, 0.9)).astype(np.uint8)
-        elif kind == 1:
-            img = np.kron((rng.random((8, 8)) < rng.uniform(0.3, 0.9)).astype(np.uint8), np.ones((2, 2), np.uint8))
-        elif kind == 2:
-            xs, ys = np.meshgrid(np.arange(16), np.arange(16), indexing="ij")
-            f = np.zeros((16, 16))
-            for _ in range(int(rng.integers(1, 5))):
-                cx, cy = rng.uniform(0, 16, 2)
-                f += rng.uniform(0.5, 1.5) * np.exp(-((xs - cx) ** 2 + (ys - cy) ** 2) / rng.uniform(4, 60))
-            img = (f > rng.uniform(0.2, 0.9)).astype(np.uint8)
-        else:
-            img = np.ones((16, 16), np.uint8)
-            for _ in range(int(rng.integers(1, 9))):
-                x0, y0 = rng.integers(0, 15, 2); w, h = rng.integers(1, 5, 2)
-                img[x0:x0 + w, y0:y0 + h] = 0
-        rows = np.zeros(16, np.uint16)
-        for y in range(16):
-            rows[y] = sum(1 << x for x in range(16) if img[y, x])
-        for legacy in (0, 1):
-            out = np.zeros(8, np.uint32)
-            rc = contour_harness.hull_bits_coop(rows.ctypes.data_as(ctypes.c_void_p), legacy, out.ctypes.data_as(ctypes.c_void_p))
-            conts = cp.find_outer_contours(img)
-            if rc == 1:
-                assert max(len(c) for c in conts) > 64
-                continue
-            want = set()
-            for c in conts:
-                want |= {(int(p[0]), int(p[1])) for p in cp.convex_vertices(cp.approx_poly_dp_closed(c, 1.0, bool(legacy)))}
-            got = {(b >> 4, b & 15) for b in range(256) if (int(out[b >> 5]) >> (b & 31)) & 1}
-            assert got == want, (it, legacy)
-            checked += 1
-    assert checked > 300

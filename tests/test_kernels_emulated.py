@@ -142,17 +142,6 @@ def test_emulated_kernels_replay_reference_episodes(emu, name, steps):
     _replay(emu, name, steps)
 
 
-@pytest.fixture(scope="module")
-def emu_coop(tmp_path_factory):
-    # threshold lowered from 17 to 6 points so that most contours of these short episodes take the warp path
-    return build_emulated(str(tmp_path_factory.mktemp("emu_coop")), defs=["-DIRBPP_COOP_APPROX", "-DIRBPP_COOP_MIN=6"])
-
-
-@pytest.mark.parametrize("name,steps", [("episode_irregular", 5), ("episode_blockout", 8), ("episode_truncate", 4)])
-def test_emulated_cooperative_variant_replays_reference_episodes(emu_coop, name, steps):
-    """The experimental build switch IRBPP_COOP_APPROX (long contours by a whole warp, off in the default
-    build) through the same episodes."""
-    _replay(emu_coop, name, steps)
 
 
 def _P(a):
@@ -310,13 +299,3 @@ def test_emulated_many_start_pixels(emu):
     env.close()
 
 
-@pytest.fixture(scope="module")
-def emu_split(tmp_path_factory):
-    return build_emulated(str(tmp_path_factory.mktemp("emu_split")), defs=["-DIRBPP_SPLIT_APPLY"])
-
-
-@pytest.mark.parametrize("name,steps", [("episode_cube", 16), ("episode_buffered", 12), ("episode_truncate", 5)])
-def test_emulated_split_apply_variant_replays_reference_episodes(emu_split, name, steps):
-    """The experimental build switch IRBPP_SPLIT_APPLY (phase A as its own one-warp-per-bin kernel, off in
-    the default build): a Cube episode incl. terminal steps / auto-resets, the buffered protocol, truncation."""
-    _replay(emu_split, name, steps)
