@@ -98,8 +98,14 @@ int irbpp_load_shapes(irbpp_handle h, int32_t num_shapes, int32_t num_rotations,
                       const double* maps, const int64_t* offsets, int64_t maps_len);
 
 /* Replaces: the item creators (environment/physics0/IRcreator.py:6-103).  ids[N,L] host int32; env e
- * draws ids[e, cursor % L] on every generate_item; the cursor persists across episodes. */
+ * draws ids[e, cursor % L] on every generate_item; the cursor persists across episodes.  Calling it again
+ * replaces the sequences and restarts the cursors. */
 int irbpp_set_sequences(irbpp_handle h, const int32_t* ids, int32_t length);
+
+/* Alternative to explicit sequences: env e draws  id = mix(seed, e, draw counter) mod num_shapes  on the device
+ * (splitmix64 finaliser, csrc/irbpp_kernels.cuh item_rng) -- i.i.d. uniform ids without a period, the stand-in
+ * for RandomItemCreator (environment/physics0/IRcreator.py:26-33: np.random.choice on every generate_item). */
+int irbpp_set_item_rng(irbpp_handle h, uint64_t seed);
 
 /* Replaces: envs.reset() (envs.py:149-152 -> ShmemVecEnv.reset, shmem_vec_env.py:60-66; and
  * reset_specific, :113-118, when `which` (host uint8[N], 1 = reset) is not NULL).

@@ -35,6 +35,7 @@ SIGNATURES = {
     "irbpp_obs_len": (c_i32, [c_void_p, ctypes.POINTER(c_i32), ctypes.POINTER(c_i32), ctypes.POINTER(c_i32)]),
     "irbpp_load_shapes": (c_i32, [c_void_p, c_i32, c_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64]),
     "irbpp_set_sequences": (c_i32, [c_void_p, c_void_p, c_i32]),
+    "irbpp_set_item_rng": (c_i32, [c_void_p, ctypes.c_uint64]),
     "irbpp_reset": (c_i32, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "irbpp_step_async": (c_i32, [c_void_p, c_void_p, c_i32, c_void_p, c_void_p]),
     "irbpp_step_wait": (c_i32, [c_void_p, ctypes.POINTER(IrbppStepResult)]),

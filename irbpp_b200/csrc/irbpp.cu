@@ -10,6 +10,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <cmath>
 #include <string>
 #include <vector>
@@ -19,7 +20,7 @@
 
 using namespace irbpp;
 
-static std::string g_create_error;
+static thread_local std::string g_create_error;     // error of the calling thread's last failed irbpp_create
 
 struct irbpp_env {
     irbpp_config cfg;
@@ -79,6 +80,29 @@ static cudaError_t dev_alloc(irbpp_env* h, T** p, size_t count, bool zero = true
     return cudaSuccess;
 }
 
+
+static void free_dev(irbpp_env* h, void* p) {
+    if (!p) return;
+    auto it = std::find(h->dev_allocs.begin(), h->dev_allocs.end(), p);
+    if (it != h->dev_allocs.end()) h->dev_allocs.erase(it);
+    cudaFree(p);
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-function, PER-DEVICE attribute: the largest value any
+// handle needed is tracked per device ordinal and only ever raised (several handles may coexist on a device,
+// and one process may hold handles on several devices).  which: 0 candidates kernel, 1 scan kernel.
+static cudaError_t raise_dynamic_smem(int device, int which, int bytes) {
+    static int raised[64][2];
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    if (device < 0 || device >= 64) return cudaErrorInvalidDevice;
+    if (bytes <= raised[device][which]) return cudaSuccess;
+    cudaError_t e = which == 0
+        ? cudaFuncSetAttribute(irbpp_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)
+        : cudaFuncSetAttribute(irbpp_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) raised[device][which] = bytes;
+    return e;
+}
 
 extern "C" {
 
@@ -143,7 +167,8 @@ int irbpp_create(const irbpp_config* cfg, irbpp_handle* out) {
     do { cudaError_t e2_ = (expr); if (e2_ != cudaSuccess) {                                      \
         fail(nullptr, IRBPP_ECUDA, "%s: %s", #expr, cudaGetErrorString(e2_)); irbpp_destroy(h); return IRBPP_ECUDA; } } while (0)
     TRY_ALLOC(dev_alloc(h, &P.hm, (size_t)N * HX * HY));
-    TRY_ALLOC(dev_alloc(h, &P.cand, (size_t)N * P.sel));
+    P.cand_stride = (P.sel + 7) & ~7;                 // rows of whole 16-byte units: the scan kernel bulk-copies them
+    TRY_ALLOC(dev_alloc(h, &P.cand, (size_t)N * P.cand_stride));
     TRY_ALLOC(dev_alloc(h, &P.state, (size_t)N));
     TRY_ALLOC(dev_alloc(h, &h->actions_dev, N)); TRY_ALLOC(dev_alloc(h, &h->which_dev, N));
     // scan -> candidates hand-over scratch
@@ -171,13 +196,7 @@ int irbpp_create(const irbpp_config* cfg, irbpp_handle* out) {
         P.r_valid = reinterpret_cast<uint8_t*>(b); b += N;
         P.r_error = reinterpret_cast<uint8_t*>(b);
     }
-    {   // per-function attribute shared by all handles: only ever raise it
-        static int cand_attr = 0;
-        if (h->cand_smem > cand_attr) {
-            TRY_ALLOC(cudaFuncSetAttribute(irbpp_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->cand_smem));
-            cand_attr = h->cand_smem;
-        }
-    }
+    TRY_ALLOC(raise_dynamic_smem(cfg->device, 0, h->cand_smem));
 #undef TRY_ALLOC
     *out = h;
     return IRBPP_OK;
@@ -311,6 +330,9 @@ int irbpp_load_shapes(irbpp_handle h, int32_t S, int32_t R, const int32_t* dims,
         for (int r = 0; r < R; ++r) max_entries = std::max(max_entries, (int)srot[(size_t)s * R + r].ntiles);
     }
     cudaSetDevice(c.device);
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    for (void* old : {(void*)h->srot_dev, (void*)h->Bs_dev, (void*)h->Ts_dev, (void*)h->vol_dev, (void*)h->rew_dev, (void*)h->tiles_dev})
+        free_dev(h, old);                                                 // a reload replaces the previous pools
     CUDA_TRY(h, dev_alloc(h, &h->srot_dev, srot.size(), false));
     CUDA_TRY(h, dev_alloc(h, &h->Bs_dev, Bs.size() + 1, false));
     CUDA_TRY(h, dev_alloc(h, &h->Ts_dev, Ts.size() + 1, false));
@@ -328,15 +350,22 @@ int irbpp_load_shapes(irbpp_handle h, int32_t S, int32_t R, const int32_t* dims,
     h->P.vol = h->vol_dev; h->P.reward_tab = h->rew_dev;
     (void)maxwh;
     h->P.maxwh = max_entries;
-    h->scan_smem = CTA_WARPS * h->P.maxwh * (int)sizeof(TileEntry);
-    {   // the attribute is per function, not per handle: only ever raise it (several handles may coexist)
-        static int scan_attr = 0;
-        if (h->scan_smem > scan_attr) {
-            CUDA_TRY(h, cudaFuncSetAttribute(irbpp_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, h->scan_smem));
-            scan_attr = h->scan_smem;
-        }
-    }
+    // per-warp staging lists, then the bin's candidate table row (bulk-copied by the scan kernel)
+    h->scan_smem = CTA_WARPS * h->P.maxwh * (int)sizeof(TileEntry) + ((h->P.cand_stride * 2 + 15) & ~15);
+    CUDA_TRY(h, raise_dynamic_smem(c.device, 1, h->scan_smem));
     h->shapes_loaded = true;
+    return IRBPP_OK;
+}
+
+// fresh per-bin state: cursors restart, every bin's first sequence entry is staged for its first draw
+static int restart_items(irbpp_env* h, const int32_t* ids, int32_t length) {
+    std::vector<EnvState> st((size_t)h->P.N);
+    memset(st.data(), 0, st.size() * sizeof(EnvState));
+    if (ids) for (int e = 0; e < h->P.N; ++e) st[e].next_seq = ids[(size_t)e * length];
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    CUDA_TRY(h, cudaMemcpy(h->P.state, st.data(), st.size() * sizeof(EnvState), cudaMemcpyHostToDevice));
+    h->was_reset = false;
+    h->scan_current = false;
     return IRBPP_OK;
 }
 
@@ -347,12 +376,22 @@ int irbpp_set_sequences(irbpp_handle h, const int32_t* ids, int32_t length) {
     for (size_t i = 0; i < n; ++i)
         if (ids[i] < 0 || ids[i] >= h->P.S) return fail(h, IRBPP_EINVAL, "item id %d out of range at %zu", ids[i], i);
     cudaSetDevice(h->cfg.device);
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    free_dev(h, h->seq_dev); h->seq_dev = nullptr;                       // a reload replaces the previous pool
     CUDA_TRY(h, dev_alloc(h, &h->seq_dev, n, false));
     CUDA_TRY(h, cudaMemcpy(h->seq_dev, ids, n * 4, cudaMemcpyHostToDevice));
-    CUDA_TRY(h, cudaMemset(h->P.state, 0, (size_t)h->P.N * sizeof(EnvState)));   // cursors restart
-    h->was_reset = false;
-    h->scan_current = false;
+    int rc = restart_items(h, ids, length); if (rc) return rc;
     h->P.seq = h->seq_dev; h->P.L = length;
+    h->sequences_set = true;
+    return IRBPP_OK;
+}
+
+int irbpp_set_item_rng(irbpp_handle h, uint64_t seed) {
+    if (!h) return IRBPP_EINVAL;
+    if (!h->shapes_loaded) return fail(h, IRBPP_ESTATE, "load shapes before the item generator");
+    cudaSetDevice(h->cfg.device);
+    int rc = restart_items(h, nullptr, 0); if (rc) return rc;
+    h->P.seq = nullptr; h->P.L = 0; h->P.rng_seed = seed;
     h->sequences_set = true;
     return IRBPP_OK;
 }

@@ -36,6 +36,7 @@
 #include "irbpp_contour.cuh"
 #include "irbpp_math.cuh"
 #include "irbpp_heuristic.cuh"
+#include "irbpp_tma.cuh"
 
 namespace irbpp {
 
@@ -110,7 +111,9 @@ struct EnvState {
     double vol_sum;            // packed volume (get_ratio, binPhy.py:149-153)
     double ep_rew;             // sum of episode rewards (monitor.py:60)
     int32_t queue[MAX_QUEUE];  // item FIFO (IRcreator.py:6-24)
-    int32_t pad[6];
+    int32_t next_seq;          // the sequence entry the next draw returns (fetched one draw ahead: off the step's critical path)
+    int32_t seq_pos;           // cursor modulo the sequence length, kept incrementally
+    int32_t pad[4];
 };
 static_assert(sizeof(EnvState) == 128, "EnvState must be 128 bytes");
 
@@ -130,10 +133,12 @@ struct Params {
     const double* reward_tab;            // [S] (vol / binvol) * 10
     const TileEntry* tiles;              // block form of the bottom tables (tile > 1 entries only)
     // sequences
-    const int32_t* seq; int32_t L;
+    const int32_t* seq; int32_t L;       // L == 0: ids drawn from the counter-based generator below instead
+    uint64_t rng_seed;
     // per-env state
     double* hm;                          // [N][2][32][16] column-parity planes
-    uint16_t* cand;                      // [N][sel] rot<<8 | x<<4 | y
+    uint16_t* cand;                      // [N][cand_stride] rot<<8 | x<<4 | y  (rows padded to 16 bytes: bulk-copied)
+    int32_t cand_stride;                 // uint16 entries per row, sel rounded up to a multiple of 8
     EnvState* state;                     // [N]
     // scan -> candidates hand-over (global scratch, L2 resident)
     double* posz;                        // [N][R][256] drop heights (posZmap)
@@ -165,9 +170,32 @@ struct Params {
 
 __device__ __forceinline__ int hm_index(int x, int y) { return ((y & 1) * HX + x) * (HY / 2) + (y >> 1); }
 
-__device__ __forceinline__ int draw_item(const Params& P, int env, int& cursor) {
-    int id = P.seq[(int64_t)env * P.L + (cursor % P.L)];
-    ++cursor;
+// Counter-based item generator (stand-in for RandomItemCreator, IRcreator.py:26-33, when no explicit sequences
+// are loaded): id = mix(seed, env, draw counter) mod S -- i.i.d. uniform ids, no period, no memory.
+__host__ __device__ __forceinline__ uint32_t item_rng(uint64_t seed, uint32_t env, uint32_t counter) {
+    uint64_t z = seed + 0x9E3779B97F4A7C15ull * (((uint64_t)env << 32) | counter) + 0x9E3779B97F4A7C15ull;   // splitmix64
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    return (uint32_t)(z >> 32);
+}
+
+// generate_item (IRcreator.py:17-24): the id at the bin's cursor.  With explicit sequences the entry was fetched
+// by the previous draw (EnvState::next_seq) and this draw fetches the one after it.
+// `next` is the caller's register copy of EnvState::next_seq: the load issued here is consumed by the NEXT draw
+// (normally in the next step; the caller stores it back with the state), so nothing waits for it.
+__device__ __forceinline__ int draw_item(const Params& P, int env, EnvState& st, int& next) {
+    if (P.L == 0) {
+        const int id = (int)(item_rng(P.rng_seed, (uint32_t)env, (uint32_t)st.cursor) % (uint32_t)P.S);
+        st.cursor += 1;
+        return id;
+    }
+    const int id = next;
+    int pos = st.seq_pos + 1;
+    if (pos >= P.L) pos = 0;
+    st.seq_pos = pos;
+    st.cursor += 1;
+    next = P.seq[(int64_t)env * P.L + pos];
     return id;
 }
 
@@ -277,13 +305,14 @@ __device__ __forceinline__ bool scan_rotation(const Params& P, const double* arr
 #define IRBPP_SCAN_MIN_CTAS 8
 #endif
 __global__ void __launch_bounds__(CTA_THREADS, IRBPP_SCAN_MIN_CTAS) irbpp_scan_kernel(const Params P) {
-    __shared__ __align__(16) double hm_s[HX * HY];
+    __shared__ __align__(128) double hm_s[HX * HY];
     extern __shared__ __align__(16) TileEntry estage[];  // CTA_WARPS x P.maxwh: scan list of each warp's rotation
     __shared__ __align__(16) EnvState st_s;              // this bin's scalar state (loaded / stored by warp 0)
     __shared__ double M_s[NPOSE];                        // block maxima of the heightmap (block form of phase B)
     __shared__ double P2_s[NPOSE];                       // 2x2 block maxima
     __shared__ double z_sh;
     __shared__ int ok_sh, rot_sh, lx_sh, ly_sh, item_sh, err_sh, any_sh;
+    __shared__ __align__(8) mbarrier_t mbar;             // completion of the bulk copies of this bin's inputs
     const int env = P.env_lo + blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int mode = P.mode;
@@ -298,62 +327,59 @@ __global__ void __launch_bounds__(CTA_THREADS, IRBPP_SCAN_MIN_CTAS) irbpp_scan_k
         }
     };
 
-    // ---- load heightmap (column-parity planes, 8 KB) and the bin's scalar state ----
-    // All of these are first-touch DRAM reads (the agent's forward pass sits between two steps).  Warp 0
-    // puts its dependent chain  state -> item, action -> candidate -> rotation  in flight before anybody
-    // waits, so that it overlaps with the heightmap load instead of following it.
+    // ---- load heightmap (column-parity planes, 8 KB), candidate table and the bin's scalar state ----
+    // All of these are first-touch DRAM reads (the agent's forward pass sits between two steps).  The 8 KB
+    // heightmap and the bin's packed candidate table (1 KB) are brought in by the copy engine: one elected
+    // thread arms an mbarrier and issues two 1-D bulk copies (cp.async.bulk), nothing is staged through
+    // registers, and the action is decoded from the shared-memory copy of the table -- the chain
+    // action -> candidate row no longer costs a second DRAM round trip.
     double* hm_g = P.hm + (int64_t)env * (HX * HY);
+    uint16_t* cand_s = reinterpret_cast<uint16_t*>(estage + CTA_WARPS * P.maxwh);     // [cand_stride], behind the staging lists
+    const bool need_cand = (mode == MODE_STEP) && !P.pose_actions;
     int64_t a_pf = 0;
-    uint32_t c_pf = 0;
-    int seq_pf = -1;             // thread 0: the sequence entry at the bin's cursor (first draw of this call)
-    {
-        uint32_t stw = 0;
-#define IRBPP_APPLY_HERE (mode == MODE_STEP)
-        if (warp == 0) {
-            stw = reinterpret_cast<const uint32_t*>(P.state + env)[lane];
-            if (IRBPP_APPLY_HERE) a_pf = P.actions[env];
+    if (tid == 0) {
+        mbar_init(&mbar, 1);
+        if (mode != MODE_RESET) {
+            const uint32_t cbytes = need_cand ? (uint32_t)P.cand_stride * 2u : 0u;
+            mbar_expect_tx(&mbar, (uint32_t)(HX * HY * sizeof(double)) + cbytes);
+            bulk_g2s(hm_s, hm_g, (uint32_t)(HX * HY * sizeof(double)), &mbar);
+            if (need_cand) bulk_g2s(cand_s, P.cand + (int64_t)env * P.cand_stride, cbytes, &mbar);
         }
-        const double2* src = reinterpret_cast<const double2*>(hm_g);
+    }
+    if (warp == 0) {
+        const uint32_t stw = reinterpret_cast<const uint32_t*>(P.state + env)[lane];
+        if (mode == MODE_STEP) a_pf = P.actions[env];
+        reinterpret_cast<uint32_t*>(&st_s)[lane] = stw;
+    }
+    if (mode == MODE_RESET) {
         double2* dst = reinterpret_cast<double2*>(hm_s);
-        static_assert(HX * HY / 2 == 4 * CTA_THREADS, "four double2 per thread");
-        double2 hreg[4];
-        if (mode == MODE_RESET) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) hreg[k] = make_double2(0.0, 0.0);
-        } else {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) hreg[k] = src[tid + k * CTA_THREADS];
-        }
-        if (tid == 0 && (IRBPP_APPLY_HERE || mode == MODE_RESET))
-            seq_pf = P.seq[(int64_t)env * P.L + ((int)stw % P.L)];          // lane 0's word is EnvState::cursor
-        if (warp == 0 && IRBPP_APPLY_HERE && !P.pose_actions && a_pf >= 0 && a_pf < P.sel) c_pf = P.cand[(int64_t)env * P.sel + a_pf];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) dst[tid + k * CTA_THREADS] = hreg[k];
-        if (warp == 0) reinterpret_cast<uint32_t*>(&st_s)[lane] = stw;
+        for (int i = tid; i < HX * HY / 2; i += CTA_THREADS) dst[i] = make_double2(0.0, 0.0);
     }
     if (tid == 0) { err_sh = 0; any_sh = 0; }
-    __syncthreads();
+    __syncthreads();                       // mbarrier initialised, state in shared memory
+    if (mode != MODE_RESET) mbar_wait(&mbar, 0);
 
     int32_t* queue_g = st_s.queue;
-    auto draw = [&](int& cursor) {                    // draw_item, the first one served from the prefetch
-        if (seq_pf >= 0) { const int id = seq_pf; seq_pf = -1; ++cursor; return id; }
-        return draw_item(P, env, cursor);
+    int next_seq = st_s.next_seq;          // thread 0's register copy; written back with the state
+    auto draw = [&]() { return draw_item(P, env, st_s, next_seq); };
+    // zero the bin's heightmap in global memory (reset / auto-reset); the shared copy is zeroed by the caller
+    auto zero_hm_global = [&]() {
+        double2* dst = reinterpret_cast<double2*>(hm_g);
+        for (int i = tid; i < HX * HY / 2; i += CTA_THREADS) dst[i] = make_double2(0.0, 0.0);
     };
-    bool hm_changed = false;
     bool st_dirty = false;
 
     // ---- phase A: bookkeeping / apply action ----
     if (mode == MODE_RESET) {
         if (tid == 0) {
-            int cursor = st_s.cursor;
             const int nfill = P.K > 1 ? P.K : 1;
-            for (int q = 0; q < nfill; ++q) queue_g[q] = draw(cursor);
-            st_s.cursor = cursor;
+            for (int q = 0; q < nfill; ++q) queue_g[q] = draw();
             st_s.packed = 0; st_s.ep_len = 0; st_s.vol_sum = 0.0; st_s.ep_rew = 0.0;
             st_s.order_act = 0;
             item_sh = queue_g[0];
         }
-        hm_changed = true; st_dirty = true;
+        zero_hm_global();
+        st_dirty = true;
         __syncthreads();
     } else if (mode == MODE_STEP) {
         // decode the action (warp 0 computes the drop height of that single pose)
@@ -364,7 +390,7 @@ __global__ void __launch_bounds__(CTA_THREADS, IRBPP_SCAN_MIN_CTAS) irbpp_scan_k
             bool ok = true;
             if (a < 0 || a >= (P.pose_actions ? P.R * NPOSE : P.sel)) { ok = false; if (lane == 0) err_sh = 2; }
             else {
-                const uint32_t c = P.pose_actions ? (uint32_t)a : c_pf;
+                const uint32_t c = P.pose_actions ? (uint32_t)a : (uint32_t)cand_s[a];
                 rot = c >> 8; lx = (c >> 4) & 15; ly = c & 15;
             }
             const ShapeRot* sr = P.srot + (int64_t)item * P.R + rot;
@@ -403,17 +429,19 @@ __global__ void __launch_bounds__(CTA_THREADS, IRBPP_SCAN_MIN_CTAS) irbpp_scan_k
             const double* __restrict__ T = P.Ts + sr->off;
             const double z = z_sh;
             const int x0 = STEP * lx_sh, y0 = STEP * ly_sh;
+            // only the cells the item raises are written back (in shared and in global memory): a placement
+            // touches at most w x h cells, the other 8 KB of the bin's heightmap stay as they are in HBM
             for (int c = tid; c < w * h; c += CTA_THREADS) {
                 const int i = c / h, j = c - i * h;
                 const double v = T[c] + z;
-                double* cell = hm_s + hm_index(x0 + i, y0 + j);
-                if (v > *cell) *cell = v;
+                const int idx = hm_index(x0 + i, y0 + j);
+                if (v > hm_s[idx]) { hm_s[idx] = v; hm_g[idx] = v; }
             }
         } else {
             for (int i = tid; i < HX * HY; i += CTA_THREADS) hm_s[i] = 0.0;    // auto-reset
+            zero_hm_global();
         }
         if (tid == 0) {
-            int cursor = st_s.cursor;
             const int nfill = P.K > 1 ? P.K : 1;
             if (ok) {
                 const double rew = P.reward_tab[item];
@@ -429,7 +457,7 @@ __global__ void __launch_bounds__(CTA_THREADS, IRBPP_SCAN_MIN_CTAS) irbpp_scan_k
                 // item_creator.update_item_queue(orderAction); generate_item()  (binPhy.py:324-325)
                 const int oa = st_s.order_act;
                 for (int q = oa; q + 1 < nfill; ++q) queue_g[q] = queue_g[q + 1];
-                queue_g[nfill - 1] = draw(cursor);
+                queue_g[nfill - 1] = draw();
             } else {
                 P.r_reward[env] = 0.0f; P.r_done[env] = 1; P.r_valid[env] = 1;
                 P.r_counter[env] = st_s.packed;
@@ -443,12 +471,11 @@ __global__ void __launch_bounds__(CTA_THREADS, IRBPP_SCAN_MIN_CTAS) irbpp_scan_k
                 }
                 st_s.packed = 0; st_s.ep_len = 0; st_s.vol_sum = 0.0; st_s.ep_rew = 0.0;
                 st_s.order_act = 0;
-                for (int q = 0; q < nfill; ++q) queue_g[q] = draw(cursor);   // reset(): clear + preview
+                for (int q = 0; q < nfill; ++q) queue_g[q] = draw();   // reset(): clear + preview
             }
-            st_s.cursor = cursor;
             item_sh = queue_g[0];
         }
-        hm_changed = true; st_dirty = true;
+        st_dirty = true;
         __syncthreads();
     } else if (mode == MODE_CANDIDATES) {
         if (tid == 0) {
@@ -478,17 +505,15 @@ __global__ void __launch_bounds__(CTA_THREADS, IRBPP_SCAN_MIN_CTAS) irbpp_scan_k
         const int hm_obs_off = emit_loc ? ncand + 9 : P.K;
         for (int i = tid; i < HX * HY; i += CTA_THREADS)
             obs_g[hm_obs_off + i] = (float)hm_s[hm_index(i >> 5, i & 31)];
-        if (hm_changed) {
-            double2* dst = reinterpret_cast<double2*>(hm_g);
-            const double2* src = reinterpret_cast<const double2*>(hm_s);
-            for (int i = tid; i < HX * HY / 2; i += CTA_THREADS) dst[i] = src[i];
-        }
     }
     if (!emit_loc) {
         // order observation: [next k item ids | heightmap]  (binPhy.py:229-230)
         for (int i = tid; i < P.K; i += CTA_THREADS) obs_g[i] = (float)queue_g[i];
-        if (tid == 0) { P.r_error[env] = (uint8_t)err_sh; if (P.h_error) P.h_error[env] = (uint8_t)err_sh; }
-        if (st_dirty && warp == 0) reinterpret_cast<uint32_t*>(P.state + env)[lane] = reinterpret_cast<const uint32_t*>(&st_s)[lane];
+        if (tid == 0) { P.r_error[env] = (uint8_t)err_sh; if (P.h_error) P.h_error[env] = (uint8_t)err_sh; st_s.next_seq = next_seq; }
+        if (st_dirty && warp == 0) {
+            __syncwarp();
+            reinterpret_cast<uint32_t*>(P.state + env)[lane] = reinterpret_cast<const uint32_t*>(&st_s)[lane];
+        }
         return;
     }
     if (tid < 9) obs_g[ncand + tid] = (tid == 0) ? (float)item : 0.0f;      // next_item_vec (binPhy.py:191)
@@ -538,6 +563,7 @@ __global__ void __launch_bounds__(CTA_THREADS, IRBPP_SCAN_MIN_CTAS) irbpp_scan_k
         const bool write_state = (mode == MODE_STEP || mode == MODE_RESET || mode == MODE_CANDIDATES ||
                                   (mode == MODE_ALL_OBS && P.slot == P.K - 1));
         if (write_state) { st_s.cur_item = item; st_s.mask_any = any_sh; }
+        st_s.next_seq = next_seq;
     }
     {
         const bool write_state = (mode == MODE_STEP || mode == MODE_RESET || mode == MODE_CANDIDATES ||
@@ -630,7 +656,7 @@ __global__ void __launch_bounds__(CTA_THREADS) irbpp_heuristic_kernel(const Para
         const double s2 = best_sh[k]; const int e2 = beste_sh[k];
         if (s2 < best || (s2 == best && e2 < beste)) { best = s2; beste = e2; }
     }
-    const uint16_t* cand_g = P.cand + (int64_t)env * P.sel;
+    const uint16_t* cand_g = P.cand + (int64_t)env * P.cand_stride;
     int first = 0x7fffffff;
     for (int i = tid; i < P.sel; i += CTA_THREADS)
         if ((int)cand_g[i] == beste) { first = i; break; }
@@ -950,7 +976,7 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
     float* obs_g = P.obs + (int64_t)env * P.obs_stride + (P.mode == MODE_ALL_OBS ? P.slot * P.loc_len : 0);
     const bool write_state = (P.mode == MODE_STEP || P.mode == MODE_RESET || P.mode == MODE_CANDIDATES ||
                               (P.mode == MODE_ALL_OBS && P.slot == P.K - 1));
-    uint16_t* cand_g = write_state ? P.cand + (int64_t)env * sel : nullptr;
+    uint16_t* cand_g = write_state ? P.cand + (int64_t)env * P.cand_stride : nullptr;
     double* dbg_cand = P.dbg_cand ? P.dbg_cand + (int64_t)env * sel * 5 : nullptr;
 
     // candidate counts per rotation (lane r), exclusive prefix, total

@@ -9,6 +9,7 @@
 // It is slow (thousands of thread switches per launch) and is never linked into the product: the
 // library built from it exports emu_irbpp_* names that irbpp_b200/_lib.py cannot bind.
 #pragma once
+#define IRBPP_HOST_EMULATION 1      // csrc/irbpp_tma.cuh: bulk copies become memcpy, mbarrier waits no-ops
 #include <math.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -151,6 +152,7 @@ static inline int atomicMin(int* p, int v) {
 // ---- runtime API on the host heap ------------------------------------------------------------------------
 typedef int cudaError_t;
 constexpr cudaError_t cudaSuccess = 0;
+constexpr cudaError_t cudaErrorInvalidDevice = 101;
 typedef void* cudaStream_t;
 enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
 constexpr unsigned cudaHostAllocMapped = 2;
