@@ -300,6 +300,98 @@ __device__ __forceinline__ bool scan_rotation(const Params& P, const double* arr
     return any != 0;
 }
 
+// ---- phase B for arbitrary tables: dense pose packing ------------------------------------------------------
+// scan_rotation maps the 16 x 16 action grid onto the lanes as it is, so a rotation whose scanned range is
+// nX x nY leaves (256 - nX nY) / 256 of the lane slots idle while they wait for the entry loop -- half of them
+// for the irregular library -- and an arbitrary table's entry loop (one entry per unmasked cell, ~60, up to 246)
+// is where the scan of general shapes spends its time.  Here only the nX * nY scanned poses are dealt to the
+// lanes (pose v -> X = v / nY, Y = v mod nY), four per lane, so one staged entry serves 128 window positions
+// and four independent accumulators hide the latency of the max chain.  Results go to posz as before and, as
+// one level code per pose, to a 256-byte map in shared memory from which a second, fixed-layout pass takes the
+// feasibility bits and the level bitmaps by warp ballots (emit_level_bitmaps).
+__device__ __forceinline__ bool scan_rotation_dense(const Params& P, const double* arr, int stride_x, TileEntry* es,
+                                                    uint8_t* lv_s /* [256], this warp's */, int env, int item, int r,
+                                                    int lane, int& err) {
+    const ShapeRot* sr = P.srot + (int64_t)item * P.R + r;
+    const int nX = sr->nX, nY = sr->nY, nt = sr->ntiles;
+    const int V = nX * nY;
+    const double ez = sr->ez;
+    const double init = sr->any_zero ? 0.0 : -INFINITY;
+    {
+        const TileEntry* __restrict__ te = P.tiles + sr->tile_off;
+        __syncwarp();                                   // previous rotation's readers are done
+        for (int k = lane; k < nt; k += 32) es[k] = te[k];
+        reinterpret_cast<uint32_t*>(lv_s)[lane] = 0u;
+        reinterpret_cast<uint32_t*>(lv_s)[lane + 32] = 0u;
+        __syncwarp();
+    }
+    const double inv = 1.0 / P.resZ;
+    double* posz_g = P.posz + ((int64_t)env * P.R + r) * NPOSE;
+    const uint32_t magic = 65536u / (uint32_t)(nY > 0 ? nY : 1) + 1u;      // v / nY == (v * magic) >> 16 for v < 256, nY <= 16
+    for (int c0 = 0; c0 < V; c0 += 128) {
+        int cell[4];
+        const double* base[4];
+        bool valid[4];
+        double acc[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int v = c0 + k * 32 + lane;
+            valid[k] = v < V;
+            const int X = valid[k] ? (int)(((uint32_t)v * magic) >> 16) : 0;
+            const int Y = valid[k] ? v - X * nY : 0;
+            cell[k] = X * 16 + Y;
+            base[k] = arr + X * stride_x + Y;
+            acc[k] = init;
+        }
+#pragma unroll 2
+        for (int e = 0; e < nt; ++e) {
+            const TileEntry en = es[e];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const double u = base[k][en.off] - en.b;
+                acc[k] = (u > acc[k]) ? u : acc[k];
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (valid[k]) {
+                const bool feas = round6_le0(acc[k] + ez - P.binz);
+                int code = 0;
+                if (feas) {
+                    const int L = (int)floor_divide_exact(acc[k], P.resZ, inv);        // cvTools.py:78
+                    if (L < -LEVEL_OFFSET || L >= LEVEL_OFFSET) { err = 1; code = LEVEL_OFFSET; /* level -1: skipped */ }
+                    else code = L + LEVEL_OFFSET + 1;                                    // 1 .. 64
+                }
+                posz_g[cell[k]] = acc[k];
+                lv_s[cell[k]] = (uint8_t)code;
+            }
+        }
+    }
+    __syncwarp();
+    // fixed-layout pass: feasibility bits, level presence, bitmaps; poses outside the scanned range keep 1e3 / 0
+    uint32_t* mask_g = P.maskbits + ((int64_t)env * P.R + r) * 8;
+    int lv[8];
+    uint32_t pres_lo = 0, pres_hi = 0, any = 0;
+#pragma unroll
+    for (int pass = 0; pass < 8; ++pass) {
+        const int pA = pass * 32 + lane;
+        const int code = lv_s[pA];
+        if ((pA >> 4) >= nX || (pA & 15) >= nY) posz_g[pA] = POSZ_INVALID;
+        const uint32_t mb = __ballot_sync(0xffffffffu, code != 0);
+        if (lane == 0) mask_g[pass] = mb;
+        any |= mb;
+        const int L = code - (LEVEL_OFFSET + 1);
+        lv[pass] = code ? L : -1;
+        if (code && L != -1) { const int b = L + LEVEL_OFFSET; if (b < 32) pres_lo |= 1u << b; else pres_hi |= 1u << (b - 32); }
+    }
+    pres_lo = __reduce_or_sync(0xffffffffu, pres_lo);
+    pres_hi = __reduce_or_sync(0xffffffffu, pres_hi);
+    const int nl = emit_level_bitmaps(P.bitmaps + ((int64_t)env * P.R + r) * MAX_LEVELS * 8, lane, lv,
+                                      ((uint64_t)pres_hi << 32) | pres_lo);
+    if (lane == 0) P.nlevels[(int64_t)env * P.R + r] = nl;
+    return any != 0;
+}
+
 // ---- scan kernel ------------------------------------------------------------------------------------------
 #ifndef IRBPP_SCAN_MIN_CTAS
 #define IRBPP_SCAN_MIN_CTAS 8
@@ -313,6 +405,7 @@ __global__ void __launch_bounds__(CTA_THREADS, IRBPP_SCAN_MIN_CTAS) irbpp_scan_k
     __shared__ double z_sh;
     __shared__ int ok_sh, rot_sh, lx_sh, ly_sh, item_sh, err_sh, any_sh;
     __shared__ __align__(8) mbarrier_t mbar;             // completion of the bulk copies of this bin's inputs
+    __shared__ __align__(16) uint8_t lvmap_s[CTA_WARPS * NPOSE];   // per warp: level code of every pose of its rotation (dense scan)
     const int env = P.env_lo + blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int mode = P.mode;
@@ -551,7 +644,7 @@ __global__ void __launch_bounds__(CTA_THREADS, IRBPP_SCAN_MIN_CTAS) irbpp_scan_k
                 any |= scan_rotation(P, Marr, 16, estage + warp * P.maxwh, env, item, r, lane, err);
         } else {
             for (int r = warp; r < P.R; r += CTA_WARPS)
-                any |= scan_rotation(P, hm_s, STEP * (HY / 2), estage + warp * P.maxwh, env, item, r, lane, err);
+                any |= scan_rotation_dense(P, hm_s, STEP * (HY / 2), estage + warp * P.maxwh, lvmap_s + warp * NPOSE, env, item, r, lane, err);
         }
         if (lane == 0 && any) any_sh = 1;
         if (__any_sync(0xffffffffu, err) && lane == 0) err_sh = 4;

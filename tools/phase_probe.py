@@ -21,8 +21,10 @@ import bench  # noqa: E402
 from irbpp_b200 import shapes  # noqa: E402
 from irbpp_b200.vec_env import GpuVecEnv  # noqa: E402
 
-lib = bench.workload()
-seqs = shapes.make_sequences(bench.N_ENVS, bench.SEQ_LEN, lib.num_shapes, seed=0)
+CONFIG = os.environ.get("IRBPP_PROBE_CONFIG", "blockout")       # any bench.py --config with k = 1
+N_ENVS = bench.CONFIGS[CONFIG]["bins"]
+lib = bench.make_library(CONFIG)
+seqs = shapes.make_sequences(N_ENVS, bench.SEQ_LEN, lib.num_shapes, seed=0)
 env = GpuVecEnv(lib, seqs, device="cuda:0")
 gen = torch.Generator(device="cuda:0")
 gen.manual_seed(1)
@@ -34,10 +36,10 @@ n = 20
 for _ in range(n):
     obs, _ = env.step_device(bench.device_policy(torch, obs, gen))
 c = env.debug_phase_cycles(False).astype(np.float64) / n
-scan_ctas = bench.N_ENVS
-cand_ctas = bench.N_ENVS // 4
+scan_ctas = N_ENVS
+cand_ctas = N_ENVS // 4
 fine = "fine" in os.path.basename(os.environ.get("IRBPP_LIB", ""))
-out = {"lib": os.environ.get("IRBPP_LIB", "default"),
+out = {"lib": os.environ.get("IRBPP_LIB", "default"), "config": CONFIG,
        "scan_kernel_cycles_per_cta": {"load + apply action (phase A)": round(c[0] / scan_ctas),
                                       "observation, pose scan, level bitmaps": round(c[1] / scan_ctas)},
        "candidates_kernel_cycles_per_cta": {"contour tasks (phase C)": round(c[2] / cand_ctas),
