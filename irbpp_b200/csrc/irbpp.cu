@@ -172,10 +172,12 @@ int irbpp_create(const irbpp_config* cfg, irbpp_handle* out) {
     TRY_ALLOC(dev_alloc(h, &P.state, (size_t)N));
     TRY_ALLOC(dev_alloc(h, &h->actions_dev, N)); TRY_ALLOC(dev_alloc(h, &h->which_dev, N));
     // scan -> candidates hand-over scratch
-    TRY_ALLOC(dev_alloc(h, &P.posz, (size_t)N * P.R * NPOSE));
-    TRY_ALLOC(dev_alloc(h, &P.maskbits, (size_t)N * P.R * 8));
-    TRY_ALLOC(dev_alloc(h, &P.bitmaps, (size_t)N * P.R * MAX_LEVELS * 8));
-    TRY_ALLOC(dev_alloc(h, &P.nlevels, (size_t)N * P.R));
+    // (buffered: one slice per (bin, buffer slot) pair, get_all_possible_observation scans all of them at once)
+    const size_t units = (size_t)N * (size_t)P.K;
+    TRY_ALLOC(dev_alloc(h, &P.posz, units * P.R * NPOSE));
+    TRY_ALLOC(dev_alloc(h, &P.maskbits, units * P.R * 8));
+    TRY_ALLOC(dev_alloc(h, &P.bitmaps, units * P.R * MAX_LEVELS * 8));
+    TRY_ALLOC(dev_alloc(h, &P.nlevels, units * P.R));
     // result block (8-byte fields first so every array stays aligned)
     h->results_bytes = (size_t)N * (8 + 8 + 4 + 4 + 4 + 1 + 1 + 1);
     TRY_ALLOC(cudaMalloc(&h->results_dev, h->results_bytes + 64));
@@ -407,16 +409,18 @@ __global__ void irbpp_copy_block_kernel(uint4* __restrict__ dst, const uint4* __
 }
 
 static int launch(irbpp_env* h, Params& P, cudaStream_t s) {
+    // the units of a launch: bins, or (bin, buffer slot) pairs for get_all_possible_observation
+    const int units = (P.mode == MODE_ALL_OBS) ? P.N * P.K : P.N;
     P.env_lo = 0;
-    P.env_hi = P.N;
+    P.env_hi = units;
     if (P.mode == MODE_DEBUG_HULLS) irbpp_levels_kernel<<<P.N, CTA_THREADS, 0, s>>>(P);
-    else irbpp_scan_kernel<<<P.N, CTA_THREADS, h->scan_smem, s>>>(P);
+    else irbpp_scan_kernel<<<units, CTA_THREADS, h->scan_smem, s>>>(P);
     h->launches += 1;
     if (mode_emits_loc(P.mode, P.K)) {
         // programmatic dependent launch: the candidates grid is scheduled while the scan grid's last
         // wave drains and waits at griddepcontrol.wait for the scan's completion
         cudaLaunchConfig_t lc = {};
-        lc.gridDim = dim3((P.N + ENVS_PER_CTA - 1) / ENVS_PER_CTA); lc.blockDim = dim3(CAND_THREADS);
+        lc.gridDim = dim3((units + ENVS_PER_CTA - 1) / ENVS_PER_CTA); lc.blockDim = dim3(CAND_THREADS);
         lc.dynamicSmemBytes = (size_t)h->cand_smem; lc.stream = s;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -428,8 +432,8 @@ static int launch(irbpp_env* h, Params& P, cudaStream_t s) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(h, IRBPP_ECUDA, "kernel launch: %s", cudaGetErrorString(e));
     // buffered step / reset change the heightmap without a scan; the debug modes scan foreign inputs
-    h->scan_current = (P.mode == MODE_CANDIDATES || P.mode == MODE_ALL_OBS ||
-                       ((P.mode == MODE_STEP || P.mode == MODE_RESET) && P.K == 1));
+    // (get_all_possible_observation leaves its scans indexed by (bin, slot): not what the heuristic kernel reads)
+    h->scan_current = (P.mode == MODE_CANDIDATES || ((P.mode == MODE_STEP || P.mode == MODE_RESET) && P.K == 1));
     return IRBPP_OK;
 }
 
@@ -577,13 +581,11 @@ int irbpp_get_all_possible_observation(irbpp_handle h, float* out, void* stream)
     if (h->P.K <= 1) return fail(h, IRBPP_ESTATE, "get_all_possible_observation needs buffer_size > 1");
     if (!h->was_reset) return fail(h, IRBPP_ESTATE, "called before reset");
     Params P = h->P;
+    // every (bin, buffered item) pair is one unit of ONE scan launch and ONE candidates launch (binPhy.py:175-179
+    // loops over the k items): the K scans of a bin share its heightmap through L2 and the candidate extraction packs
+    // the contour tasks of all pairs densely
     P.mode = MODE_ALL_OBS; P.obs = out; P.obs_stride = P.K * P.loc_len;
-    for (int slot = 0; slot < P.K; ++slot) {        // one pipeline pass per buffered item (binPhy.py:175-179)
-        P.slot = slot;
-        rc = launch(h, P, (cudaStream_t)stream);
-        if (rc) return rc;
-    }
-    return IRBPP_OK;
+    return launch(h, P, (cudaStream_t)stream);
 }
 
 int irbpp_heuristic_actions(irbpp_handle h, int32_t method, int32_t dir_idx, int32_t* poses_out, int64_t* index_out,

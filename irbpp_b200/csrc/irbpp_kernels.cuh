@@ -149,7 +149,6 @@ struct Params {
     const int64_t* actions;              // MODE_STEP / MODE_CANDIDATES
     const uint8_t* which;                // MODE_RESET (NULL = all)
     const int32_t* dbg_items;            // MODE_DEBUG_SCAN
-    int32_t slot;                        // MODE_ALL_OBS: queue slot of this pass
     int32_t ws_bytes;                    // per-warp scratch of the candidates kernel (ws_bytes_for(R))
     int32_t pose_actions;                // MODE_STEP: actions are flat poses (rot*256 + lx*16 + ly), not candidate rows
     int32_t heur_method, heur_dir;       // heuristic kernel: Heuristic, dirIdx 0..3 (space.py:162-166)
@@ -406,9 +405,13 @@ __global__ void __launch_bounds__(CTA_THREADS, IRBPP_SCAN_MIN_CTAS) irbpp_scan_k
     __shared__ int ok_sh, rot_sh, lx_sh, ly_sh, item_sh, err_sh, any_sh;
     __shared__ __align__(8) mbarrier_t mbar;             // completion of the bulk copies of this bin's inputs
     __shared__ __align__(16) uint8_t lvmap_s[CTA_WARPS * NPOSE];   // per warp: level code of every pose of its rotation (dense scan)
-    const int env = P.env_lo + blockIdx.x;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int mode = P.mode;
+    // One CTA per bin; get_all_possible_observation (MODE_ALL_OBS) runs one CTA per (bin, buffer slot) in a single
+    // launch: `vb` indexes the hand-over scratch, the slot picks the item and the place in the observation.
+    const int vb = P.env_lo + blockIdx.x;
+    const int slot = (mode == MODE_ALL_OBS) ? vb % P.K : 0;
+    const int env = (mode == MODE_ALL_OBS) ? vb / P.K : vb;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     asm volatile("griddepcontrol.launch_dependents;");      // the candidates grid may be scheduled as this one drains (PDL)
     if (mode == MODE_RESET && P.which && !P.which[env]) return;
     long long t_prev = P.phase_cycles ? clock64() : 0;
@@ -580,7 +583,7 @@ __global__ void __launch_bounds__(CTA_THREADS, IRBPP_SCAN_MIN_CTAS) irbpp_scan_k
         st_dirty = true;
         __syncthreads();
     } else if (mode == MODE_ALL_OBS) {
-        if (tid == 0) item_sh = queue_g[P.slot];
+        if (tid == 0) item_sh = queue_g[slot];
         __syncthreads();
     } else {   // MODE_DEBUG_SCAN
         if (tid == 0) item_sh = P.dbg_items[env];
@@ -589,7 +592,7 @@ __global__ void __launch_bounds__(CTA_THREADS, IRBPP_SCAN_MIN_CTAS) irbpp_scan_k
     phase_mark(0);   // load + phase A
 
     const bool emit_loc = mode_emits_loc(mode, P.K);
-    float* obs_g = P.obs + (int64_t)env * P.obs_stride + (mode == MODE_ALL_OBS ? P.slot * P.loc_len : 0);
+    float* obs_g = P.obs + (int64_t)env * P.obs_stride + slot * P.loc_len;
     const int item = item_sh;
     const int ncand = P.sel * 5;
 
@@ -641,26 +644,28 @@ __global__ void __launch_bounds__(CTA_THREADS, IRBPP_SCAN_MIN_CTAS) irbpp_scan_k
             }
             const double* Marr = (tile == 4) ? M_s : P2_s;
             for (int r = warp; r < P.R; r += CTA_WARPS)
-                any |= scan_rotation(P, Marr, 16, estage + warp * P.maxwh, env, item, r, lane, err);
+                any |= scan_rotation(P, Marr, 16, estage + warp * P.maxwh, vb, item, r, lane, err);
         } else {
             for (int r = warp; r < P.R; r += CTA_WARPS)
-                any |= scan_rotation_dense(P, hm_s, STEP * (HY / 2), estage + warp * P.maxwh, lvmap_s + warp * NPOSE, env, item, r, lane, err);
+                any |= scan_rotation_dense(P, hm_s, STEP * (HY / 2), estage + warp * P.maxwh, lvmap_s + warp * NPOSE, vb, item, r, lane, err);
         }
         if (lane == 0 && any) any_sh = 1;
         if (__any_sync(0xffffffffu, err) && lane == 0) err_sh = 4;
     }
     __syncthreads();
     if (tid == 0) {
-        P.r_error[env] = (uint8_t)err_sh;          // the candidates kernel may overwrite with its own code
-        if (P.h_error) P.h_error[env] = (uint8_t)err_sh;
+        if (mode != MODE_ALL_OBS || err_sh) {      // (several CTAs per bin in MODE_ALL_OBS: only error codes are written)
+            P.r_error[env] = (uint8_t)err_sh;      // the candidates kernel may overwrite with its own code
+            if (P.h_error) P.h_error[env] = (uint8_t)err_sh;
+        }
         const bool write_state = (mode == MODE_STEP || mode == MODE_RESET || mode == MODE_CANDIDATES ||
-                                  (mode == MODE_ALL_OBS && P.slot == P.K - 1));
+                                  (mode == MODE_ALL_OBS && slot == P.K - 1));
         if (write_state) { st_s.cur_item = item; st_s.mask_any = any_sh; }
         st_s.next_seq = next_seq;
     }
     {
         const bool write_state = (mode == MODE_STEP || mode == MODE_RESET || mode == MODE_CANDIDATES ||
-                                  (mode == MODE_ALL_OBS && P.slot == P.K - 1));
+                                  (mode == MODE_ALL_OBS && slot == P.K - 1));
         if (st_dirty || write_state) {
             __syncthreads();
             if (warp == 0) reinterpret_cast<uint32_t*>(P.state + env)[lane] = reinterpret_cast<const uint32_t*>(&st_s)[lane];
@@ -814,10 +819,16 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
         }
     };
     auto env_live = [&](int e) { return !(P.mode == MODE_RESET && P.which && !P.which[e]); };
+    // the "bins" of this kernel are (bin, buffer slot) pairs in MODE_ALL_OBS (see the scan kernel): real bin, slot and
+    // the place of a pair's rows in the observation
+    const bool all_obs = (P.mode == MODE_ALL_OBS);
+    auto real_env = [&](int e) { return all_obs ? e / P.K : e; };
+    auto slot_of_e = [&](int e) { return all_obs ? e % P.K : 0; };
+    auto obs_offset = [&](int e) { return (int64_t)real_env(e) * P.obs_stride + slot_of_e(e) * P.loc_len; };
     // Zero the candidate rows [first, sel) of one bin's observation (one warp): scalar stores up to a 16-byte
     // boundary, float4 after it.
     auto zero_obs_rows = [&](int e, int first) {
-        float* z0 = P.obs + (int64_t)e * P.obs_stride + (P.mode == MODE_ALL_OBS ? P.slot * P.loc_len : 0) + first * 5;
+        float* z0 = P.obs + obs_offset(e) + first * 5;
         const int count = (P.sel - first) * 5;
         int head = (int)((16u - ((uint32_t)(uintptr_t)z0 & 15u)) & 15u) >> 2;
         head = head < count ? head : count;
@@ -1066,10 +1077,11 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
     const uint32_t* cbits = candbits + warp * R * 8;
     const uint32_t* mask_g = P.maskbits + (int64_t)env * R * 8;
     const double* posz_g = P.posz + (int64_t)env * R * NPOSE;
-    float* obs_g = P.obs + (int64_t)env * P.obs_stride + (P.mode == MODE_ALL_OBS ? P.slot * P.loc_len : 0);
+    const int renv = real_env(env);
+    float* obs_g = P.obs + obs_offset(env);
     const bool write_state = (P.mode == MODE_STEP || P.mode == MODE_RESET || P.mode == MODE_CANDIDATES ||
-                              (P.mode == MODE_ALL_OBS && P.slot == P.K - 1));
-    uint16_t* cand_g = write_state ? P.cand + (int64_t)env * P.cand_stride : nullptr;
+                              (all_obs && slot_of_e(env) == P.K - 1));
+    uint16_t* cand_g = write_state ? P.cand + (int64_t)renv * P.cand_stride : nullptr;
     double* dbg_cand = P.dbg_cand ? P.dbg_cand + (int64_t)env * sel * 5 : nullptr;
 
     // candidate counts per rotation (lane r), exclusive prefix, total
@@ -1200,7 +1212,7 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
         if (Ktot < sel) zero_rows(Ktot);
     }
     if (lane == 0) {
-        if (dev_err) { P.r_error[env] = (uint8_t)dev_err; if (P.h_error) P.h_error[env] = (uint8_t)dev_err; }
+        if (dev_err) { P.r_error[renv] = (uint8_t)dev_err; if (P.h_error) P.h_error[renv] = (uint8_t)dev_err; }
         if (P.dbg_nhull) P.dbg_nhull[env] = Ktot;
     }
     phase_mark(3);   // select / pad, candidate rows of the observation

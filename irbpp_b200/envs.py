@@ -10,8 +10,10 @@ path reads (``binPhy.py:25-49``):
 
 plus the shape data: ``args.shapeLibrary`` (a ``shapes.ShapeLibrary``) or the reference's own
 ``args.shotInfo`` / ``args.shapeDict`` (extents) / ``args.infoDict`` (volumes), and optionally
-``args.itemSequences`` (int ids ``[num_processes, L]``; default: seeded uniform ids, the stand-in for
-``RandomItemCreator``, ``IRcreator.py:26-33``)."""
+``args.itemSequences`` (int ids ``[num_processes, L]``, replayed modulo L).  Without it the ids are drawn
+i.i.d. uniform ON THE DEVICE from a counter-based generator seeded with ``args.seed`` -- the role of
+``RandomItemCreator`` (``IRcreator.py:26-33``); there is no period.  ``args.approxLegacy`` (optional, default
+False) selects the older point-to-line ``approxPolyDP`` rule (the reference pins OpenCV 4.4.0.46)."""
 import numpy as np
 
 from . import shapes
@@ -40,10 +42,9 @@ def make_vec_envs(args, log_dir=None, allow_early_resets=True):
     if lib is None:
         lib = library_from_reference_args(args)
     n = int(args.num_processes)
-    seqs = getattr(args, "itemSequences", None)
-    if seqs is None:
-        seqs = shapes.make_sequences(n, 256, lib.num_shapes, seed=int(getattr(args, "seed", 0)))
+    seqs = getattr(args, "itemSequences", None)        # None: i.i.d. ids generated on the device
     envs = GpuVecEnv(lib, seqs, num_envs=n, device=getattr(args, "device", "cuda:0"),
+                     item_seed=int(getattr(args, "seed", 0)), approx_legacy=bool(getattr(args, "approxLegacy", False)),
                      selected_action=int(getattr(args, "selectedAction", 500)),
                      buffer_size=int(getattr(args, "bufferSize", 1)),
                      bin_dimension=tuple(getattr(args, "bin_dimension", (0.32, 0.32, 0.30))),

@@ -365,3 +365,20 @@ def make_sequences(num_envs, length, num_shapes, seed=0):
     for e in range(num_envs):
         out[e] = np.random.default_rng(seed + e).integers(0, num_shapes, size=length)
     return out
+
+
+def item_rng_ids(seed, num_envs, count, num_shapes):
+    """The ids the device draws in item-generator mode (``irbpp_set_item_rng``): env e's d-th draw is
+    ``mix(seed, e, d) mod num_shapes`` with the splitmix64 finaliser of ``csrc/irbpp_kernels.cuh``
+    (``item_rng``).  Returns ``ids[num_envs, count]`` int32 -- used by the tests to give the CPU oracle
+    the very same i.i.d. stream (the stand-in for ``RandomItemCreator``, reference ``IRcreator.py:26-33``)."""
+    M = np.uint64(0xFFFFFFFFFFFFFFFF)
+    e = np.arange(num_envs, dtype=np.uint64)[:, None]
+    d = np.arange(count, dtype=np.uint64)[None, :]
+    g = np.uint64(0x9E3779B97F4A7C15)
+    with np.errstate(over="ignore"):
+        z = (np.uint64(seed) + g * ((e << np.uint64(32)) | d) + g) & M
+        z = ((z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)) & M
+        z = ((z ^ (z >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)) & M
+        z = z ^ (z >> np.uint64(31))
+    return ((z >> np.uint64(32)) % np.uint64(num_shapes)).astype(np.int32)

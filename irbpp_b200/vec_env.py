@@ -154,22 +154,31 @@ class GpuVecEnv(VecEnv):
 
     Parameters mirror what ``PackingGame.__init__`` reads from ``args`` (binPhy.py:25-49):
     ``library`` is a ``shapes.ShapeLibrary`` (the ``shotInfo`` / ``shapeDict`` / ``infoDict`` data),
-    ``sequences`` the per-env item ids (stand-in for the item creators, IRcreator.py)."""
+    ``sequences`` the per-env item ids ``[N, L]`` (replayed modulo L; what the parity tests use), or ``None``
+    for i.i.d. ids generated on the device from ``item_seed`` (the stand-in for ``RandomItemCreator``,
+    IRcreator.py:26-33).  ``approx_legacy`` selects the point-to-line ``approxPolyDP`` rule believed to be
+    what the reference's pinned OpenCV 4.4.0.46 computes (default: the 4.13 rule, the one testable here)."""
 
     def __init__(self, library, sequences, num_envs=None, device="cuda:0", selected_action=500, buffer_size=1,
                  bin_dimension=(0.32, 0.32, 0.30), resolution_act=0.02, resolution_h=0.01, resolution_z=0.01,
-                 approx_legacy=False):
+                 approx_legacy=False, item_seed=0):
         import torch
         self._torch = torch
         self._lib = _lib.load()
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("GpuVecEnv needs a CUDA device; there is no CPU path")
-        sequences = np.ascontiguousarray(sequences, dtype=np.int32)
-        if num_envs is None:
-            num_envs = sequences.shape[0]
-        if sequences.shape[0] != num_envs:
-            raise ValueError("sequences has %d rows for %d envs" % (sequences.shape[0], num_envs))
+        if sequences is None:
+            # no explicit sequences: ids are drawn on the device, i.i.d. uniform from a counter-based generator
+            # seeded with ``item_seed`` (RandomItemCreator's role, IRcreator.py:26-33; no period)
+            if num_envs is None:
+                raise ValueError("num_envs is required when no sequences are given")
+        else:
+            sequences = np.ascontiguousarray(sequences, dtype=np.int32)
+            if num_envs is None:
+                num_envs = sequences.shape[0]
+            if sequences.shape[0] != num_envs:
+                raise ValueError("sequences has %d rows for %d envs" % (sequences.shape[0], num_envs))
         idx = self.device.index if self.device.index is not None else torch.cuda.current_device()
         cfg = _lib.IrbppConfig()
         cfg.num_envs = num_envs
@@ -195,7 +204,10 @@ class GpuVecEnv(VecEnv):
                                          dims.ctypes.data, ext.ctypes.data, vol.ctypes.data, maps.ctypes.data,
                                          offsets.ctypes.data, maps.size)
         self._check(rc)
-        rc = self._lib.irbpp_set_sequences(self._h, sequences.ctypes.data, sequences.shape[1])
+        if sequences is None:
+            rc = self._lib.irbpp_set_item_rng(self._h, int(item_seed) & 0xFFFFFFFFFFFFFFFF)
+        else:
+            rc = self._lib.irbpp_set_sequences(self._h, sequences.ctypes.data, sequences.shape[1])
         self._check(rc)
         o, l, k = _lib.c_i32(), _lib.c_i32(), _lib.c_i32()
         self._check(self._lib.irbpp_obs_len(self._h, ctypes.byref(o), ctypes.byref(l), ctypes.byref(k)))

@@ -223,6 +223,13 @@ def gen_heuristic_episode(tag, lib, R, n_envs, n_steps, seed):
 def main():
     assert ref_loader.reference_available(), "needs /root/reference"
     _, space_mod, cv_mod = ref_loader.load_reference()
+    # BASELINE.json configs[3]: buffered k = 10 (--hierachical).  Added in round 2; generated on its own
+    # (--buffered10-only) so the round-1 fixtures stay byte-identical.
+    if "--buffered10-only" in sys.argv or "--all" in sys.argv:
+        d = gen_episode("buffered10", shapes.make_blockout_library(16, seed=8), 4, 3, 36, 29, bufferSize=10)
+        np.savez_compressed(os.path.join(HERE, "episode_buffered10.npz"), **d)
+        if "--buffered10-only" in sys.argv:
+            return
     heur = {
         "heuristic_blockout": gen_heuristic_episode("heur-blockout", shapes.make_blockout_library(16, seed=6), 4, 3, 64, 26),
         "heuristic_irregular": gen_heuristic_episode("heur-irregular", shapes.make_irregular_library(12, seed=7), 8, 3, 48, 27),

@@ -115,6 +115,11 @@ class EmuEnv(object):
                                                         ctypes.c_void_p(loc.ctypes.data), None) == 0
         return loc
 
+    def get_all_possible_observation(self, k):
+        out = np.zeros((self.n, k * self.loc_len), np.float32)
+        assert self.lib.emu_irbpp_get_all_possible_observation(self.h, ctypes.c_void_p(out.ctypes.data), None) == 0
+        return out
+
     def close(self):
         self.lib.emu_irbpp_destroy(self.h)
 
@@ -137,11 +142,37 @@ def _replay(lib, name, steps):
 
 
 @pytest.mark.parametrize("name,steps", [("episode_blockout", 12), ("episode_cube", 14), ("episode_irregular", 5),
-                                        ("episode_truncate", 6), ("episode_buffered", 6)])
+                                        ("episode_truncate", 6), ("episode_buffered", 6), ("episode_buffered10", 5)])
 def test_emulated_kernels_replay_reference_episodes(emu, name, steps):
     _replay(emu, name, steps)
 
 
+
+
+def test_emulated_fused_all_possible_observation(emu):
+    """get_all_possible_observation as ONE scan + ONE candidates launch over (bin, buffer slot) pairs, k = 10, vs
+    the oracle's per-item loop (binPhy.py:171-180); then the protocol goes on (candidate state of slot k-1)."""
+    from irbpp_b200 import shapes
+    from oracle.oracle_env import OracleConfig, OracleVecEnv
+    lib = shapes.make_blockout_library(12, seed=41)
+    n, k = 3, 10
+    seqs = shapes.make_sequences(n, 40, lib.num_shapes, seed=9)
+    ora = OracleVecEnv(OracleConfig(ZRotNum=4, bufferSize=k), lib, seqs)
+    env = EmuEnv(emu, lib, seqs, buffer_size=k)
+    assert np.array_equal(env.reset(), ora.reset().astype(np.float32))
+    rng = np.random.default_rng(2)
+    for t in range(3):
+        want = np.stack([e.get_all_possible_observation() for e in ora.envs])
+        assert np.array_equal(env.get_all_possible_observation(k), want.astype(np.float32)), t
+        order = rng.integers(0, k, size=n)
+        loc_o = np.stack(ora.get_action_candidates(order))
+        assert np.array_equal(env.get_action_candidates(order), loc_o.astype(np.float32)), t
+        acts = np.zeros(n, dtype=np.int64)
+        for i in range(n):
+            valid = np.nonzero(loc_o[i][:2500].reshape(500, 5)[:, 4] == 1)[0]
+            acts[i] = int(rng.choice(valid)) if len(valid) else 0
+        assert np.array_equal(env.step(acts)[0], ora.step(acts)[0].astype(np.float32)), t
+    env.close()
 
 
 def _P(a):
