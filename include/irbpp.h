@@ -184,6 +184,30 @@ int irbpp_debug_hulls(irbpp_handle h, const double* posZValid, const double* mas
 /* Kernel launches issued by this handle so far (bench.py's gpu_launches). */
 int64_t irbpp_launch_count(irbpp_handle h);
 
+/* ---- point clouds of the next items --------------------------------------------------------
+ * Replaces model.py:328-335 / :366-372: `shapeArray[next_item_ID.cpu()]` (a HOST gather of [B, P, 3] float32 rows),
+ * `np.random.randint(P, size=samplePointsNum)` (one index set shared by the batch) and the host-to-device copy
+ * of [B, n, 3] on every forward pass.  Handle-free; every pointer is a DEVICE pointer owned by the caller;
+ * errors are reported through irbpp_last_error(NULL).
+ *   shape_array  float32 [S, P, 3], resident on the device (agent.py:26 `args.shapeArray`)
+ *   item ids     ids int32 [B] when not NULL, else (int) obs[b * obs_stride + item_col]  (the next_item_vec slot of
+ *                the observation: item_col = selected_action * 5, binPhy.py:191,227; model.py:327)
+ *   index set    index j = mix(seed, counter, j) mod P  (counter-based, uniform with replacement like randint;
+ *                csrc/irbpp_pointnet.cuh pn_index; pass a new counter per forward pass)
+ * irbpp_sample_point_clouds: out float32 [B, n_points, 3] = shapeArray[item_b][indices] (drop-in for `nextShape`);
+ *   indices_out int32 [n_points] or NULL.
+ * irbpp_shape_features: the fused path -- shapeEncoder (model.py:266-270: Linear(3,128), LeakyReLU, Linear(128,128),
+ *   LeakyReLU; weights in nn.Linear layout, float32) and the max over the points (model.py:335), evaluated once per
+ *   library SHAPE (the index set is shared by the batch, so the feature depends on the shape only) and gathered per
+ *   bin: out float32 [B, 128].  scratch_keys: int32 [S * 128] work space. */
+int irbpp_sample_point_clouds(const float* shape_array, int32_t S, int32_t P, const float* obs, int64_t obs_stride,
+                              int32_t item_col, const int32_t* ids, int32_t B, uint64_t seed, uint64_t counter,
+                              int32_t n_points, float* out, int32_t* indices_out, void* stream);
+int irbpp_shape_features(const float* shape_array, int32_t S, int32_t P, const float* obs, int64_t obs_stride,
+                         int32_t item_col, const int32_t* ids, int32_t B, uint64_t seed, uint64_t counter,
+                         int32_t n_points, const float* W1, const float* b1, const float* W2, const float* b2,
+                         float negative_slope, int32_t* scratch_keys, float* out, void* stream);
+
 /* Profiling aid: when enabled, thread 0 of every CTA adds the SM cycles it spent in each kernel phase
  * (0 scan kernel: load + apply action, 1 scan kernel: observation heightmap + scan + level bitmaps,
  * 2 candidates kernel: contour tasks, 3 candidates kernel: select / pad) to counters 0-3; counters 4-7 count

@@ -49,6 +49,11 @@ SIGNATURES = {
     "irbpp_debug_scan": (c_i32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "irbpp_debug_hulls": (c_i32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "irbpp_launch_count": (c_i64, [c_void_p]),
+    "irbpp_sample_point_clouds": (c_i32, [c_void_p, c_i32, c_i32, c_void_p, c_i64, c_i32, c_void_p, c_i32, ctypes.c_uint64,
+                                          ctypes.c_uint64, c_i32, c_void_p, c_void_p, c_void_p]),
+    "irbpp_shape_features": (c_i32, [c_void_p, c_i32, c_i32, c_void_p, c_i64, c_i32, c_void_p, c_i32, ctypes.c_uint64,
+                                     ctypes.c_uint64, c_i32, c_void_p, c_void_p, c_void_p, c_void_p, ctypes.c_float,
+                                     c_void_p, c_void_p, c_void_p]),
     "irbpp_debug_phase_cycles": (c_i32, [c_void_p, c_i32, c_void_p]),
 }
 

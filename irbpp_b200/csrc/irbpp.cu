@@ -17,6 +17,7 @@
 
 #include "../../include/irbpp.h"
 #include "irbpp_kernels.cuh"
+#include "irbpp_pointnet.cuh"
 
 using namespace irbpp;
 
@@ -90,16 +91,17 @@ static void free_dev(irbpp_env* h, void* p) {
 
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-function, PER-DEVICE attribute: the largest value any
 // handle needed is tracked per device ordinal and only ever raised (several handles may coexist on a device,
-// and one process may hold handles on several devices).  which: 0 candidates kernel, 1 scan kernel.
+// and one process may hold handles on several devices).  which: 0 candidates kernel, 1 scan kernel, 2 shape encoder.
 static cudaError_t raise_dynamic_smem(int device, int which, int bytes) {
-    static int raised[64][2];
+    static int raised[64][3];
     static std::mutex mu;
     std::lock_guard<std::mutex> lk(mu);
     if (device < 0 || device >= 64) return cudaErrorInvalidDevice;
     if (bytes <= raised[device][which]) return cudaSuccess;
     cudaError_t e = which == 0
         ? cudaFuncSetAttribute(irbpp_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)
-        : cudaFuncSetAttribute(irbpp_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        : (which == 1 ? cudaFuncSetAttribute(irbpp_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)
+                      : cudaFuncSetAttribute(irbpp_shape_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     if (e == cudaSuccess) raised[device][which] = bytes;
     return e;
 }
@@ -723,6 +725,56 @@ int irbpp_debug_hulls(irbpp_handle h, const double* posZValid, const double* mas
 }
 
 int64_t irbpp_launch_count(irbpp_handle h) { return h ? h->launches : 0; }
+
+// ---- point clouds of the next items (csrc/irbpp_pointnet.cuh) ----------------------------------
+static int pn_common(PointNetParams& Q, const float* shape_array, int32_t S, int32_t P, const float* obs, int64_t obs_stride,
+                     int32_t item_col, const int32_t* ids, int32_t B, uint64_t seed, uint64_t counter, int32_t n_points) {
+    if (!shape_array || S <= 0 || P <= 0 || B <= 0 || n_points <= 0) return fail(nullptr, IRBPP_EINVAL, "bad point-cloud arguments");
+    if (!obs && !ids) return fail(nullptr, IRBPP_EINVAL, "either the observations or explicit item ids are needed");
+    if (obs && !ids && (obs_stride <= 0 || item_col < 0 || item_col >= obs_stride)) return fail(nullptr, IRBPP_EINVAL, "bad item column");
+    memset(&Q, 0, sizeof(Q));
+    Q.shape_array = shape_array; Q.S = S; Q.P = P; Q.n_points = n_points; Q.seed = seed; Q.counter = counter;
+    Q.obs = obs; Q.obs_stride = obs_stride; Q.item_col = item_col; Q.ids = ids; Q.B = B;
+    return IRBPP_OK;
+}
+
+int irbpp_sample_point_clouds(const float* shape_array, int32_t S, int32_t P, const float* obs, int64_t obs_stride,
+                              int32_t item_col, const int32_t* ids, int32_t B, uint64_t seed, uint64_t counter,
+                              int32_t n_points, float* out, int32_t* indices_out, void* stream) {
+    PointNetParams Q;
+    int rc = pn_common(Q, shape_array, S, P, obs, obs_stride, item_col, ids, B, seed, counter, n_points); if (rc) return rc;
+    if (!out) return fail(nullptr, IRBPP_EINVAL, "null output");
+    Q.out = out; Q.indices_out = indices_out;
+    const int64_t n = (int64_t)B * n_points;
+    const int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 16);
+    irbpp_cloud_gather_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(Q);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(nullptr, IRBPP_ECUDA, "kernel launch: %s", cudaGetErrorString(e));
+    return IRBPP_OK;
+}
+
+int irbpp_shape_features(const float* shape_array, int32_t S, int32_t P, const float* obs, int64_t obs_stride,
+                         int32_t item_col, const int32_t* ids, int32_t B, uint64_t seed, uint64_t counter,
+                         int32_t n_points, const float* W1, const float* b1, const float* W2, const float* b2,
+                         float negative_slope, int32_t* scratch_keys, float* out, void* stream) {
+    PointNetParams Q;
+    int rc = pn_common(Q, shape_array, S, P, obs, obs_stride, item_col, ids, B, seed, counter, n_points); if (rc) return rc;
+    if (!W1 || !b1 || !W2 || !b2 || !scratch_keys || !out) return fail(nullptr, IRBPP_EINVAL, "null argument");
+    Q.W1 = W1; Q.b1 = b1; Q.W2 = W2; Q.b2 = b2; Q.slope = negative_slope; Q.feat_keys = scratch_keys; Q.out = out;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = raise_dynamic_smem(dev, 2, PN_SMEM_BYTES);
+    if (e != cudaSuccess) return fail(nullptr, IRBPP_ECUDA, "shape encoder set-up: %s", cudaGetErrorString(e));
+    cudaStream_t s = (cudaStream_t)stream;
+    irbpp_pn_init_kernel<<<(S * PN_H + 255) / 256, 256, 0, s>>>(scratch_keys, S * PN_H);
+    const int tiles = (n_points + PN_TILE - 1) / PN_TILE;
+    irbpp_shape_encode_kernel<<<S * tiles, PN_THREADS, PN_SMEM_BYTES, s>>>(Q);
+    const int64_t n = (int64_t)B * PN_H;
+    irbpp_feature_gather_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 148 * 16), 256, 0, s>>>(Q);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(nullptr, IRBPP_ECUDA, "kernel launch: %s", cudaGetErrorString(e));
+    return IRBPP_OK;
+}
 
 int irbpp_debug_phase_cycles(irbpp_handle h, int32_t enable, uint64_t* out8) {
     if (!h) return IRBPP_EINVAL;

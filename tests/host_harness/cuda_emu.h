@@ -122,6 +122,8 @@ static inline unsigned __reduce_max_sync(unsigned, unsigned v) {
     uint64_t o[32]; cuda_emu::exchange(v, o); unsigned r = 0; for (int i = 0; i < 32; ++i) r = std::max(r, (unsigned)o[i]); return r;
 }
 
+static inline int __float_as_int(float f) { int i; memcpy(&i, &f, 4); return i; }
+static inline float __int_as_float(int i) { float f; memcpy(&f, &i, 4); return f; }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline int __popcll(unsigned long long x) { return __builtin_popcountll(x); }
 static inline int __ffs(int x) { return __builtin_ffs(x); }
@@ -164,6 +166,7 @@ struct cudaLaunchConfig_t { dim3 gridDim, blockDim; size_t dynamicSmemBytes; cud
 static inline const char* cudaGetErrorString(cudaError_t) { return "emulated"; }
 static inline cudaError_t cudaGetDeviceCount(int* n) { *n = 1; return cudaSuccess; }
 static inline cudaError_t cudaSetDevice(int) { return cudaSuccess; }
+static inline cudaError_t cudaGetDevice(int* d) { *d = 0; return cudaSuccess; }
 static inline cudaError_t cudaDeviceSynchronize() { return cudaSuccess; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }

@@ -238,3 +238,32 @@ def test_handles_on_two_devices():
             assert np.array_equal(e.step(acts)[0].cpu().numpy(), want), t
     for e in envs:
         e.close()
+
+
+def test_point_cloud_sampling_and_shape_features_match_torch_fp32():
+    """SURVEY.md 8(f)3 on the GPU: DeviceShapeClouds.sample == shapeArray[ids][:, indices] (exact) and
+    DeviceShapeClouds.features == max(shapeEncoder(nextShape)) of model.py:328-335 evaluated by torch in float32 on
+    the same device.  Tolerance (stated): |diff| <= 2e-5 * (1 + |want|) -- the fused kernel accumulates the 128
+    products of the second layer with FMA in index order, cuBLAS in its own order (possibly TF32-free fp32)."""
+    import torch
+    from irbpp_b200.pointnet import DeviceShapeClouds, pn_indices
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator().manual_seed(5)
+    S, Pn, B = 32, 20000, 4096
+    shape_array = (torch.rand((S, Pn, 3), generator=g) * 0.15).float()
+    ids = torch.randint(0, S, (B,), generator=g)
+    obs = torch.zeros((B, 3533)); obs[:, 2500] = ids.float()
+    obs = obs.cuda()
+    enc = torch.nn.Sequential(torch.nn.Linear(3, 128), torch.nn.LeakyReLU(), torch.nn.Linear(128, 128), torch.nn.LeakyReLU()).cuda()
+    clouds = DeviceShapeClouds(shape_array, device="cuda:0", n_points=1024, seed=11)
+    for counter in (0, 1, 7):
+        idx = torch.from_numpy(pn_indices(11, counter, 1024, Pn))
+        want_cloud = shape_array[ids][:, idx].cuda()                      # the reference's host gather + H2D
+        got_cloud, got_idx = clouds.sample(obs, counter=counter, return_indices=True)
+        assert torch.equal(got_idx.cpu().long(), idx) and torch.equal(got_cloud, want_cloud)
+        with torch.no_grad():
+            want = torch.max(enc(want_cloud), dim=1)[0]
+        got = clouds.features(obs, enc, counter=counter)
+        assert torch.all((got - want).abs() <= 2e-5 * (1 + want.abs())), float((got - want).abs().max())
+        got2 = clouds.features(ids.cuda(), enc, counter=counter)         # explicit ids instead of the observation column
+        assert torch.equal(got, got2)

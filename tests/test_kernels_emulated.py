@@ -330,3 +330,34 @@ def test_emulated_many_start_pixels(emu):
     env.close()
 
 
+
+
+def test_emulated_point_cloud_features_match_torch_fp32(emu):
+    """sampled clouds and the fused shapeEncoder + max (csrc/irbpp_pointnet.cuh) run on host threads
+    against the reference's own formulation in torch float32 (model.py:328-335).  Tolerance: the second layer sums
+    128 products in a different order than torch's GEMM (and with FMA): |diff| <= 1e-5 * (1 + |want|)."""
+    import torch
+    from irbpp_b200.pointnet import pn_indices
+    rng = np.random.default_rng(3)
+    S, Pn, n_pts, B = 5, 300, 70, 9                     # 70 points: a full 64-point tile and a ragged one
+    shape_array = rng.normal(0, 0.1, size=(S, Pn, 3)).astype(np.float32)
+    ids = rng.integers(0, S, size=B).astype(np.int32)
+    obs = np.zeros((B, 2500 + 9 + 1024), np.float32); obs[:, 2500] = ids
+    enc = torch.nn.Sequential(torch.nn.Linear(3, 128), torch.nn.LeakyReLU(), torch.nn.Linear(128, 128), torch.nn.LeakyReLU())
+    W1, b1, W2, b2 = [np.ascontiguousarray(t.detach().numpy()) for t in (enc[0].weight, enc[0].bias, enc[2].weight, enc[2].bias)]
+    seed, counter = 77, 5
+    idx = pn_indices(seed, counter, n_pts, Pn)
+    want_cloud = shape_array[ids][:, idx]                                                  # model.py:330-332
+    with torch.no_grad():
+        want_feat = torch.max(enc(torch.from_numpy(want_cloud)), dim=1)[0].numpy()         # model.py:334-335
+    cloud = np.zeros((B, n_pts, 3), np.float32); got_idx = np.zeros(n_pts, np.int32)
+    U64 = ctypes.c_uint64
+    assert emu.emu_irbpp_sample_point_clouds(_P(shape_array), S, Pn, _P(obs), ctypes.c_int64(obs.shape[1]), 2500, None, B, U64(seed),
+                                             U64(counter), n_pts, _P(cloud), _P(got_idx), None) == 0
+    assert np.array_equal(got_idx, idx) and np.array_equal(cloud, want_cloud)
+    keys = np.zeros(S * 128, np.int32); feat = np.zeros((B, 128), np.float32)
+    for use_ids in (False, True):
+        assert emu.emu_irbpp_shape_features(_P(shape_array), S, Pn, None if use_ids else _P(obs), ctypes.c_int64(obs.shape[1]), 2500,
+                                            _P(ids) if use_ids else None, B, U64(seed), U64(counter), n_pts, _P(W1), _P(b1), _P(W2),
+                                            _P(b2), ctypes.c_float(0.01), _P(keys), _P(feat), None) == 0
+        assert np.all(np.abs(feat - want_feat) <= 1e-5 * (1 + np.abs(want_feat))), np.abs(feat - want_feat).max()
