@@ -125,6 +125,19 @@ class LazyInfos(Sequence):
     def __len__(self):
         return self._n
 
+    # -- batched views (consume a step without a Python loop over N dicts) --
+    def valid_array(self):
+        """``[info['Valid'] for info in infos]`` as one bool array (``trainer.py:167-169``)."""
+        return self._views()["valid"][:self._n]
+
+    def finished(self):
+        """The episodes that ended in this step: ``(indices, episode_reward, ratio, counter, valid)`` arrays over
+        the bins with ``done`` -- what ``trainer.py:170-178`` collects bin by bin (``episode_reward`` rounded to
+        6 decimals like ``monitor.py:60``)."""
+        v = self._views()
+        idx = np.nonzero(self._done)[0]
+        return (idx, np.round(v["ep_reward"][idx], 6), v["ratio"][idx], v["counter"][idx], v["valid"][idx])
+
     def __getitem__(self, i):
         if isinstance(i, slice):
             return [self[j] for j in range(*i.indices(len(self)))]
@@ -356,7 +369,19 @@ class GpuVecEnv(VecEnv):
         self._check(self._lib.irbpp_get_action_candidates(self._h, ptr, on_dev, out.data_ptr(), self._stream()))
         if as_tensor:
             return out
-        return list(out.cpu().numpy().astype(np.float64))
+        # the reference returns N float64 rows (``trainer.py:267-268`` stacks them with np.array): one D2H copy into
+        # pinned memory, one widening pass, rows handed out as views of that array (no per-row copies)
+        host = self._pinned_loc()
+        host.copy_(out, non_blocking=False)
+        wide = host.numpy().astype(np.float64)
+        return list(wide)
+
+    def _pinned_loc(self):
+        buf = getattr(self, "_loc_pinned", None)
+        if buf is None:
+            buf = self._torch.empty((self.num_envs, self.loc_obs_len), dtype=self._torch.float32).pin_memory()
+            self._loc_pinned = buf
+        return buf
 
     def get_all_possible_observation(self):
         """``PackingGame.get_all_possible_observation`` for every env (binPhy.py:171-180):

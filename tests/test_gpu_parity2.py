@@ -267,3 +267,44 @@ def test_point_cloud_sampling_and_shape_features_match_torch_fp32():
         assert torch.all((got - want).abs() <= 2e-5 * (1 + want.abs())), float((got - want).abs().max())
         got2 = clouds.features(ids.cuda(), enc, counter=counter)         # explicit ids instead of the observation column
         assert torch.equal(got, got2)
+
+
+def test_actor_loop_through_learner_glue_at_4096_bins():
+    """SURVEY.md 8(f)2, executed: the reference's actor loop shape (trainer.py:157-186) for 24 iterations at N = 4096
+    -- mask on the device (tools.py:283-300), infos consumed through the batched views, one replay-bank append per
+    step, a batch drawn with the segment rule of agent.py:69 made safe for N > batch_size -- and the batched views
+    agree with the per-bin dicts the reference's loop reads."""
+    import torch
+    from irbpp_b200 import shapes, learner_glue as glue
+    n, sel = 4096, 500
+    lib = shapes.make_blockout_library(32, seed=1)
+    env = _env(lib, None, num_envs=n, item_seed=3)
+    gen = torch.Generator(device="cuda:0"); gen.manual_seed(1)
+    bank = glue.ReplayBank(n, 8, env.obs_len, "cuda:0")
+    stats = glue.EpisodeStats()
+    state = env.reset()
+    assert glue.segment_size(64, 4096) == (64, 1) and glue.segment_size(64, 16) == (16, 4)
+    total_done = 0
+    for T in range(1, 25):
+        mask = glue.get_mask_from_state(state, sel)
+        assert mask.shape == (n, sel) and mask.is_cuda
+        q = torch.rand((n, sel), device="cuda:0", generator=gen)
+        q[(1 - mask).bool()] = -float("inf")
+        action = q.argmax(1)
+        next_state, reward, done, infos = env.step(action.cpu().numpy())
+        valid = stats.update(done, infos)
+        idx, ep_r, ratio, counter, v = infos.finished()
+        assert np.array_equal(idx, np.nonzero(done)[0]) and valid.all()
+        for j in idx[:5]:                                   # the batched views say what the per-bin dicts say
+            info = infos[int(j)]
+            k = int(np.nonzero(idx == j)[0][0])
+            assert info["episode"]["r"] == ep_r[k] and info["ratio"] == ratio[k] and info["counter"] == counter[k]
+        total_done += len(idx)
+        bank.append_batch(state, action, reward, done, valid)
+        if T % 4 == 0:
+            envs, slots, s, a, r, s2, nonterm = bank.sample(64, generator=gen)
+            assert s.shape == (64, env.obs_len) and s2.shape == s.shape and a.shape == (64,)
+            assert torch.equal(s, bank.states[slots, envs])
+        state = next_state
+    assert stats.episodes == total_done and total_done > 0 and len(stats.episode_ratio) > 0
+    env.close()

@@ -52,3 +52,18 @@ def test_result_block_views_and_lazy_infos(n):
         assert [d["Valid"] for d in infos[0:2]] == [True, True]
     with pytest.raises(IndexError):
         infos[n]
+    # batched views (learner glue): the same numbers without building dicts
+    idx, ep_r, ratio, counter, valid = infos.finished()
+    assert np.array_equal(idx, np.nonzero(done)[0]) and infos.valid_array().all() and len(infos.valid_array()) == n
+    for k, i in enumerate(idx[:4]):
+        d = infos[int(i)]
+        assert d["episode"]["r"] == ep_r[k] and d["ratio"] == ratio[k] and d["counter"] == counter[k] and valid[k]
+
+
+def test_learner_glue_host_pieces():
+    from irbpp_b200 import learner_glue as glue
+    obs = np.arange(3 * 3533, dtype=np.float32).reshape(3, 3533)
+    m = glue.get_mask_from_state(obs, 500)
+    assert m.shape == (3, 500) and m[2, 7] == obs[2, 7 * 5 + 4]          # tools.py:298-299
+    assert glue.segment_size(64, 4) == (4, 16)                           # agent.py:69 when it works
+    assert glue.segment_size(64, 4096) == (64, 1)                        # ... and when int(64 / 4096) == 0
