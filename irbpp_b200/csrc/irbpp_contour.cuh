@@ -199,6 +199,44 @@ __device__ void finish_polygon(S& sc, int n, int pos, Emit emit) {
 }
 
 // ---- approxPolyDP(eps = 1, closed) + convex-vertex filter ---------------------------------------
+// Farthest point of the ring positions s + 1 .. s + len - 1 (mod n) -- the first maximum in traversal order, as
+// the serial scan with its strict `>` keeps it -- under the measure
+//   legacy: |cr|          else: cr^2 + (dot - clamp(dot, 0, hi))^2,    cr = (p - a) x d,  dot = (p - a) . d
+// (callers pass d = (1, 0), hi = 0 for "squared distance to the point a": the seeding rounds and degenerate
+// segments).  Four positions per trip: their loads and products are independent, only the final compare chain is
+// ordered, so a lane's dependent chain per four points is about as long as it used to be per point -- the chain,
+// not the instruction count, is what the lock-stepped warp waits for (profiles/).
+template <class S>
+__device__ __forceinline__ void farthest_on_arc(const S& sc, int n, int s, int len, int ax, int ay, int dx, int dy, int hi,
+                                                bool legacy, int& best, int& bi) {
+    const int c0 = ay * dx - ax * dy, d0 = ax * dx + ay * dy;
+    best = -1; bi = s;
+    int k = s;
+    for (int t = 1; t < len; t += 4) {
+        int kk[4], num[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { k = (k + 1 == n) ? 0 : k + 1; kk[j] = k; }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int p = sc.pt(kk[j]);
+            const int px = p >> 4, py = p & 15;
+            const int cr = py * dx - px * dy - c0;
+            int v;
+            if (legacy) v = cr < 0 ? -cr : cr;
+            else {
+                const int dot = px * dx + py * dy - d0;
+                const int cl = dot < 0 ? 0 : (dot > hi ? hi : dot);
+                const int tt = dot - cl;
+                v = cr * cr + tt * tt;
+            }
+            num[j] = (t + j < len) ? v : -1;             // positions beyond the arc never win
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (num[j] > best) { best = num[j]; bi = kk[j]; }
+    }
+}
+
 // Emits the selected vertices through `emit(x, y)`.
 template <class S, class Emit>
 __device__ void approx_and_emit(S& sc, int n, bool legacy, Emit emit) {
@@ -222,16 +260,11 @@ __device__ void approx_and_emit(S& sc, int n, bool legacy, Emit emit) {
     for (int it = 0; it < 3; ++it) {
         pos += far; if (pos >= n) pos -= n;
         const int pp = sc.pt(pos);
-        const int sx = pp >> 4, sy = pp & 15;
-        maxd = 0; far = 0;
-        int k = pos;
-        for (int j = 1; j < n; ++j) {
-            k = (k + 1 == n) ? 0 : k + 1;
-            const int p = sc.pt(k);
-            const int ex = (p >> 4) - sx, ey = (p & 15) - sy;
-            const int d = ex * ex + ey * ey;
-            if (d > maxd) { maxd = d; far = j; }
-        }
+        int best, bi;
+        farthest_on_arc(sc, n, pos, n, pp >> 4, pp & 15, 1, 0, 0, false, best, bi);
+        maxd = best > 0 ? best : 0;
+        far = bi - pos; if (far < 0) far += n;
+        if (maxd == 0) far = 0;
     }
     if (maxd <= 1) {  // whole contour within eps of one point
         emit(PX(pos), PY(pos));
@@ -252,45 +285,17 @@ __device__ void approx_and_emit(S& sc, int n, bool legacy, Emit emit) {
             if (len == 1) { sc.kept_set(s); break; }
             const int ps = sc.pt(s), pe = sc.pt(e);
             const int sx = ps >> 4, sy = ps & 15;
-            const int dx = (pe >> 4) - sx, dy = (pe & 15) - sy;
+            int dx = (pe >> 4) - sx, dy = (pe & 15) - sy;
             const int seg2 = dx * dx + dy * dy;
-            int best = -1, bi = s;
-            int k = s;
             // Squared distance to the segment times seg2 (4.13 rule).  With cr = v x d and dot = v . d,
             // |v|^2 |d|^2 = cr^2 + dot^2 (Lagrange), and for w = v - d: w x d = cr, w . d = dot - seg2, so
             //   inside the segment: cr^2;  before its start: cr^2 + dot^2;  beyond its end: cr^2 + (dot - seg2)^2
             // i.e. cr^2 + t^2 with t = dot - clamp(dot, 0, seg2): identical integers to the three-case form.
-            // A degenerate segment (seg2 == 0) uses |v|^2, the legacy line rule |cr|.
-            if (legacy) {
-                for (int t = 1; t < len; ++t) {
-                    k = (k + 1 == n) ? 0 : k + 1;
-                    const int p = sc.pt(k);
-                    const int vx = (p >> 4) - sx, vy = (p & 15) - sy;
-                    const int cr = vy * dx - vx * dy;
-                    const int num = cr < 0 ? -cr : cr;
-                    if (num > best) { best = num; bi = k; }
-                }
-            } else if (seg2 == 0) {
-                for (int t = 1; t < len; ++t) {
-                    k = (k + 1 == n) ? 0 : k + 1;
-                    const int p = sc.pt(k);
-                    const int vx = (p >> 4) - sx, vy = (p & 15) - sy;
-                    const int num = vx * vx + vy * vy;
-                    if (num > best) { best = num; bi = k; }
-                }
-            } else {
-                for (int t = 1; t < len; ++t) {
-                    k = (k + 1 == n) ? 0 : k + 1;
-                    const int p = sc.pt(k);
-                    const int vx = (p >> 4) - sx, vy = (p & 15) - sy;
-                    const int cr = vy * dx - vx * dy;
-                    const int dot = vx * dx + vy * dy;
-                    const int cl = dot < 0 ? 0 : (dot > seg2 ? seg2 : dot);
-                    const int tt = dot - cl;
-                    const int num = cr * cr + tt * tt;
-                    if (num > best) { best = num; bi = k; }
-                }
-            }
+            // A degenerate segment (seg2 == 0) uses |v|^2 (d = (1, 0), clamp to 0); the legacy line rule |cr|.
+            int hi = seg2;
+            if (!legacy && seg2 == 0) { dx = 1; dy = 0; hi = 0; }
+            int best, bi;
+            farthest_on_arc(sc, n, s, len, sx, sy, dx, dy, hi, legacy, best, bi);
             bool le;
             if (legacy) le = (best * best <= seg2);
             else le = (seg2 == 0) ? (best <= 1) : (best <= seg2);
@@ -302,197 +307,6 @@ __device__ void approx_and_emit(S& sc, int n, bool legacy, Emit emit) {
         }
     }
     finish_polygon(sc, n, pos, emit);
-}
-
-// ---- register-resident approxPolyDP (contours of <= 32 points) ---------------------------------------------
-// Same result as approx_and_emit, organised for the SIMT machine instead of for one thread: the contour lives
-// in NW registers (four packed points per word), and every "farthest point" search -- the three seeding rounds
-// and every Douglas-Peucker range -- is ONE statically unrolled pass over all 4*NW positions with the range as a
-// bit mask.  No loads, no loop-carried addresses, no data-dependent trip counts: the lanes of a warp, each on
-// its own contour, stay converged, and the visits of a pass are independent (instruction-level parallelism
-// instead of one dependent chain per point).  The serial form spent ~1.6 k cycles per contour point in the
-// lock-stepped warp (profiles/); see DESIGN.md.
-// The first maximum in traversal order (what the serial scan's strict `>` keeps) is recovered from two running
-// maxima of the key  num << 6 | (63 - i):  positions above the range start come first in traversal order,
-// positions below it after the wrap; inside each group a smaller index is an earlier visit.
-template <int NW>
-struct PackedContour {
-    static constexpr int CAP = 4 * NW;
-    static_assert(NW <= 8, "kept set is one 32-bit register");
-    uint32_t w[NW];
-    uint32_t kept;
-    __device__ __forceinline__ int pt(int i) const {          // dynamic index: select the word, then the byte
-        uint32_t v = w[0];
-#pragma unroll
-        for (int k = 1; k < NW; ++k) v = ((i >> 2) == k) ? w[k] : v;
-        return (int)((v >> ((i & 3) * 8)) & 0xFFu);
-    }
-    __device__ __forceinline__ void kept_clear(int) { kept = 0; }
-    __device__ __forceinline__ void kept_set(int i) { kept |= 1u << i; }
-    __device__ __forceinline__ int kept_count(int) const { return __popc(kept); }
-    __device__ __forceinline__ int kept_next(int i, int) const {
-        const uint32_t hi = (i >= 31) ? 0u : (kept & ~((2u << i) - 1u));
-        return hi ? (__ffs((int)hi) - 1) : (__ffs((int)kept) - 1);
-    }
-};
-
-// One pass: among the ring positions i = s + t (mod n), 1 <= t < len, the first one maximising
-//   LEGACY: |cr|          else: cr^2 + (dot - clamp(dot, 0, hi))^2
-// with cr = (p - a) x d, dot = (p - a) . d.  The caller passes d = (1, 0), hi = 0 for "squared distance to the
-// point a" (seeding; degenerate segment).  Returns num << 6 | (63 - i); never 0 when len >= 2.
-template <int NW, bool LEGACY>
-__device__ __forceinline__ uint32_t packed_farthest(const uint32_t (&w)[NW], int n, int s, int len, int ax, int ay,
-                                                    int dx, int dy, int hi) {
-    // bit i set <=> position i is inside the range: the low (len - 1) bits rotated left by s + 1 within n bits
-    const uint32_t m = (uint32_t)((1ull << (len - 1)) - 1ull);
-    const int sh = (s + 1 == n) ? 0 : s + 1;
-    const uint64_t mm = (uint64_t)m << sh;
-    const uint32_t in = (uint32_t)(mm | (mm >> n));           // bits >= n are never tested below (i < n is static-free: see `live`)
-    const uint32_t live = (n >= 32) ? 0xFFFFFFFFu : ((1u << n) - 1u);
-    const uint32_t above = (s >= 31) ? 0u : ~((2u << s) - 1u);
-    const uint32_t in_hi = in & live & above, in_lo = in & live & ~above;
-    const int c0 = ay * dx - ax * dy, d0 = ax * dx + ay * dy;
-    uint32_t kh = 0, kl = 0;
-#pragma unroll
-    for (int i = 0; i < 4 * NW; ++i) {
-        const int px = (int)((w[i >> 2] >> (8 * (i & 3) + 4)) & 15u), py = (int)((w[i >> 2] >> (8 * (i & 3))) & 15u);
-        const int cr = py * dx - px * dy - c0;
-        int num;
-        if (LEGACY) num = cr < 0 ? -cr : cr;
-        else {
-            const int dot = px * dx + py * dy - d0;
-            const int cl = dot < 0 ? 0 : (dot > hi ? hi : dot);
-            const int tt = dot - cl;
-            num = cr * cr + tt * tt;
-        }
-        const uint32_t key = ((uint32_t)num << 6) | (uint32_t)(63 - i);
-        const uint32_t a = ((in_hi >> i) & 1u) ? key : 0u, b = ((in_lo >> i) & 1u) ? key : 0u;
-        kh = a > kh ? a : kh;
-        kl = b > kl ? b : kl;
-    }
-    return (kh != 0u && (kh >> 6) >= (kl >> 6)) ? kh : kl;
-}
-
-// approxPolyDP(eps = 1, closed) + convex filter of the packed contour `pc` (n points, 2 <= ... handled below).
-// `active` lanes do real work; the loop structure is uniform over the warp (IRBPP_ANY: warp vote).
-#ifndef IRBPP_ANY
-#define IRBPP_ANY(p) __any_sync(0xffffffffu, (p))
-#endif
-template <int NW, bool LEGACY, class Emit>
-__device__ void approx_packed(PackedContour<NW>& pc, int n, bool active, Emit emit) {
-    bool run = active && n > 0;
-    if (run && n == 4) {       // filled axis-aligned rectangle with both sides >= 2: its four corners (see approx_and_emit)
-        const int p0 = pc.w[0] & 0xFF, p1 = (pc.w[0] >> 8) & 0xFF, p2 = (pc.w[0] >> 16) & 0xFF, p3 = pc.w[0] >> 24;
-        if ((p0 >> 4) == (p1 >> 4) && (p1 & 15) == (p2 & 15) && (p2 >> 4) == (p3 >> 4) && (p3 & 15) == (p0 & 15) &&
-            (p1 & 15) - (p0 & 15) >= 2 && (p2 >> 4) - (p1 >> 4) >= 2) {
-            emit(p0 >> 4, p0 & 15); emit(p1 >> 4, p1 & 15); emit(p2 >> 4, p2 & 15); emit(p3 >> 4, p3 & 15);
-            run = false;
-        }
-    }
-    if (run && n == 1) { const int p = pc.w[0] & 0xFF; emit(p >> 4, p & 15); run = false; }
-    // 1. seed: three rounds of "farthest point from the current one" (a point-distance pass each)
-    int pos = 0, far = 0, maxd = 0;
-#pragma unroll 1
-    for (int it = 0; it < 3; ++it) {
-        if (!IRBPP_ANY(run)) break;
-        if (run) {
-            pos += far; if (pos >= n) pos -= n;
-            const int pp = pc.pt(pos);
-            const uint32_t k = packed_farthest<NW, false>(pc.w, n, pos, n, pp >> 4, pp & 15, 1, 0, 0);
-            maxd = (int)(k >> 6);
-            int fi = 63 - (int)(k & 63u);                          // index of the farthest point
-            fi -= pos; if (fi < 0) fi += n;
-            far = maxd > 0 ? fi : 0;
-        }
-    }
-    if (run && maxd <= 1) {  // whole contour within eps of one point
-        const int pp = pc.pt(pos);
-        emit(pp >> 4, pp & 15);
-        run = false;
-    }
-    // 2. Douglas-Peucker: one range per lane and iteration; one-step ranges are resolved when they are created
-    pc.kept_clear(n);
-    RangeStack<true> st;
-    int s = 0, e = 0;
-    bool have = false;
-    if (run) {
-        int fp = pos + far; if (fp >= n) fp -= n;
-        // the two arcs pos -> fp and fp -> pos; an arc of one step keeps its start
-        int l1 = fp - pos; if (l1 <= 0) l1 += n;
-        int l2 = pos - fp; if (l2 <= 0) l2 += n;
-        if (l2 == 1) pc.kept_set(fp); else st.push(fp, pos);
-        if (l1 == 1) pc.kept_set(pos); else st.push(pos, fp);
-    }
-#pragma unroll 1
-    for (;;) {
-        if (run && !have) {
-            if (st.empty()) run = false;
-            else { st.pop(s, e); have = true; }
-        }
-        if (!IRBPP_ANY(run)) break;
-        if (run) {
-            int len = e - s; if (len <= 0) len += n;             // >= 2 by construction
-            const int ps = pc.pt(s), pe = pc.pt(e);
-            const int sx = ps >> 4, sy = ps & 15;
-            int dx = (pe >> 4) - sx, dy = (pe & 15) - sy;
-            const int seg2 = dx * dx + dy * dy;
-            int hi = seg2;
-            if (!LEGACY && seg2 == 0) { dx = 1; dy = 0; hi = 0; }     // squared distance to the point
-            const uint32_t k = packed_farthest<NW, LEGACY>(pc.w, n, s, len, sx, sy, dx, dy, hi);
-            const int best = (int)(k >> 6);
-            const int bi = 63 - (int)(k & 63u);
-            bool le;
-            if (LEGACY) le = (best * best <= seg2);
-            else le = (seg2 == 0) ? (best <= 1) : (best <= seg2);
-            if (le) { pc.kept_set(s); have = false; }
-            else {
-                int ll = bi - s; if (ll <= 0) ll += n;
-                const int lr = len - ll;
-                // children (s, bi) and (bi, e); a one-step child keeps its start at once; the larger one is deferred
-                const bool left_leaf = (ll == 1), right_leaf = (lr == 1);
-                if (left_leaf) pc.kept_set(s);
-                if (right_leaf) pc.kept_set(bi);
-                if (left_leaf && right_leaf) have = false;
-                else if (left_leaf) { s = bi; }
-                else if (right_leaf) { e = bi; }
-                else if (ll <= lr) { st.push(bi, e); e = bi; }
-                else { st.push(s, bi); s = bi; }
-            }
-        }
-    }
-    if (active && n > 0 && pc.kept != 0u) finish_polygon(pc, n, pos, emit);
-}
-
-// Load the first n (<= 4 * NW) points of a scratch accessor into the packed form.
-template <int NW, class S>
-__device__ __forceinline__ void load_packed(PackedContour<NW>& pc, const S& sc, int n) {
-#pragma unroll
-    for (int k = 0; k < NW; ++k) {
-        uint32_t v = 0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-            if (4 * k + j < n) v |= (uint32_t)sc.pt(4 * k + j) << (8 * j);
-        pc.w[k] = v;
-    }
-    pc.kept = 0;
-}
-
-// One warp-uniform call: every lane brings a contour of n points (0: none) in `sc`; `cls` is the smallest of
-// 1, 2, 4, 8 with 4 * cls >= the largest n of the warp (<= 32; longer contours take approx_and_emit).
-template <class S, class Emit>
-__device__ __forceinline__ void approx_packed_dispatch(const S& sc, int n, int cls, bool legacy, bool active, Emit emit) {
-#define IRBPP_APPROX_CASE(NW)                                                                     \
-    {                                                                                              \
-        PackedContour<NW> pc;                                                                      \
-        load_packed(pc, sc, active ? n : 0);                                                       \
-        if (legacy) approx_packed<NW, true>(pc, n, active, emit);                                  \
-        else approx_packed<NW, false>(pc, n, active, emit);                                        \
-    }
-    if (cls <= 1) IRBPP_APPROX_CASE(1)
-    else if (cls == 2) IRBPP_APPROX_CASE(2)
-    else if (cls <= 4) IRBPP_APPROX_CASE(4)
-    else IRBPP_APPROX_CASE(8)
-#undef IRBPP_APPROX_CASE
 }
 
 // ---- start pixels ------------------------------------------------------------------------------------------
@@ -550,8 +364,8 @@ __device__ int follow_outer_rows(S& sc, const uint32_t* rows, int x0, int y0, in
     for (;;) {
         const uint32_t rot = ((ring * 0x101u) >> ((s + 1) & 7)) & 0xFFu;     // s points back to the previous pixel
         s = (s + __ffs((int)rot)) & 7;
-        const int x4 = x3 + ddx(s), y4 = y3 + ddy(s);
-        const int p4 = (y4 << 5) | x4;
+        int x4 = x3 + ddx(s), y4 = y3 + ddy(s);
+        int p4 = (y4 << 5) | x4;
         if (p4 < p0) return -2;                          // a pixel of this border precedes the start
         a2 += x3 * y4 - x4 * y3;
         if (s != prev_s) {
@@ -560,6 +374,46 @@ __device__ int follow_outer_rows(S& sc, const uint32_t* rows, int x0, int y0, in
         }
         prev_s = s;
         if (p4 == p0 && ((y3 << 5) | x3) == p1) break;
+        // Straight runs along an axis are taken in one jump.  Arrived at p4 in direction s, the follower goes on in
+        // direction s iff the three neighbours it probes first (counter-clockwise from the way back) are background
+        // and the pixel ahead is foreground: for E / W that is one row of clear pixels beside the run (below for E,
+        // above for W) and a run of set pixels in the row itself -- its length by bit scans of the two row words;
+        // for N / S the same condition is stepped pixel by pixel (three bits of the neighbouring column, one ahead).
+        // No point is emitted inside a run (the direction does not change); the start pixel p0 can only be the
+        // LAST pixel of a run (its W, N neighbours are background), so the end test below sees it; a W or N run
+        // only descends in raster order, so its end pixel is the one to test against p0.
+        if ((s & 1) == 0) {
+            int k = 0;                                   // further steps in direction s
+            if (s == 0) {          // E: row below clear at x-1..x+1 of every pixel left, pixel ahead set
+                const uint32_t below = rows[y4 + 2];
+                const uint32_t clr = ~(below | (below << 1) | (below >> 1));        // bit c+1: columns c-1..c+1 of the row below clear
+                const uint32_t ahead = rows[y4 + 1] >> (x4 + 2);                    // bit t: pixel (x4 + 1 + t, y4)
+                const uint32_t ok = ahead & (clr >> (x4 + 1));
+                k = __ffs((int)~ok) - 1;
+            } else if (s == 4) {   // W: row above clear, pixel behind (x - 1) set; bits scanned downwards from x4
+                const uint32_t above = rows[y4];
+                const uint32_t clr = ~(above | (above << 1) | (above >> 1));
+                // continuing from pixel c needs clr bit (c + 1) and the pixel c - 1 (row bit c): aligned at bit c
+                const uint32_t ok = rows[y4 + 1] & (clr >> 1);
+                k = __clz((int)~(ok << (31 - x4)));
+            } else if (s == 6) {   // S: column x-1 clear at y-1..y+1, pixel below set
+                int yy = y4;
+                while ((((rows[yy] | rows[yy + 1] | rows[yy + 2]) >> x4) & 1u) == 0u && ((rows[yy + 2] >> (x4 + 1)) & 1u)) { ++yy; ++k; }
+            } else {               // N: column x+1 clear at y-1..y+1, pixel above set
+                int yy = y4;
+                while ((((rows[yy] | rows[yy + 1] | rows[yy + 2]) >> (x4 + 2)) & 1u) == 0u && ((rows[yy] >> (x4 + 1)) & 1u)) { --yy; ++k; }
+            }
+            if (k > 0) {
+                const int dx = ddx(s), dy = ddy(s);
+                const int xe = x4 + k * dx, ye = y4 + k * dy;                       // last pixel of the run
+                if (((ye << 5) | xe) < p0) return -2;
+                // sum over the k steps of x_i * y_{i+1} - x_{i+1} * y_i: along an axis each term is -+y (E / W) or +-x (S / N)
+                a2 += k * (x4 * dy - y4 * dx);
+                x3 = xe - dx; y3 = ye - dy;
+                x4 = xe; y4 = ye; p4 = (y4 << 5) | x4;
+                if (p4 == p0 && ((y3 << 5) | x3) == p1) break;
+            }
+        }
         x3 = x4; y3 = y4;
         s ^= 4;
         ring = ring_at(x3, y3);

@@ -1020,21 +1020,16 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
             phase_mark(6);   // length sort
 #endif
             // (c) lane i approximates the i-th longest contour (points live in its owner's scratch)
-            //     in the register-resident form (approx_packed): the warp runs the class of its longest contour
             {
                 const int owner = S.order2[tid];
-                const int on = S.n_of[owner];                       // 0: nothing to approximate
-                StridedScratch<32, FAST_CAP> sc;
-                sc.b = ws_base + (size_t)(owner >> 5) * P.ws_bytes + (owner & 31);
-                sc.kept = 0;
-                uint32_t* cb = candbits + (int)S.q_of[owner] * 8;
-                auto emit = [&](int ex, int ey) { const int b = ex * 16 + ey; atomicOr(cb + (b >> 5), 1u << (b & 31)); };
-                const int nmax = (int)__reduce_max_sync(0xffffffffu, (unsigned)on);
-                if (nmax > 0) {
-                    if (on > 32) approx_and_emit(sc, on, P.legacy != 0, emit);          // rare: longer than the register form holds
-                    const int m32 = nmax < 32 ? nmax : 32;
-                    const int cls = m32 <= 4 ? 1 : (m32 <= 8 ? 2 : (m32 <= 16 ? 4 : 8));
-                    approx_packed_dispatch(sc, on, cls, P.legacy != 0, on > 0 && on <= 32, emit);
+                const int on = S.n_of[owner];
+                if (on > 0) {
+                    StridedScratch<32, FAST_CAP> sc;
+                    sc.b = ws_base + (size_t)(owner >> 5) * P.ws_bytes + (owner & 31);
+                    sc.kept = 0;
+                    uint32_t* cb = candbits + (int)S.q_of[owner] * 8;
+                    approx_and_emit(sc, on, P.legacy != 0,
+                                    [&](int ex, int ey) { const int b = ex * 16 + ey; atomicOr(cb + (b >> 5), 1u << (b & 31)); });
                 }
             }
             __syncthreads();           // scratch of every lane is free again

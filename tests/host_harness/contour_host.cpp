@@ -33,29 +33,7 @@ extern "C" int hull_bits(const uint16_t* rows16, int legacy, int mode, uint32_t*
         irbpp::StridedScratch<1, 64> sc; sc.b = b; sc.kept = 0;
         return irbpp::process_level_image_mt(sc, rows, legacy != 0, emit) ? 0 : 1;
     }
-    if (mode == 7 || mode == 8) {
-        // the register-resident form the kernel runs (approx_packed): contours of <= 32 points in the smallest
-        // class that holds them (7) or always in the 32-point class (8); longer ones take the serial routine
-        static uint8_t b[64];
-        bool ok = true;
-        for (int y = 0; y < 16; ++y) {
-            uint32_t c = irbpp::start_candidates_rows(rows, y);
-            while (c) {
-                const int x = __builtin_ctz(c);
-                c &= c - 1;
-                irbpp::StridedScratch<1, 64> sc; sc.b = b; sc.kept = 0;
-                int area2;
-                const int n = irbpp::follow_outer_rows(sc, rows, x, y, area2);
-                if (n == -2 || area2 > 0) continue;
-                if (n < 0) { ok = false; continue; }
-                if (n > 32) { irbpp::approx_and_emit(sc, n, legacy != 0, emit); continue; }
-                const int cls = (mode == 8) ? 8 : (n <= 4 ? 1 : n <= 8 ? 2 : n <= 16 ? 4 : 8);
-                irbpp::approx_packed_dispatch(sc, n, cls, legacy != 0, true, emit);
-            }
-        }
-        return ok ? 0 : 1;
-    }
-    return -1;   // modes 5 to 8 only
+    return -1;   // modes 5 and 6 only
 }
 
 extern "C" void floor_div_many(const double* a, double b, int n, double* out) {

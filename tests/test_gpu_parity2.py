@@ -270,7 +270,7 @@ def test_point_cloud_sampling_and_shape_features_match_torch_fp32():
 
 
 def test_actor_loop_through_learner_glue_at_4096_bins():
-    """SURVEY.md 8(f)2, executed: the reference's actor loop shape (trainer.py:157-186) for 24 iterations at N = 4096
+    """SURVEY.md 8(f)2, executed: the reference's actor loop shape (trainer.py:157-186) for 60 iterations at N = 4096
     -- mask on the device (tools.py:283-300), infos consumed through the batched views, one replay-bank append per
     step, a batch drawn with the segment rule of agent.py:69 made safe for N > batch_size -- and the batched views
     agree with the per-bin dicts the reference's loop reads."""
@@ -285,7 +285,7 @@ def test_actor_loop_through_learner_glue_at_4096_bins():
     state = env.reset()
     assert glue.segment_size(64, 4096) == (64, 1) and glue.segment_size(64, 16) == (16, 4)
     total_done = 0
-    for T in range(1, 25):
+    for T in range(1, 61):
         mask = glue.get_mask_from_state(state, sel)
         assert mask.shape == (n, sel) and mask.is_cuda
         q = torch.rand((n, sel), device="cuda:0", generator=gen)

@@ -54,7 +54,7 @@ def main():
             want = set()
             for c in conts:
                 want |= {(int(p[0]), int(p[1])) for p in cp.convex_vertices(cp.approx_poly_dp_closed(c, 1.0, bool(legacy)))}
-            for mode in (5, 6, 7, 8):
+            for mode in (5, 6):
                 rc = lib.hull_bits(rows.ctypes.data_as(ctypes.c_void_p), legacy, mode, out.ctypes.data_as(ctypes.c_void_p))
                 if rc != 0:
                     assert max(len(c) for c in conts) > 64, (it, legacy, mode)
