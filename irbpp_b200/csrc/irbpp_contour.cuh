@@ -364,8 +364,8 @@ __device__ int follow_outer_rows(S& sc, const uint32_t* rows, int x0, int y0, in
     for (;;) {
         const uint32_t rot = ((ring * 0x101u) >> ((s + 1) & 7)) & 0xFFu;     // s points back to the previous pixel
         s = (s + __ffs((int)rot)) & 7;
-        int x4 = x3 + ddx(s), y4 = y3 + ddy(s);
-        int p4 = (y4 << 5) | x4;
+        const int x4 = x3 + ddx(s), y4 = y3 + ddy(s);
+        const int p4 = (y4 << 5) | x4;
         if (p4 < p0) return -2;                          // a pixel of this border precedes the start
         a2 += x3 * y4 - x4 * y3;
         if (s != prev_s) {
@@ -374,46 +374,6 @@ __device__ int follow_outer_rows(S& sc, const uint32_t* rows, int x0, int y0, in
         }
         prev_s = s;
         if (p4 == p0 && ((y3 << 5) | x3) == p1) break;
-        // Straight runs along an axis are taken in one jump.  Arrived at p4 in direction s, the follower goes on in
-        // direction s iff the three neighbours it probes first (counter-clockwise from the way back) are background
-        // and the pixel ahead is foreground: for E / W that is one row of clear pixels beside the run (below for E,
-        // above for W) and a run of set pixels in the row itself -- its length by bit scans of the two row words;
-        // for N / S the same condition is stepped pixel by pixel (three bits of the neighbouring column, one ahead).
-        // No point is emitted inside a run (the direction does not change); the start pixel p0 can only be the
-        // LAST pixel of a run (its W, N neighbours are background), so the end test below sees it; a W or N run
-        // only descends in raster order, so its end pixel is the one to test against p0.
-        if ((s & 1) == 0) {
-            int k = 0;                                   // further steps in direction s
-            if (s == 0) {          // E: row below clear at x-1..x+1 of every pixel left, pixel ahead set
-                const uint32_t below = rows[y4 + 2];
-                const uint32_t clr = ~(below | (below << 1) | (below >> 1));        // bit c+1: columns c-1..c+1 of the row below clear
-                const uint32_t ahead = rows[y4 + 1] >> (x4 + 2);                    // bit t: pixel (x4 + 1 + t, y4)
-                const uint32_t ok = ahead & (clr >> (x4 + 1));
-                k = __ffs((int)~ok) - 1;
-            } else if (s == 4) {   // W: row above clear, pixel behind (x - 1) set; bits scanned downwards from x4
-                const uint32_t above = rows[y4];
-                const uint32_t clr = ~(above | (above << 1) | (above >> 1));
-                // continuing from pixel c needs clr bit (c + 1) and the pixel c - 1 (row bit c): aligned at bit c
-                const uint32_t ok = rows[y4 + 1] & (clr >> 1);
-                k = __clz((int)~(ok << (31 - x4)));
-            } else if (s == 6) {   // S: column x-1 clear at y-1..y+1, pixel below set
-                int yy = y4;
-                while ((((rows[yy] | rows[yy + 1] | rows[yy + 2]) >> x4) & 1u) == 0u && ((rows[yy + 2] >> (x4 + 1)) & 1u)) { ++yy; ++k; }
-            } else {               // N: column x+1 clear at y-1..y+1, pixel above set
-                int yy = y4;
-                while ((((rows[yy] | rows[yy + 1] | rows[yy + 2]) >> (x4 + 2)) & 1u) == 0u && ((rows[yy] >> (x4 + 1)) & 1u)) { --yy; ++k; }
-            }
-            if (k > 0) {
-                const int dx = ddx(s), dy = ddy(s);
-                const int xe = x4 + k * dx, ye = y4 + k * dy;                       // last pixel of the run
-                if (((ye << 5) | xe) < p0) return -2;
-                // sum over the k steps of x_i * y_{i+1} - x_{i+1} * y_i: along an axis each term is -+y (E / W) or +-x (S / N)
-                a2 += k * (x4 * dy - y4 * dx);
-                x3 = xe - dx; y3 = ye - dy;
-                x4 = xe; y4 = ye; p4 = (y4 << 5) | x4;
-                if (p4 == p0 && ((y3 << 5) | x3) == p1) break;
-            }
-        }
         x3 = x4; y3 = y4;
         s ^= 4;
         ring = ring_at(x3, y3);

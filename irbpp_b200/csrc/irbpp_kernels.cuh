@@ -327,13 +327,16 @@ __device__ __forceinline__ bool scan_rotation_dense(const Params& P, const doubl
     const double inv = 1.0 / P.resZ;
     double* posz_g = P.posz + ((int64_t)env * P.R + r) * NPOSE;
     const uint32_t magic = 65536u / (uint32_t)(nY > 0 ? nY : 1) + 1u;      // v / nY == (v * magic) >> 16 for v < 256, nY <= 16
-    for (int c0 = 0; c0 < V; c0 += 128) {
-        int cell[4];
-        const double* base[4];
-        bool valid[4];
-        double acc[4];
+    // PPL poses per lane: chunks of 128 poses with four accumulators per lane, then what is left (nX * nY is
+    // rarely a multiple of 128) with two or one, so the tail does not cost a full four-pose pass
+    auto chunk = [&](int c0, auto ppl_tag) {
+        constexpr int PPL = decltype(ppl_tag)::value;
+        int cell[PPL];
+        const double* base[PPL];
+        bool valid[PPL];
+        double acc[PPL];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < PPL; ++k) {
             const int v = c0 + k * 32 + lane;
             valid[k] = v < V;
             const int X = valid[k] ? (int)(((uint32_t)v * magic) >> 16) : 0;
@@ -346,13 +349,13 @@ __device__ __forceinline__ bool scan_rotation_dense(const Params& P, const doubl
         for (int e = 0; e < nt; ++e) {
             const TileEntry en = es[e];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < PPL; ++k) {
                 const double u = base[k][en.off] - en.b;
                 acc[k] = (u > acc[k]) ? u : acc[k];
             }
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < PPL; ++k) {
             if (valid[k]) {
                 const bool feas = round6_le0(acc[k] + ez - P.binz);
                 int code = 0;
@@ -365,6 +368,12 @@ __device__ __forceinline__ bool scan_rotation_dense(const Params& P, const doubl
                 lv_s[cell[k]] = (uint8_t)code;
             }
         }
+    };
+    {
+        int c0 = 0;
+        for (; V - c0 > 64; c0 += 128) chunk(c0, std::integral_constant<int, 4>());
+        if (V - c0 > 32) chunk(c0, std::integral_constant<int, 2>());
+        else if (V - c0 > 0) chunk(c0, std::integral_constant<int, 1>());
     }
     __syncwarp();
     // fixed-layout pass: feasibility bits, level presence, bitmaps; poses outside the scanned range keep 1e3 / 0
@@ -818,6 +827,19 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
             t_prev = now;
         }
     };
+#ifdef IRBPP_PROBE_TRACE
+    // profiling build only: per-CTA timeline (globaltimer, ns) in P.phase_cycles[8 + blockIdx.x * 8 + slot]
+    auto trace = [&](int slot, unsigned long long v = ~0ull) {
+        if (P.phase_cycles && tid == 0) {
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+            P.phase_cycles[8 + (size_t)blockIdx.x * 8 + slot] = (v == ~0ull) ? t : v;
+        }
+    };
+    trace(0);
+#else
+    auto trace = [&](int, unsigned long long = 0ull) {};
+#endif
     auto env_live = [&](int e) { return !(P.mode == MODE_RESET && P.which && !P.which[e]); };
     // the "bins" of this kernel are (bin, buffer slot) pairs in MODE_ALL_OBS (see the scan kernel): real bin, slot and
     // the place of a pair's rows in the observation
@@ -859,6 +881,7 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
     }
     __syncthreads();
     const int nimg = S.pre[npairs];
+    trace(1);
     unsigned char* ws_base = smem_raw + ((sizeof(CandSmem) + 15) & ~(size_t)15);     // CAND_WARPS blocks of P.ws_bytes
     uint8_t* W_pts = ws_base + (size_t)warp * P.ws_bytes;
 
@@ -949,6 +972,7 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
             }
         }
         __syncthreads();
+        if (base == 0) trace(2);
 #ifdef IRBPP_PROBE_FINE
         phase_mark(4);   // prologue, image loads, cost sort, start-pixel prefix
 #else
@@ -993,6 +1017,7 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
             //     of a warp have similar trip counts and abandoned / hole paths drop out
             if (tid < 64) S.hist[tid] = 0;
             __syncthreads();
+            if (base == 0 && mb == 0) trace(3);
 #ifdef IRBPP_PROBE_FINE
             phase_mark(5);   // find start pixel + follow (incl. waiting for the slowest warp)
 #endif
@@ -1033,6 +1058,7 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
                 }
             }
             __syncthreads();           // scratch of every lane is free again
+            if (base == 0 && mb == 0) { trace(4); int mx = 0; for (int i = 0; i < CAND_THREADS; ++i) mx = max(mx, (int)S.n_of[i]); trace(7, ((unsigned long long)ntask << 8) | (unsigned long long)mx); }
 #ifdef IRBPP_PROBE_FINE
             phase_mark(7);   // approxPolyDP + emit
 #endif
@@ -1060,6 +1086,7 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
         __syncthreads();
     }
     __syncthreads();
+    trace(5);
     phase_mark(2);   // contour tasks
 
     // ---- phase D: warp w serves bin env0 + w ----
@@ -1210,6 +1237,7 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
         if (dev_err) { P.r_error[renv] = (uint8_t)dev_err; if (P.h_error) P.h_error[renv] = (uint8_t)dev_err; }
         if (P.dbg_nhull) P.dbg_nhull[env] = Ktot;
     }
+    if (warp == 0) trace(6);
     phase_mark(3);   // select / pad, candidate rows of the observation
 }
 

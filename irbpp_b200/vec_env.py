@@ -357,7 +357,31 @@ class GpuVecEnv(VecEnv):
         self._check(self._lib.irbpp_step_async(self._h, ptr, 1, obs.data_ptr(), self._stream()))
         res = self._result
         self._check(self._lib.irbpp_step_wait_device(self._h, ctypes.byref(res)))
+        if getattr(self, "_dev_ptrs", None) is None:
+            self._dev_ptrs = {k: getattr(res, k) for k, _ in self._RESULT_BYTES}
         return obs, res
+
+    def last_step_device(self):
+        """Device views of the last step's result arrays -- ``reward`` float32 [N], ``done`` / ``valid`` uint8 [N],
+        ``counter`` int32 [N], ``ratio`` float64 [N] -- as torch tensors aliasing the library's buffers (valid until
+        the next step on this handle): what a device-resident replay bank appends without any host round trip."""
+        torch = self._torch
+        res = _lib.IrbppStepResult()
+        lib = self._lib
+        # the device pointers are fixed for the life of the handle; irbpp_step_wait_device only reports them when a
+        # step is pending, so they are cached from the first device-resident query
+        ptrs = getattr(self, "_dev_ptrs", None)
+        if ptrs is None:
+            raise RuntimeError("no device result views yet: call step_device() once, or step() after enable_device_results()")
+        n = self.num_envs
+
+        class _View(object):
+            def __init__(self, ptr, shape, typestr):
+                self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (int(ptr), False), "version": 2}
+        spec = {"reward": ("<f4", torch.float32), "done": ("|u1", torch.uint8), "valid": ("|u1", torch.uint8),
+                "counter": ("<i4", torch.int32), "ratio": ("<f8", torch.float64), "ep_len": ("<i4", torch.int32),
+                "ep_reward": ("<f8", torch.float64)}
+        return {k: torch.as_tensor(_View(ptrs[k], (n,), ts), device=self.device) for k, (ts, _) in spec.items()}
 
     def get_action_candidates(self, order_actions, as_tensor=False):
         """``envs.get_action_candidates(orderAction)`` (shmem_vec_env.py:99-102 -> binPhy.py:161-169).

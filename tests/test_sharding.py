@@ -48,6 +48,17 @@ def _worker(rank, world, port, n_total, width, out_q):
     acts = torch.arange(n_total, dtype=torch.int64) * 3
     mine_acts = sharding.scatter_actions(acts, rank, world)
     ok = ok and bool((mine_acts == acts[lo:hi]).all())
+    # the pipelined form bench.py uses: start the gather, keep "stepping", finish; two rollouts back to back
+    g = sharding.AsyncRolloutGather(world)
+    for rollout in range(3):
+        g.start(local + rollout)
+        busy = torch.ones(4).sum()                     # work that overlaps the collective
+        got = g.finish()
+        ok = ok and got.shape == (n_total, width) and bool((got[:, 0] == torch.arange(n_total, dtype=torch.float32) + rollout).all())
+    try:
+        g.finish(); ok = False                         # nothing in flight
+    except RuntimeError:
+        pass
     t = torch.tensor([1.0 + rank])
     dist.all_reduce(t, op=dist.ReduceOp.MAX)          # the bench's max-over-ranks timing reduction
     ok = ok and float(t.item()) == float(world)
