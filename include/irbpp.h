@@ -127,6 +127,10 @@ int irbpp_step_wait(irbpp_handle h, irbpp_step_result* out);
  * returns device views of the result arrays (valid in stream order). */
 int irbpp_step_wait_device(irbpp_handle h, irbpp_device_result* out);
 
+/* The device copies of the per-env result arrays (fixed for the life of the handle; every step writes them in
+ * stream order, also when its results are delivered to the host): what a device-resident replay buffer reads. */
+int irbpp_device_results(irbpp_handle h, irbpp_device_result* out);
+
 /* Replaces: envs.get_action_candidates(order_actions) (wrapper/shmem_vec_env.py:99-102 ->
  * binPhy.py:161-169), buffer_size > 1 only.  order_actions: int64[N] host or device.
  * loc_obs_out: dev float32 [N, loc_obs_len]. */

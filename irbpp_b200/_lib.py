@@ -40,6 +40,7 @@ SIGNATURES = {
     "irbpp_step_async": (c_i32, [c_void_p, c_void_p, c_i32, c_void_p, c_void_p]),
     "irbpp_step_wait": (c_i32, [c_void_p, ctypes.POINTER(IrbppStepResult)]),
     "irbpp_step_wait_device": (c_i32, [c_void_p, ctypes.POINTER(IrbppStepResult)]),
+    "irbpp_device_results": (c_i32, [c_void_p, ctypes.POINTER(IrbppStepResult)]),
     "irbpp_get_action_candidates": (c_i32, [c_void_p, c_void_p, c_i32, c_void_p, c_void_p]),
     "irbpp_get_all_possible_observation": (c_i32, [c_void_p, c_void_p, c_void_p]),
     "irbpp_heuristic_actions": (c_i32, [c_void_p, c_i32, c_i32, c_void_p, c_void_p, c_i32, c_void_p]),

@@ -163,6 +163,11 @@ int irbpp_create(const irbpp_config* cfg, irbpp_handle* out) {
     P.resA = cfg->resolution_act;
     P.binvol = (cfg->bin_dimension[0] * cfg->bin_dimension[1]) * cfg->bin_dimension[2];   // np.prod
     P.ws_bytes = ws_bytes_for(P.R);
+    {   // bins per candidates CTA: one round of CAND_THREADS level images should hold them (~6 images per rotation and bin)
+        int epc = CAND_THREADS / (6 * P.R);
+        P.epc = epc < 1 ? 1 : (epc > ENVS_PER_CTA ? ENVS_PER_CTA : epc);
+        if (const char* m = getenv("IRBPP_BINS_PER_CTA")) { const int v = atoi(m); if (v >= 1 && v <= ENVS_PER_CTA) P.epc = v; }
+    }
     h->cand_smem = (int)((sizeof(CandSmem) + 15) & ~(size_t)15) + CAND_WARPS * P.ws_bytes + ENVS_PER_CTA * P.R * 8 * 4;
 
 #define TRY_ALLOC(expr)                                                                          \
@@ -180,6 +185,7 @@ int irbpp_create(const irbpp_config* cfg, irbpp_handle* out) {
     TRY_ALLOC(dev_alloc(h, &P.maskbits, units * P.R * 8));
     TRY_ALLOC(dev_alloc(h, &P.bitmaps, units * P.R * MAX_LEVELS * 8));
     TRY_ALLOC(dev_alloc(h, &P.nlevels, units * P.R));
+    if (!lists_in_smem(P.R)) TRY_ALLOC(dev_alloc(h, &P.dlist, units * 2 * P.R * NPOSE));
     // result block (8-byte fields first so every array stays aligned)
     h->results_bytes = (size_t)N * (8 + 8 + 4 + 4 + 4 + 1 + 1 + 1);
     TRY_ALLOC(cudaMalloc(&h->results_dev, h->results_bytes + 64));
@@ -422,7 +428,7 @@ static int launch(irbpp_env* h, Params& P, cudaStream_t s) {
         // programmatic dependent launch: the candidates grid is scheduled while the scan grid's last
         // wave drains and waits at griddepcontrol.wait for the scan's completion
         cudaLaunchConfig_t lc = {};
-        lc.gridDim = dim3((units + ENVS_PER_CTA - 1) / ENVS_PER_CTA); lc.blockDim = dim3(CAND_THREADS);
+        lc.gridDim = dim3((units + P.epc - 1) / P.epc); lc.blockDim = dim3(CAND_THREADS);
         lc.dynamicSmemBytes = (size_t)h->cand_smem; lc.stream = s;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -555,6 +561,14 @@ int irbpp_step_wait_device(irbpp_handle h, irbpp_device_result* out) {
         out->counter = h->P.r_counter; out->ep_len = h->P.r_eplen; out->done = h->P.r_done;
         out->valid = h->P.r_valid; out->error = h->P.r_error;
     }
+    return IRBPP_OK;
+}
+
+int irbpp_device_results(irbpp_handle h, irbpp_device_result* out) {
+    if (!h || !out) return IRBPP_EINVAL;
+    out->ratio = h->P.r_ratio; out->ep_reward = h->P.r_eprew; out->reward = h->P.r_reward;
+    out->counter = h->P.r_counter; out->ep_len = h->P.r_eplen; out->done = h->P.r_done;
+    out->valid = h->P.r_valid; out->error = h->P.r_error;
     return IRBPP_OK;
 }
 
@@ -780,7 +794,7 @@ int irbpp_debug_phase_cycles(irbpp_handle h, int32_t enable, uint64_t* out8) {
     if (!h) return IRBPP_EINVAL;
     cudaSetDevice(h->cfg.device);
 #ifdef IRBPP_PROBE_TRACE
-    const size_t trace_words = 8 + ((size_t)h->P.N * h->P.K / ENVS_PER_CTA + 1) * 8;     // profiling build: per-CTA timelines behind the counters
+    const size_t trace_words = 8 + ((size_t)h->P.N * h->P.K + 1) * 8;     // profiling build: per-CTA timelines behind the counters
 #else
     const size_t trace_words = 8;
 #endif

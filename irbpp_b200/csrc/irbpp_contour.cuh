@@ -333,10 +333,10 @@ __device__ __forceinline__ uint32_t start_candidates_rows(const uint32_t* rows, 
 // spot.  So every candidate pixel of an image can be processed independently -- one (image, candidate)
 // pair per lane: follow, test the signed area, approximate, emit.  The serial chain of a lane is one
 // contour instead of all contours of an image.
-// Returns the number of stored points (>= 1), -1 if the contour exceeded S::CAP, or -2 if the path
+// Returns the number of stored points (>= 1), -1 if the contour exceeded `cap` (<= S::CAP) points, or -2 if the path
 // was abandoned (not a raster-first start) -- in which case nothing must be emitted.
 template <class S>
-__device__ int follow_outer_rows(S& sc, const uint32_t* rows, int x0, int y0, int& area2) {
+__device__ int follow_outer_rows(S& sc, const uint32_t* rows, int x0, int y0, int& area2, int cap = S::CAP) {
     // 8-neighbourhood ring of pixel (x, y), bit d = neighbour in direction d
     auto ring_at = [&](int x, int y) -> uint32_t {
         const uint32_t wm = (rows[y] >> x) & 7u;        // bit0 = col x-1, bit1 = col x, bit2 = col x+1
@@ -369,7 +369,7 @@ __device__ int follow_outer_rows(S& sc, const uint32_t* rows, int x0, int y0, in
         if (p4 < p0) return -2;                          // a pixel of this border precedes the start
         a2 += x3 * y4 - x4 * y3;
         if (s != prev_s) {
-            if (n < S::CAP) sc.set_pt(n, (x3 << 4) | y3);
+            if (n < cap) sc.set_pt(n, (x3 << 4) | y3);
             ++n;
         }
         prev_s = s;
@@ -379,7 +379,7 @@ __device__ int follow_outer_rows(S& sc, const uint32_t* rows, int x0, int y0, in
         ring = ring_at(x3, y3);
     }
     area2 = a2;
-    return (n > S::CAP) ? -1 : n;
+    return (n > cap) ? -1 : n;
 }
 
 // one micro-task: returns false only when the contour overflowed S::CAP points

@@ -57,7 +57,8 @@ constexpr int CAND_WARPS = IRBPP_CAND_WARPS;          // warps per CTA of the ca
 constexpr int CAND_THREADS = 32 * CAND_WARPS;
 static_assert(CAND_WARPS >= ENVS_PER_CTA, "phase D needs one warp per bin");
 constexpr int MAX_LEVELS = 64;           // level-image slots per (bin, rotation) in the scratch
-constexpr int TASK_TAB = 256;            // start pixels of a round listed explicitly (the rest are found by search)
+constexpr int TASKS_PER_LANE = 3;        // micro-tasks a lane takes per batch of the candidates kernel (one follow / sort / approximate cycle)
+constexpr int TASK_TAB = 384;            // start pixels of a round listed explicitly (the rest are found by search)
 constexpr int FAST_CAP = 64;             // contour points on the fast path (32 was measured slower: every overflow redo stalls a warp)
 constexpr int BIG_CAP = 1024;            // contour points on the overflow path
 constexpr int LEVEL_OFFSET = 32;         // levels in [-32, 31] -> presence bit (level + 32)
@@ -150,6 +151,8 @@ struct Params {
     const uint8_t* which;                // MODE_RESET (NULL = all)
     const int32_t* dbg_items;            // MODE_DEBUG_SCAN
     int32_t ws_bytes;                    // per-warp scratch of the candidates kernel (ws_bytes_for(R))
+    int32_t epc;                         // bins per CTA of the candidates kernel (1 .. ENVS_PER_CTA)
+    uint16_t* dlist;                     // [units][2][R*256] phase D lists when they do not fit the warp scratch (R > 4), else NULL
     int32_t pose_actions;                // MODE_STEP: actions are flat poses (rot*256 + lx*16 + ly), not candidate rows
     int32_t heur_method, heur_dir;       // heuristic kernel: Heuristic, dirIdx 0..3 (space.py:162-166)
     int32_t* heur_pose;                  // [N][3] rot, lx, ly
@@ -790,10 +793,12 @@ __global__ void __launch_bounds__(CTA_THREADS) irbpp_heuristic_kernel(const Para
 constexpr int WS_MIN_BYTES = 4096;
 static_assert(WS_MIN_BYTES >= 2 * BIG_CAP && WS_MIN_BYTES >= FAST_CAP * 32, "overflow buffers must fit the lane scratch");
 static_assert(CAND_THREADS * ROWS_WORDS >= ENVS_PER_CTA * 128, "phase D's rank histograms reuse the image slots");
-__host__ __device__ inline int ws_bytes_for(int R) {
-    const int need = R * NPOSE * 4;                      // uint16 list + uint16 sorted list for every pose
-    return ((need > WS_MIN_BYTES ? need : WS_MIN_BYTES) + 15) & ~15;
-}
+// Phase D's candidate list + bucket-sorted index list (2 x uint16 per pose of the bin) live in the warp scratch when
+// they fit (R <= 4); for more rotations they go to a global scratch (Params::dlist, L2 resident) instead of growing
+// the CTA's shared memory: at R = 8 the 8 KB per warp cut the residency to 4 CTAs per SM, the grid no longer fitted
+// in one wave and the kernel took two (per-CTA timelines, profiles/).
+__host__ __device__ inline bool lists_in_smem(int R) { return R * NPOSE * 4 <= WS_MIN_BYTES; }
+__host__ __device__ inline int ws_bytes_for(int R) { (void)R; return WS_MIN_BYTES; }
 
 struct CandSmem {
     uint32_t slots[CAND_THREADS * ROWS_WORDS];            // level images of this round in padded row form (one per thread)
@@ -801,9 +806,9 @@ struct CandSmem {
     int32_t pre[ENVS_PER_CTA * MAX_ROT + 1];              // prefix of level counts over (bin, rotation)
     int32_t cand_off[CAND_THREADS + 1];                   // prefix of start-candidate counts over the images, in cost order
     uint16_t slot_of[CAND_THREADS];                       // image slot at each position of the cost order
-    uint16_t order2[CAND_THREADS];                        // contour owner (thread) by decreasing contour length
-    uint16_t q_of[CAND_THREADS];                          // (bin, rotation) pair of a thread's contour
-    uint8_t n_of[CAND_THREADS];                           // points of a thread's contour (0: nothing to approximate)
+    uint16_t order2[CAND_THREADS * TASKS_PER_LANE];       // contour owner (task slot j * CAND_THREADS + thread) by decreasing contour length
+    uint16_t q_of[CAND_THREADS * TASKS_PER_LANE];         // (bin, rotation) pair of a task slot's contour
+    uint8_t n_of[CAND_THREADS * TASKS_PER_LANE];          // points of a task slot's contour (0: nothing to approximate)
     int32_t hist[64], hbase[64];
     uint16_t pair_of[CAND_THREADS];                       // (bin, rotation) pair of image t
     int32_t warp_tot[CAND_WARPS];
@@ -814,8 +819,10 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CandSmem& S = *reinterpret_cast<CandSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int env0 = P.env_lo + blockIdx.x * ENVS_PER_CTA;
-    const int nenv = min(ENVS_PER_CTA, P.env_hi - env0);
+    // bins of this CTA: P.epc <= ENVS_PER_CTA, chosen per configuration so that a CTA's level images fit one round
+    // of CAND_THREADS (about 5-6 images per rotation and bin: 4 bins at R <= 4, 2 at R = 8, 1 beyond)
+    const int env0 = P.env_lo + blockIdx.x * P.epc;
+    const int nenv = min(P.epc, P.env_hi - env0);
     asm volatile("griddepcontrol.wait;" ::: "memory");      // PDL: scan grid complete, its scratch writes visible
     const int R = P.R;
     const int npairs = nenv * R;
@@ -979,40 +986,56 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
         if (P.phase_cycles && tid == 0) { atomicAdd(P.phase_cycles + 4, (unsigned long long)nround); atomicAdd(P.phase_cycles + 5, (unsigned long long)ntask); atomicAdd(P.phase_cycles + 6, 1ull); }
 #endif
 
-        // 2. one (image, start pixel) micro-task per lane
-        for (int mb = 0; mb < ntask; mb += CAND_THREADS) {
-            const int m = mb + tid;
-            const bool has = m < ntask;
-            int slot = 0, x = 0, y = 0;
-            if (has && m < TASK_TAB) {
-                const int tk = S.task_tab[m];
-                slot = tk >> 8; x = (tk >> 4) & 15; y = tk & 15;
-            } else if (has) {                               // beyond the table: search the prefix and the image
-                int lo = 0, hi = CAND_THREADS;              // cand_off[lo] <= m < cand_off[hi]
-                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (S.cand_off[mid] <= m) lo = mid; else hi = mid; }
-                slot = S.slot_of[lo];
-                int k = m - S.cand_off[lo];
-                const uint32_t* ri = S.slots + slot * ROWS_WORDS;
-                for (y = 0; y < 16; ++y) {
-                    const uint32_t c = start_candidates_rows(ri, y);
-                    const int pc = __popc(c);
-                    if (k < pc) { x = (int)__fns(c, 0u, k + 1); break; }
-                    k -= pc;
+        // 2. micro-tasks: one (image, start pixel) pair each, TASKS_PER_LANE per lane and batch.  The tasks are in cost
+        //    order, so task slot 0 of the lanes holds the 128 most expensive ones (64-point scratch), slots 1 and 2 the
+        //    cheap rest (32-point scratch): one follow / sort / approximate cycle with its five block barriers serves
+        //    up to 384 tasks -- a 4-bin CTA of the bench workload has ~170 (profiles/: per-CTA timelines showed the
+        //    second and third cycle of the one-task-per-lane form costing 7.5 us of a 43 us CTA, 30 us in the worst)
+        constexpr int TPL = TASKS_PER_LANE;
+        constexpr int BATCH = CAND_THREADS * TPL;
+        static_assert(FAST_CAP * 32 + (TPL - 1) * 32 * 32 <= WS_MIN_BYTES, "the task slots' point buffers share the warp scratch");
+        auto slot_scratch = [&](int owner) {               // point buffer of task slot `owner` (j * CAND_THREADS + thread)
+            const int jj = owner / CAND_THREADS, th = owner - jj * CAND_THREADS;
+            return ws_base + (size_t)(th >> 5) * P.ws_bytes + (jj == 0 ? 0 : FAST_CAP * 32 + (jj - 1) * 32 * 32) + (th & 31);
+        };
+        for (int mb = 0; mb < ntask; mb += BATCH) {
+            int tk[TPL];                                    // slot << 8 | x << 4 | y of my tasks, -1: none
+            int npts_j[TPL];
+            uint32_t ovf_bits = 0;
+#pragma unroll
+            for (int jt = 0; jt < TPL; ++jt) {
+                const int m = mb + jt * CAND_THREADS + tid;
+                const bool has = m < ntask;
+                int slot = 0, x = 0, y = 0;
+                if (has && m < TASK_TAB) {
+                    const int t = S.task_tab[m];
+                    slot = t >> 8; x = (t >> 4) & 15; y = t & 15;
+                } else if (has) {                               // beyond the table: search the prefix and the image
+                    int lo = 0, hi = CAND_THREADS;              // cand_off[lo] <= m < cand_off[hi]
+                    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (S.cand_off[mid] <= m) lo = mid; else hi = mid; }
+                    slot = S.slot_of[lo];
+                    int k = m - S.cand_off[lo];
+                    const uint32_t* ri = S.slots + slot * ROWS_WORDS;
+                    for (y = 0; y < 16; ++y) {
+                        const uint32_t c = start_candidates_rows(ri, y);
+                        const int pc = __popc(c);
+                        if (k < pc) { x = (int)__fns(c, 0u, k + 1); break; }
+                        k -= pc;
+                    }
                 }
+                tk[jt] = has ? ((slot << 8) | (x << 4) | y) : -1;
+                // (a) the lane follows the border; the points stay in the task slot's scratch
+                int n = -2, area2 = 1;
+                if (has) {
+                    StridedScratch<32, FAST_CAP> sc;
+                    sc.b = slot_scratch(jt * CAND_THREADS + tid);
+                    sc.kept = 0;
+                    n = follow_outer_rows(sc, S.slots + slot * ROWS_WORDS, x, y, area2, jt == 0 ? FAST_CAP : 32);
+                }
+                const bool keep = has && n != -2 && area2 <= 0;        // a raster-first start of an outer border
+                if (keep && n < 0) ovf_bits |= 1u << jt;
+                npts_j[jt] = (keep && n > 0) ? n : 0;
             }
-            const uint32_t* rows = S.slots + slot * ROWS_WORDS;
-            const int q = S.pair_of[slot];
-            // (a) every lane follows its border; the points stay in the lane's scratch
-            int n = -2, area2 = 1;
-            {
-                StridedScratch<32, FAST_CAP> sc;
-                sc.b = W_pts + lane;
-                sc.kept = 0;
-                if (has) n = follow_outer_rows(sc, rows, x, y, area2);
-            }
-            const bool keep = has && n != -2 && area2 <= 0;        // a raster-first start of an outer border
-            const bool ovf_mine = keep && n < 0;
-            const int npts = (keep && n > 0) ? n : 0;
             // (b) the contours of the CTA are re-dealt in decreasing length, so that the approximation loops
             //     of a warp have similar trip counts and abandoned / hole paths drop out
             if (tid < 64) S.hist[tid] = 0;
@@ -1021,10 +1044,13 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
 #ifdef IRBPP_PROBE_FINE
             phase_mark(5);   // find start pixel + follow (incl. waiting for the slowest warp)
 #endif
-            const int bucket = 63 - min(63, npts);
-            const int boff = atomicAdd(&S.hist[bucket], 1);
-            S.n_of[tid] = (uint8_t)npts;
-            S.q_of[tid] = (uint16_t)q;
+            int boff[TPL];
+#pragma unroll
+            for (int jt = 0; jt < TPL; ++jt) {
+                boff[jt] = atomicAdd(&S.hist[63 - min(63, npts_j[jt])], 1);
+                S.n_of[jt * CAND_THREADS + tid] = (uint8_t)npts_j[jt];
+                S.q_of[jt * CAND_THREADS + tid] = (uint16_t)(tk[jt] >= 0 ? S.pair_of[tk[jt] >> 8] : 0);
+            }
             __syncthreads();
             if (warp == 0) {   // exclusive prefix over the 64 buckets
                 const int h0 = S.hist[lane], h1 = S.hist[32 + lane];
@@ -1039,18 +1065,21 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
                 S.hbase[32 + lane] = tot0 + i1 - h1;
             }
             __syncthreads();
-            S.order2[S.hbase[bucket] + boff] = (uint16_t)tid;
+#pragma unroll
+            for (int jt = 0; jt < TPL; ++jt)
+                S.order2[S.hbase[63 - min(63, npts_j[jt])] + boff[jt]] = (uint16_t)(jt * CAND_THREADS + tid);
             __syncthreads();
 #ifdef IRBPP_PROBE_FINE
             phase_mark(6);   // length sort
 #endif
-            // (c) lane i approximates the i-th longest contour (points live in its owner's scratch)
-            {
-                const int owner = S.order2[tid];
+            // (c) lane i approximates the contours of rank i, 128 + i, 256 + i (points live in their owners' scratch)
+#pragma unroll 1
+            for (int jt = 0; jt < TPL; ++jt) {
+                const int owner = S.order2[jt * CAND_THREADS + tid];
                 const int on = S.n_of[owner];
                 if (on > 0) {
                     StridedScratch<32, FAST_CAP> sc;
-                    sc.b = ws_base + (size_t)(owner >> 5) * P.ws_bytes + (owner & 31);
+                    sc.b = slot_scratch(owner);
                     sc.kept = 0;
                     uint32_t* cb = candbits + (int)S.q_of[owner] * 8;
                     approx_and_emit(sc, on, P.legacy != 0,
@@ -1058,28 +1087,32 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
                 }
             }
             __syncthreads();           // scratch of every lane is free again
-            if (base == 0 && mb == 0) { trace(4); int mx = 0; for (int i = 0; i < CAND_THREADS; ++i) mx = max(mx, (int)S.n_of[i]); trace(7, ((unsigned long long)ntask << 8) | (unsigned long long)mx); }
+            if (base == 0 && mb == 0) { trace(4); int mx = 0; for (int i = 0; i < BATCH; ++i) mx = max(mx, (int)S.n_of[i]); trace(7, ((unsigned long long)ntask << 8) | (unsigned long long)mx); }
 #ifdef IRBPP_PROBE_FINE
             phase_mark(7);   // approxPolyDP + emit
 #endif
-            // rare: a contour longer than FAST_CAP points; the lanes concerned redo it one at a time with
-            // 1024-point buffers laid over the (now idle) lane scratch of this warp
-            uint32_t ovf = __ballot_sync(0xffffffffu, ovf_mine);
-            while (ovf) {
-                const int src_lane = __ffs((int)ovf) - 1;
-                ovf &= ovf - 1;
-                if (lane == src_lane) {
+            // rare: a contour longer than its slot's buffer; the lanes concerned redo it one at a time with
+            // 1024-point buffers laid over the (now idle) scratch of this warp
+#pragma unroll 1
+            for (int jt = 0; jt < TPL; ++jt) {
+                uint32_t ovf = __ballot_sync(0xffffffffu, (ovf_bits >> jt) & 1u);
+                while (ovf) {
+                    const int src_lane = __ffs((int)ovf) - 1;
+                    ovf &= ovf - 1;
+                    if (lane == src_lane) {
 #ifndef IRBPP_PROBE_FINE
-                    if (P.phase_cycles) atomicAdd(P.phase_cycles + 7, 1ull);     // overflow redo counter
+                        if (P.phase_cycles) atomicAdd(P.phase_cycles + 7, 1ull);     // overflow redo counter
 #endif
-                    FlatScratch<BIG_CAP> bs;
-                    bs.b = W_pts;
-                    uint32_t* cb = candbits + q * 8;
-                    if (!process_start_candidate(bs, rows, x, y, P.legacy != 0,
-                            [&](int ex, int ey) { const int b = ex * 16 + ey; atomicOr(cb + (b >> 5), 1u << (b & 31)); }))
-                        atomicMax(&S.error[q / R], 6);
+                        FlatScratch<BIG_CAP> bs;
+                        bs.b = W_pts;
+                        const int slot = tk[jt] >> 8, q = S.pair_of[slot];
+                        uint32_t* cb = candbits + q * 8;
+                        if (!process_start_candidate(bs, S.slots + slot * ROWS_WORDS, (tk[jt] >> 4) & 15, tk[jt] & 15, P.legacy != 0,
+                                [&](int ex, int ey) { const int b = ex * 16 + ey; atomicOr(cb + (b >> 5), 1u << (b & 31)); }))
+                            atomicMax(&S.error[q / R], 6);
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
             }
             __syncthreads();
         }
@@ -1157,8 +1190,9 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
         // rows in rotation order, then (col, row) ascending == bit order of the per-rotation sets.
         // Pass 1 compacts the set bits into a list (no memory loads); pass 2 gives every lane one
         // candidate, so the height gathers of 32 candidates are in flight together.
-        uint16_t* list = reinterpret_cast<uint16_t*>(W_pts);          // lane scratch is idle now
-        const int LIST_CAP = P.ws_bytes / 4;                          // list + bucket-sorted index list; >= R * 256 >= Ktot
+        // candidate list + bucket-sorted index list: the (now idle) lane scratch, or the bin's slice of the global scratch
+        const int LIST_CAP = R * NPOSE;                               // >= Ktot
+        uint16_t* list = P.dlist ? P.dlist + (int64_t)env * 2 * LIST_CAP : reinterpret_cast<uint16_t*>(W_pts);
         auto cell_of = [](int e) { const int b = e & 255; return (e >> 8) * NPOSE + (b & 15) * 16 + (b >> 4); };
         {
             for (int r = 0; r < R; ++r) {

@@ -53,11 +53,12 @@ class EpisodeStats(object):
 
     def update(self, done, infos):
         idx, ep_r, ratio, counter, valid = infos.finished()
-        for i in range(len(idx)):                      # finished episodes of this step only (in bin order, as the reference)
-            if valid[i]:
-                self.episode_rewards.append(float(ep_r[i]))
-                self.episode_ratio.append(float(ratio[i]))
-                self.episode_counter.append(int(counter[i]))
+        if len(idx):                                   # finished episodes of this step only (in bin order, as the reference)
+            keep = valid.astype(bool)
+            tail = slice(-self.episode_rewards.maxlen, None)      # only the last maxlen can survive in the deques
+            self.episode_rewards.extend(ep_r[keep][tail].tolist())
+            self.episode_ratio.extend(ratio[keep][tail].tolist())
+            self.episode_counter.extend(counter[keep][tail].tolist())
         self.episodes += int(len(idx))
         return infos.valid_array()
 
@@ -81,6 +82,22 @@ class ReplayBank(object):
 
     def __len__(self):
         return min(self.t, self.cap)
+
+    def append_from_env(self, env, state, action, reward_clip=0.0):
+        """The same append with the step's reward / done / valid taken from the environment's DEVICE result arrays
+        (``GpuVecEnv.last_step_device``): no host round trip, five device-to-device copies."""
+        torch = self._torch
+        dv = env.last_step_device()
+        s = self.t % self.cap
+        self.states[s].copy_(state)
+        self.actions[s].copy_(action.reshape(-1))
+        if reward_clip > 0:
+            torch.clamp(dv["reward"], -reward_clip, reward_clip, out=self.rewards[s])       # trainer.py:180-181
+        else:
+            self.rewards[s].copy_(dv["reward"])
+        torch.eq(dv["done"], 0, out=self.nonterminal[s])
+        torch.ne(dv["valid"], 0, out=self.valid[s])
+        self.t += 1
 
     def append_batch(self, state, action, reward, done, valid=None):
         """``self.mem[i].append(state[i], action[i], reward[i], done[i])`` for every i (``trainer.py:183-185``) as

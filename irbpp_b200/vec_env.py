@@ -357,8 +357,6 @@ class GpuVecEnv(VecEnv):
         self._check(self._lib.irbpp_step_async(self._h, ptr, 1, obs.data_ptr(), self._stream()))
         res = self._result
         self._check(self._lib.irbpp_step_wait_device(self._h, ctypes.byref(res)))
-        if getattr(self, "_dev_ptrs", None) is None:
-            self._dev_ptrs = {k: getattr(res, k) for k, _ in self._RESULT_BYTES}
         return obs, res
 
     def last_step_device(self):
@@ -366,13 +364,11 @@ class GpuVecEnv(VecEnv):
         ``counter`` int32 [N], ``ratio`` float64 [N] -- as torch tensors aliasing the library's buffers (valid until
         the next step on this handle): what a device-resident replay bank appends without any host round trip."""
         torch = self._torch
-        res = _lib.IrbppStepResult()
-        lib = self._lib
-        # the device pointers are fixed for the life of the handle; irbpp_step_wait_device only reports them when a
-        # step is pending, so they are cached from the first device-resident query
         ptrs = getattr(self, "_dev_ptrs", None)
-        if ptrs is None:
-            raise RuntimeError("no device result views yet: call step_device() once, or step() after enable_device_results()")
+        if ptrs is None:                              # fixed for the life of the handle
+            res = _lib.IrbppStepResult()
+            self._check(self._lib.irbpp_device_results(self._h, ctypes.byref(res)))
+            ptrs = self._dev_ptrs = {k: getattr(res, k) for k, _ in self._RESULT_BYTES}
         n = self.num_envs
 
         class _View(object):

@@ -300,7 +300,14 @@ def test_actor_loop_through_learner_glue_at_4096_bins():
             k = int(np.nonzero(idx == j)[0][0])
             assert info["episode"]["r"] == ep_r[k] and info["ratio"] == ratio[k] and info["counter"] == counter[k]
         total_done += len(idx)
-        bank.append_batch(state, action, reward, done, valid)
+        dv = env.last_step_device()                          # device copies of the step's results == what step() returned
+        assert np.array_equal(dv["reward"].cpu().numpy(), reward.numpy()[:, 0]) and np.array_equal(dv["done"].cpu().numpy() != 0, done)
+        if T % 2:
+            bank.append_batch(state, action, reward, done, valid)
+        else:
+            bank.append_from_env(env, state, action)        # the same transition without the host round trip
+            slot = (bank.t - 1) % bank.cap
+            assert torch.equal(bank.rewards[slot].cpu(), reward[:, 0]) and np.array_equal(bank.nonterminal[slot].cpu().numpy(), ~done)
         if T % 4 == 0:
             envs, slots, s, a, r, s2, nonterm = bank.sample(64, generator=gen)
             assert s.shape == (64, env.obs_len) and s2.shape == s.shape and a.shape == (64,)

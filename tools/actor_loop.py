@@ -67,9 +67,8 @@ def main():
         mask = glue.get_mask_from_state(state, SEL)
         action = agent.act(state, mask)
         next_state, reward, done, infos = env.step(action.cpu().numpy())
-        valid = stats.update(done, infos)
-        reward = torch.maximum(torch.minimum(reward, reward_clip), -reward_clip)
-        bank.append_batch(state, action, reward, done, valid)
+        stats.update(done, infos)
+        bank.append_from_env(env, state, action, reward_clip=10.0)       # reward clip + append on the device
         if T % a.replay_frequency == 0 and len(bank) >= 2:
             batch = bank.sample(a.batch_size)
         state = next_state

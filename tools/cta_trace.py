@@ -30,7 +30,8 @@ for rep in range(3):
     obs, _ = env.step_device(acts)
     torch.cuda.synchronize()
     env.debug_phase_cycles(False)                    # dumps the trace
-    tr = np.fromfile(path, dtype=np.uint64)[8:].reshape(-1, 8)[:n // 4].astype(np.int64)
+    tr = np.fromfile(path, dtype=np.uint64)[8:].reshape(-1, 8).astype(np.int64)
+    tr = tr[tr[:, 6] > 0]                            # the CTAs that ran (the grid depends on the bins per CTA)
     t0 = tr[:, 0].min()
     rel = (tr[:, :7] - t0) / 1e3                     # microseconds since the first CTA started
     dur = rel[:, 6] - rel[:, 0]

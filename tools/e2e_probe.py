@@ -21,7 +21,8 @@ def main():
     steps = int(sys.argv[1]) if len(sys.argv) > 1 else 300
     dev = torch.device("cuda:0")
     lib = shapes.make_blockout_library(32, seed=1)
-    seqs = shapes.make_sequences(bench.N_ENVS, 128, lib.num_shapes, seed=0)
+    N_ENVS = 4096
+    seqs = shapes.make_sequences(N_ENVS, 128, lib.num_shapes, seed=0)
     env = GpuVecEnv(lib, seqs, device="cuda:0")
     gen = torch.Generator(device=dev); gen.manual_seed(1)
     obs = env.reset()
@@ -61,8 +62,8 @@ def main():
         if k >= 5:
             acc += [t1 - t0, t2 - t1, t3 - t2, t3b - t3, t4 - t3b, t5 - t4, t5 - t0]
     # alternative host path: actions through an explicit pinned H2D copy, results through one D2H copy
-    pin = torch.empty(bench.N_ENVS, dtype=torch.int64).pin_memory()
-    a_dev = torch.empty(bench.N_ENVS, dtype=torch.int64, device=dev)
+    pin = torch.empty(N_ENVS, dtype=torch.int64).pin_memory()
+    a_dev = torch.empty(N_ENVS, dtype=torch.int64, device=dev)
     pin_np = pin.numpy()
     staged = np.zeros(3)
     for k in range(steps + 5):
