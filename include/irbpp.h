@@ -51,8 +51,8 @@ typedef struct irbpp_config {
     int32_t approx_legacy;     /* 0: approxPolyDP as cv2 4.13 (segment distance); 1: legacy line distance */
 } irbpp_config;
 
-/* Host views of the per-env results of the last step (library-owned pinned memory, valid until the
- * next irbpp_step_async on the handle).  Replaces the (rews, dones, infos) tuple of
+/* Host views of the per-env results of the last step (library-owned pinned memory; two blocks alternate, so the
+ * views stay valid until the SECOND next irbpp_step_async on the handle).  Replaces the (rews, dones, infos) tuple of
  * ShmemVecEnv.step_wait (wrapper/shmem_vec_env.py:76-81) and the Monitor episode info
  * (wrapper/monitor.py:58-75). */
 typedef struct irbpp_step_result {

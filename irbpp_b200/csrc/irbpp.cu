@@ -39,7 +39,11 @@ struct irbpp_env {
     // device allocations
     std::vector<void*> dev_allocs;
     void* results_dev = nullptr;   // one block: ratio | ep_reward | reward | counter | ep_len | done | valid | error
-    void* results_host = nullptr;  // pinned mirror
+    void* results_host = nullptr;  // pinned mirror of the CURRENT step (one of results_host2[]: the blocks alternate, so the
+                                   // views of step k stay valid until step k + 2 is launched)
+    void* results_host2[2] = {nullptr, nullptr};
+    char* results_mapped2[2] = {nullptr, nullptr};
+    int res_turn = 0;
     size_t results_bytes = 0;
     int64_t* actions_dev = nullptr;
     int64_t* actions_pinned = nullptr;      // [2][N] mapped pinned: step actions, order actions (read zero-copy)
@@ -162,7 +166,9 @@ int irbpp_create(const irbpp_config* cfg, irbpp_handle* out) {
     P.resZ = cfg->resolution_z;
     P.resA = cfg->resolution_act;
     P.binvol = (cfg->bin_dimension[0] * cfg->bin_dimension[1]) * cfg->bin_dimension[2];   // np.prod
-    P.ws_bytes = ws_bytes_for(P.R);
+    bool lists_global = !lists_in_smem(P.R);
+    if (const char* m = getenv("IRBPP_LISTS")) lists_global = !lists_in_smem(P.R) && strcmp(m, "smem") != 0;     // experiment knob
+    P.ws_bytes = ws_bytes_for(P.R, lists_global);
     {   // bins per candidates CTA: one round of CAND_THREADS level images should hold them (~6 images per rotation and bin)
         int epc = CAND_THREADS / (6 * P.R);
         P.epc = epc < 1 ? 1 : (epc > ENVS_PER_CTA ? ENVS_PER_CTA : epc);
@@ -185,14 +191,17 @@ int irbpp_create(const irbpp_config* cfg, irbpp_handle* out) {
     TRY_ALLOC(dev_alloc(h, &P.maskbits, units * P.R * 8));
     TRY_ALLOC(dev_alloc(h, &P.bitmaps, units * P.R * MAX_LEVELS * 8));
     TRY_ALLOC(dev_alloc(h, &P.nlevels, units * P.R));
-    if (!lists_in_smem(P.R)) TRY_ALLOC(dev_alloc(h, &P.dlist, units * 2 * P.R * NPOSE));
+    if (lists_global) TRY_ALLOC(dev_alloc(h, &P.dlist, units * 2 * P.R * NPOSE));
     // result block (8-byte fields first so every array stays aligned)
     h->results_bytes = (size_t)N * (8 + 8 + 4 + 4 + 4 + 1 + 1 + 1);
     TRY_ALLOC(cudaMalloc(&h->results_dev, h->results_bytes + 64));
     TRY_ALLOC(cudaMemset(h->results_dev, 0, h->results_bytes + 64));
-    TRY_ALLOC(cudaHostAlloc(&h->results_host, h->results_bytes + 64, cudaHostAllocMapped));
-    TRY_ALLOC(cudaHostGetDevicePointer((void**)&h->results_mapped, h->results_host, 0));
-    memset(h->results_host, 0, h->results_bytes + 64);
+    for (int t = 0; t < 2; ++t) {
+        TRY_ALLOC(cudaHostAlloc(&h->results_host2[t], h->results_bytes + 64, cudaHostAllocMapped));
+        TRY_ALLOC(cudaHostGetDevicePointer((void**)&h->results_mapped2[t], h->results_host2[t], 0));
+        memset(h->results_host2[t], 0, h->results_bytes + 64);
+    }
+    h->results_host = h->results_host2[0]; h->results_mapped = h->results_mapped2[0];
     TRY_ALLOC(cudaHostAlloc((void**)&h->actions_pinned, 2 * (size_t)N * sizeof(int64_t), cudaHostAllocMapped));
     TRY_ALLOC(cudaHostGetDevicePointer((void**)&h->actions_mapped, h->actions_pinned, 0));
     {
@@ -218,7 +227,7 @@ int irbpp_destroy(irbpp_handle h) {
     cudaDeviceSynchronize();
     for (void* p : h->dev_allocs) cudaFree(p);
     if (h->results_dev) cudaFree(h->results_dev);
-    if (h->results_host) cudaFreeHost(h->results_host);
+    for (int t = 0; t < 2; ++t) if (h->results_host2[t]) cudaFreeHost(h->results_host2[t]);
     if (h->actions_pinned) cudaFreeHost(h->actions_pinned);
     delete h;
     return IRBPP_OK;
@@ -491,6 +500,8 @@ static int step_async_impl(irbpp_env* h, const int64_t* actions, int32_t on_devi
             CUDA_TRY(h, cudaMemcpyAsync(h->actions_dev, h->actions_pinned, (size_t)P.N * sizeof(int64_t), cudaMemcpyHostToDevice, s));
             P.actions = h->actions_dev;
         }
+        h->res_turn ^= 1;                                   // this step's host block (the previous step's stays readable)
+        h->results_host = h->results_host2[h->res_turn]; h->results_mapped = h->results_mapped2[h->res_turn];
         char* b = h->results_mapped;
         const size_t N = P.N;
         if (h->host_results_mode == 0) {

@@ -57,7 +57,10 @@ constexpr int CAND_WARPS = IRBPP_CAND_WARPS;          // warps per CTA of the ca
 constexpr int CAND_THREADS = 32 * CAND_WARPS;
 static_assert(CAND_WARPS >= ENVS_PER_CTA, "phase D needs one warp per bin");
 constexpr int MAX_LEVELS = 64;           // level-image slots per (bin, rotation) in the scratch
-constexpr int TASKS_PER_LANE = 3;        // micro-tasks a lane takes per batch of the candidates kernel (one follow / sort / approximate cycle)
+#ifndef IRBPP_TASKS_PER_LANE
+#define IRBPP_TASKS_PER_LANE 3
+#endif
+constexpr int TASKS_PER_LANE = IRBPP_TASKS_PER_LANE;        // micro-tasks a lane takes per batch of the candidates kernel (one follow / sort / approximate cycle)
 constexpr int TASK_TAB = 384;            // start pixels of a round listed explicitly (the rest are found by search)
 constexpr int FAST_CAP = 64;             // contour points on the fast path (32 was measured slower: every overflow redo stalls a warp)
 constexpr int BIG_CAP = 1024;            // contour points on the overflow path
@@ -798,7 +801,10 @@ static_assert(CAND_THREADS * ROWS_WORDS >= ENVS_PER_CTA * 128, "phase D's rank h
 // the CTA's shared memory: at R = 8 the 8 KB per warp cut the residency to 4 CTAs per SM, the grid no longer fitted
 // in one wave and the kernel took two (per-CTA timelines, profiles/).
 __host__ __device__ inline bool lists_in_smem(int R) { return R * NPOSE * 4 <= WS_MIN_BYTES; }
-__host__ __device__ inline int ws_bytes_for(int R) { (void)R; return WS_MIN_BYTES; }
+__host__ __device__ inline int ws_bytes_for(int R, bool lists_global) {
+    const int need = lists_global ? 0 : R * NPOSE * 4;
+    return ((need > WS_MIN_BYTES ? need : WS_MIN_BYTES) + 15) & ~15;
+}
 
 struct CandSmem {
     uint32_t slots[CAND_THREADS * ROWS_WORDS];            // level images of this round in padded row form (one per thread)

@@ -16,6 +16,7 @@ launch (see ``csrc/irbpp_kernels.cuh``).  PyTorch is used for device memory and 
 """
 import ctypes
 import time
+import weakref
 from abc import ABC, abstractmethod
 from collections.abc import Sequence
 
@@ -112,9 +113,18 @@ class LazyInfos(Sequence):
     _FIELDS = (("valid", np.bool_), ("counter", np.int32), ("ratio", np.float64),
                ("ep_reward", np.float64), ("ep_len", np.int32))
 
-    def __init__(self, n, block, offsets, done, t_rel):
+    def __init__(self, n, block, offsets, done, t_rel, borrowed=False):
         self._n, self._block, self._offsets, self._done, self._t = n, block, offsets, done, t_rel
         self._v = None
+        self._borrowed = borrowed        # `block` is the library's pinned buffer: copied (detach) before it is reused
+
+    def detach(self):
+        """Take a private copy of the result block (called by the environment before the library reuses the
+        buffer, if this object is still alive by then)."""
+        if self._borrowed:
+            self._block = self._block.copy()
+            self._v = None
+            self._borrowed = False
 
     def _views(self):
         if self._v is None:
@@ -229,6 +239,7 @@ class GpuVecEnv(VecEnv):
         act_space = Discrete(buffer_size if buffer_size > 1 else selected_action)     # binPhy.py:81-85,102
         VecEnv.__init__(self, num_envs, obs_space, act_space)
         self.waiting_step = False
+        self._live_infos = []
         self._obs_pending = None
         self._spare_obs = None
         self._spare_stream = None
@@ -300,6 +311,7 @@ class GpuVecEnv(VecEnv):
             raise AlreadySteppingError()
         keep, ptr, on_dev = self._actions_arg(actions, "actions")
         obs = self._take_obs()
+        self._release_result_block()
         self._check(self._lib.irbpp_step_async(self._h, ptr, on_dev, obs.data_ptr(), self._stream()))
         self._obs_pending = (obs, keep)
         self.waiting_step = True
@@ -321,29 +333,40 @@ class GpuVecEnv(VecEnv):
         self._check(self._lib.irbpp_step_wait(self._h, ctypes.byref(res)))
         src, offs = self._result_block(res)
         n = self.num_envs
-        block = src.copy()                        # one copy of the pinned block; everything else is a view of it
-        reward = block[offs["reward"]:offs["reward"] + 4 * n].view(np.float32)
-        done = block[offs["done"]:offs["done"] + n].view(np.bool_)
-        infos = LazyInfos(n, block, offs, done, t_rel)
+        # reward and done are returned as arrays of their own (24 KB); everything else stays in the library's pinned
+        # block, which is not reused before the second next step: the infos of a step are normally consumed and dropped
+        # by then (trainer.py:167-178) -- if one is still alive when its block comes up for reuse it takes a copy first
+        reward = src[offs["reward"]:offs["reward"] + 4 * n].view(np.float32).copy()
+        done = src[offs["done"]:offs["done"] + n].view(np.bool_).copy()
+        infos = LazyInfos(n, src, offs, done, t_rel, borrowed=True)
+        self._live_infos = (self._live_infos + [weakref.ref(infos)])[-2:]
         return obs, torch.from_numpy(reward).unsqueeze(dim=1), done, infos
+
+    def _release_result_block(self):
+        """The step about to be launched writes into the pinned block the second-last step used: an infos object
+        of that step that is still referenced somewhere takes its private copy now."""
+        if len(self._live_infos) == 2:
+            old = self._live_infos[0]()
+            if old is not None:
+                old.detach()
 
     _RESULT_BYTES = (("ratio", 8), ("ep_reward", 8), ("reward", 4), ("counter", 4), ("ep_len", 4),
                      ("done", 1), ("valid", 1), ("error", 1))
 
     def _result_block(self, res):
         """uint8 view of the library's pinned result block and the byte offset of every array in it (from
-        the pointers of ``irbpp_step_result``; fixed for the life of the handle, so built once)."""
+        the pointers of ``irbpp_step_result``; two blocks per handle, each view built once)."""
         key = (res.reward, res.done)
-        if getattr(self, "_block_key", None) != key:
+        cache = self.__dict__.setdefault("_block_cache", {})      # the library alternates between two blocks
+        hit = cache.get(key)
+        if hit is None:
             n = self.num_envs
             ptrs = {k: getattr(res, k) for k, _ in self._RESULT_BYTES}
             base = min(ptrs.values())
             end = max(ptrs[k] + n * sz for k, sz in self._RESULT_BYTES)
             buf = (ctypes.c_uint8 * (end - base)).from_address(base)
-            self._block_src = np.frombuffer(buf, dtype=np.uint8)
-            self._block_offs = {k: ptrs[k] - base for k, _ in self._RESULT_BYTES}
-            self._block_key = key
-        return self._block_src, self._block_offs
+            hit = cache[key] = (np.frombuffer(buf, dtype=np.uint8), {k: ptrs[k] - base for k, _ in self._RESULT_BYTES})
+        return hit
 
     def step_device(self, actions):
         """Device-resident loop: ``actions`` is a CUDA int64 tensor; nothing is copied to the host and
@@ -451,6 +474,7 @@ class GpuVecEnv(VecEnv):
             poses = np.ascontiguousarray(poses, dtype=np.int64)
         keep, ptr, on_dev = self._actions_arg(poses, "poses")
         obs = self._take_obs()
+        self._release_result_block()
         self._check(self._lib.irbpp_step_poses_async(self._h, ptr, on_dev, obs.data_ptr(), self._stream()))
         self._obs_pending = (obs, keep)
         self.waiting_step = True

@@ -37,11 +37,14 @@ def test_result_block_views_and_lazy_infos(n):
     env.num_envs = n
     src, got_offs = env._result_block(res)
     assert got_offs == offs and src.ctypes.data == buf.ctypes.data
-    assert env._result_block(res)[0] is src                       # built once per handle
+    assert env._result_block(res)[0] is src                       # built once per block
     block = src.copy()
     done = block[offs["done"]:offs["done"] + n].view(np.bool_)
     infos = LazyInfos(n, block, offs, done, 1.5)
+    borrowed = LazyInfos(n, src, offs, done.copy(), 1.5, borrowed=True)   # as step_wait builds it: a view of the pinned block ...
+    borrowed.detach()                                                     # ... copied before the library reuses the block
     buf[:] = 0                                                    # the step's copy is private
+    assert borrowed[n - 1] == infos[n - 1] and borrowed.finished()[1].tolist() == infos.finished()[1].tolist()
     assert len(infos) == n
     assert infos[0] == {"Valid": True}
     if n > 1:

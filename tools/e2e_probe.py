@@ -30,7 +30,7 @@ def main():
         obs, _ = env.step_device(bench.device_policy(torch, obs, gen))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     names = ["actions_arg", "take_obs + stream", "step_async (memcpy + 2 launches)", "spare obs alloc (overlapped)",
-             "step_wait (sync + error scan)", "result block copy + views", "total"]
+             "step_wait (sync + error scan)", "reward / done copies + views", "total"]
     acc = np.zeros(len(names))
     n = env.num_envs
     for k in range(steps + 5):
@@ -52,10 +52,9 @@ def main():
         env._check(env._lib.irbpp_step_wait(env._h, ctypes.byref(res)))
         t4 = time.perf_counter()
         src, offs = env._result_block(res)
-        block = src.copy()
-        reward = block[offs["reward"]:offs["reward"] + 4 * n].view(np.float32)
-        done = block[offs["done"]:offs["done"] + n].view(np.bool_)
-        infos = LazyInfos(n, block, offs, done, t_rel)
+        reward = src[offs["reward"]:offs["reward"] + 4 * n].view(np.float32).copy()
+        done = src[offs["done"]:offs["done"] + n].view(np.bool_).copy()
+        infos = LazyInfos(n, src, offs, done, t_rel, borrowed=True)
         rew = torch.from_numpy(reward).unsqueeze(dim=1)
         t5 = time.perf_counter()
         obs = o
