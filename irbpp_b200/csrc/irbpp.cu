@@ -166,14 +166,7 @@ int irbpp_create(const irbpp_config* cfg, irbpp_handle* out) {
     P.resZ = cfg->resolution_z;
     P.resA = cfg->resolution_act;
     P.binvol = (cfg->bin_dimension[0] * cfg->bin_dimension[1]) * cfg->bin_dimension[2];   // np.prod
-    bool lists_global = !lists_in_smem(P.R);
-    if (const char* m = getenv("IRBPP_LISTS")) lists_global = !lists_in_smem(P.R) && strcmp(m, "smem") != 0;     // experiment knob
-    P.ws_bytes = ws_bytes_for(P.R, lists_global);
-    {   // bins per candidates CTA: one round of CAND_THREADS level images should hold them (~6 images per rotation and bin)
-        int epc = CAND_THREADS / (6 * P.R);
-        P.epc = epc < 1 ? 1 : (epc > ENVS_PER_CTA ? ENVS_PER_CTA : epc);
-        if (const char* m = getenv("IRBPP_BINS_PER_CTA")) { const int v = atoi(m); if (v >= 1 && v <= ENVS_PER_CTA) P.epc = v; }
-    }
+    P.ws_bytes = ws_bytes_for(P.R);
     h->cand_smem = (int)((sizeof(CandSmem) + 15) & ~(size_t)15) + CAND_WARPS * P.ws_bytes + ENVS_PER_CTA * P.R * 8 * 4;
 
 #define TRY_ALLOC(expr)                                                                          \
@@ -191,7 +184,6 @@ int irbpp_create(const irbpp_config* cfg, irbpp_handle* out) {
     TRY_ALLOC(dev_alloc(h, &P.maskbits, units * P.R * 8));
     TRY_ALLOC(dev_alloc(h, &P.bitmaps, units * P.R * MAX_LEVELS * 8));
     TRY_ALLOC(dev_alloc(h, &P.nlevels, units * P.R));
-    if (lists_global) TRY_ALLOC(dev_alloc(h, &P.dlist, units * 2 * P.R * NPOSE));
     // result block (8-byte fields first so every array stays aligned)
     h->results_bytes = (size_t)N * (8 + 8 + 4 + 4 + 4 + 1 + 1 + 1);
     TRY_ALLOC(cudaMalloc(&h->results_dev, h->results_bytes + 64));
@@ -437,7 +429,7 @@ static int launch(irbpp_env* h, Params& P, cudaStream_t s) {
         // programmatic dependent launch: the candidates grid is scheduled while the scan grid's last
         // wave drains and waits at griddepcontrol.wait for the scan's completion
         cudaLaunchConfig_t lc = {};
-        lc.gridDim = dim3((units + P.epc - 1) / P.epc); lc.blockDim = dim3(CAND_THREADS);
+        lc.gridDim = dim3((units + ENVS_PER_CTA - 1) / ENVS_PER_CTA); lc.blockDim = dim3(CAND_THREADS);
         lc.dynamicSmemBytes = (size_t)h->cand_smem; lc.stream = s;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;

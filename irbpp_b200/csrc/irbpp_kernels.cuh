@@ -154,8 +154,6 @@ struct Params {
     const uint8_t* which;                // MODE_RESET (NULL = all)
     const int32_t* dbg_items;            // MODE_DEBUG_SCAN
     int32_t ws_bytes;                    // per-warp scratch of the candidates kernel (ws_bytes_for(R))
-    int32_t epc;                         // bins per CTA of the candidates kernel (1 .. ENVS_PER_CTA)
-    uint16_t* dlist;                     // [units][2][R*256] phase D lists when they do not fit the warp scratch (R > 4), else NULL
     int32_t pose_actions;                // MODE_STEP: actions are flat poses (rot*256 + lx*16 + ly), not candidate rows
     int32_t heur_method, heur_dir;       // heuristic kernel: Heuristic, dirIdx 0..3 (space.py:162-166)
     int32_t* heur_pose;                  // [N][3] rot, lx, ly
@@ -796,13 +794,10 @@ __global__ void __launch_bounds__(CTA_THREADS) irbpp_heuristic_kernel(const Para
 constexpr int WS_MIN_BYTES = 4096;
 static_assert(WS_MIN_BYTES >= 2 * BIG_CAP && WS_MIN_BYTES >= FAST_CAP * 32, "overflow buffers must fit the lane scratch");
 static_assert(CAND_THREADS * ROWS_WORDS >= ENVS_PER_CTA * 128, "phase D's rank histograms reuse the image slots");
-// Phase D's candidate list + bucket-sorted index list (2 x uint16 per pose of the bin) live in the warp scratch when
-// they fit (R <= 4); for more rotations they go to a global scratch (Params::dlist, L2 resident) instead of growing
-// the CTA's shared memory: at R = 8 the 8 KB per warp cut the residency to 4 CTAs per SM, the grid no longer fitted
-// in one wave and the kernel took two (per-CTA timelines, profiles/).
-__host__ __device__ inline bool lists_in_smem(int R) { return R * NPOSE * 4 <= WS_MIN_BYTES; }
-__host__ __device__ inline int ws_bytes_for(int R, bool lists_global) {
-    const int need = lists_global ? 0 : R * NPOSE * 4;
+// (Measured and dropped, profiles/README.md: keeping phase D's lists in a global scratch for R > 4 so that the grid
+// of an R = 8 run fits one wave, and fewer bins per CTA for many rotations -- both slower than this form.)
+__host__ __device__ inline int ws_bytes_for(int R) {
+    const int need = R * NPOSE * 4;                      // uint16 list + uint16 sorted list for every pose
     return ((need > WS_MIN_BYTES ? need : WS_MIN_BYTES) + 15) & ~15;
 }
 
@@ -825,10 +820,8 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
     extern __shared__ __align__(16) unsigned char smem_raw[];
     CandSmem& S = *reinterpret_cast<CandSmem*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // bins of this CTA: P.epc <= ENVS_PER_CTA, chosen per configuration so that a CTA's level images fit one round
-    // of CAND_THREADS (about 5-6 images per rotation and bin: 4 bins at R <= 4, 2 at R = 8, 1 beyond)
-    const int env0 = P.env_lo + blockIdx.x * P.epc;
-    const int nenv = min(P.epc, P.env_hi - env0);
+    const int env0 = P.env_lo + blockIdx.x * ENVS_PER_CTA;
+    const int nenv = min(ENVS_PER_CTA, P.env_hi - env0);
     asm volatile("griddepcontrol.wait;" ::: "memory");      // PDL: scan grid complete, its scratch writes visible
     const int R = P.R;
     const int npairs = nenv * R;
@@ -1196,9 +1189,8 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
         // rows in rotation order, then (col, row) ascending == bit order of the per-rotation sets.
         // Pass 1 compacts the set bits into a list (no memory loads); pass 2 gives every lane one
         // candidate, so the height gathers of 32 candidates are in flight together.
-        // candidate list + bucket-sorted index list: the (now idle) lane scratch, or the bin's slice of the global scratch
-        const int LIST_CAP = R * NPOSE;                               // >= Ktot
-        uint16_t* list = P.dlist ? P.dlist + (int64_t)env * 2 * LIST_CAP : reinterpret_cast<uint16_t*>(W_pts);
+        uint16_t* list = reinterpret_cast<uint16_t*>(W_pts);          // lane scratch is idle now
+        const int LIST_CAP = P.ws_bytes / 4;                          // list + bucket-sorted index list; >= R * 256 >= Ktot
         auto cell_of = [](int e) { const int b = e & 255; return (e >> 8) * NPOSE + (b & 15) * 16 + (b >> 4); };
         {
             for (int r = 0; r < R; ++r) {

@@ -387,20 +387,19 @@ class GpuVecEnv(VecEnv):
         ``counter`` int32 [N], ``ratio`` float64 [N] -- as torch tensors aliasing the library's buffers (valid until
         the next step on this handle): what a device-resident replay bank appends without any host round trip."""
         torch = self._torch
-        ptrs = getattr(self, "_dev_ptrs", None)
-        if ptrs is None:                              # fixed for the life of the handle
+        views = getattr(self, "_dev_views", None)
+        if views is None:                             # the device arrays are fixed for the life of the handle: built once
             res = _lib.IrbppStepResult()
             self._check(self._lib.irbpp_device_results(self._h, ctypes.byref(res)))
-            ptrs = self._dev_ptrs = {k: getattr(res, k) for k, _ in self._RESULT_BYTES}
-        n = self.num_envs
+            n = self.num_envs
 
-        class _View(object):
-            def __init__(self, ptr, shape, typestr):
-                self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (int(ptr), False), "version": 2}
-        spec = {"reward": ("<f4", torch.float32), "done": ("|u1", torch.uint8), "valid": ("|u1", torch.uint8),
-                "counter": ("<i4", torch.int32), "ratio": ("<f8", torch.float64), "ep_len": ("<i4", torch.int32),
-                "ep_reward": ("<f8", torch.float64)}
-        return {k: torch.as_tensor(_View(ptrs[k], (n,), ts), device=self.device) for k, (ts, _) in spec.items()}
+            class _View(object):
+                def __init__(self, ptr, shape, typestr):
+                    self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (int(ptr), False), "version": 2}
+            spec = {"reward": "<f4", "done": "|u1", "valid": "|u1", "counter": "<i4", "ratio": "<f8", "ep_len": "<i4", "ep_reward": "<f8"}
+            views = self._dev_views = {k: torch.as_tensor(_View(getattr(res, k), (n,), ts), device=self.device)
+                                       for k, ts in spec.items()}
+        return views
 
     def get_action_candidates(self, order_actions, as_tensor=False):
         """``envs.get_action_candidates(orderAction)`` (shmem_vec_env.py:99-102 -> binPhy.py:161-169).

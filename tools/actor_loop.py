@@ -62,19 +62,34 @@ def main():
     # ---- the loop through learner_glue (batched) ----
     bank = glue.ReplayBank(n, a.capacity, env.obs_len, dev)
     stats = glue.EpisodeStats()
+    parts = {"mask+act": 0.0, "env.step": 0.0, "episode stats": 0.0, "replay append": 0.0, "replay sample": 0.0}
+
+    def lap(name, t):
+        torch.cuda.synchronize()
+        now = time.perf_counter()
+        parts[name] += now - t
+        return now
     torch.cuda.synchronize(); t0 = time.perf_counter()
     for T in range(1, a.iters + 1):
+        t = time.perf_counter()
         mask = glue.get_mask_from_state(state, SEL)
         action = agent.act(state, mask)
-        next_state, reward, done, infos = env.step(action.cpu().numpy())
+        acts_host = action.cpu().numpy()
+        t = lap("mask+act", t)
+        next_state, reward, done, infos = env.step(acts_host)
+        t = lap("env.step", t)
         stats.update(done, infos)
+        t = lap("episode stats", t)
         bank.append_from_env(env, state, action, reward_clip=10.0)       # reward clip + append on the device
+        t = lap("replay append", t)
         if T % a.replay_frequency == 0 and len(bank) >= 2:
             batch = bank.sample(a.batch_size)
+            t = lap("replay sample", t)
         state = next_state
     torch.cuda.synchronize(); dt = time.perf_counter() - t0
     out["glue_loop"] = {"iters_per_s": a.iters / dt, "env_steps_per_s": n * a.iters / dt, "episodes": stats.episodes,
-                        "mean_ratio_last10": float(np.mean(stats.episode_ratio)) if stats.episode_ratio else None}
+                        "mean_ratio_last10": float(np.mean(stats.episode_ratio)) if stats.episode_ratio else None,
+                        "ms_per_iter_by_part": {k: round(1e3 * v / a.iters, 4) for k, v in parts.items()}}
 
     # ---- the loop as trainer.py:157-186 writes it (per-bin Python) ----
     if not a.skip_reference_style:

@@ -37,8 +37,7 @@ for _ in range(n):
     obs, _ = env.step_device(bench.device_policy(torch, obs, gen))
 c = env.debug_phase_cycles(False).astype(np.float64) / n
 scan_ctas = N_ENVS
-_epc = int(os.environ.get('IRBPP_BINS_PER_CTA', 0)) or max(1, min(4, 128 // (6 * lib.num_rotations)))
-cand_ctas = N_ENVS // _epc
+cand_ctas = N_ENVS // 4
 fine = "fine" in os.path.basename(os.environ.get("IRBPP_LIB", ""))
 out = {"lib": os.environ.get("IRBPP_LIB", "default"), "config": CONFIG,
        "scan_kernel_cycles_per_cta": {"load + apply action (phase A)": round(c[0] / scan_ctas),
