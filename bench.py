@@ -17,7 +17,7 @@ metric is quoted on):
 A "step" is one batched ``step()`` over all bins of a GPU.  For N > 1 the driver launches one rank per GPU
 with torch.distributed.run; bins are sharded by index (weak scaling), there is no collective inside a step,
 and ONE NCCL all-gather of the observations per rollout.  That gather is pipelined: the
-gather of the previous rollout's observations runs on a side stream while this rollout's steps execute; the
+gather of the previous rollout's observations is started with this rollout's first timed step and runs on a side stream beside the steps; the
 timed total counts every part of the gather's duration that did NOT run concurrently with a timed step
 interval (`gather_exposed_ms`), so gather time hidden behind L2 flushes or the stand-in policy is charged.
 
@@ -421,11 +421,12 @@ def main_gpu(args):
     barrier()
     t_wall0 = time.perf_counter()
     origin.record()
-    if world > 1:                                   # the previous rollout's observations go out while this rollout steps
-        gatherer.start(state["obs"])
+    prev_rollout_obs = state["obs"]
     for i in range(args.steps):
         choice = choose()
         flush.fill_(float(i))                       # L2 flush, outside the event pair
+        if i == 0 and world > 1:                    # the previous rollout's observations go out while this rollout's
+            gatherer.start(prev_rollout_obs)        # first steps run (side stream; starts with the first timed step)
         one_step(choice, ev[i])
     gathered = None
     if world > 1:
@@ -466,7 +467,7 @@ def main_gpu(args):
     e2e_steps = args.steps
     t_e2e = 0.0
 
-    def e2e_step(timed):
+    def e2e_step(timed, gather_obs=None):
         if k > 1:
             order = torch.randint(0, k, (n_envs,), device=dev, generator=gen).cpu().numpy()
         else:
@@ -474,6 +475,8 @@ def main_gpu(args):
         if timed is not None:
             flush.fill_(1.0)
             torch.cuda.synchronize(dev)
+            if gather_obs is not None:
+                gatherer.start(gather_obs)          # the previous rollout's gather runs beside this rollout's first steps
             timed[0].record()
         t0 = time.perf_counter()
         if k > 1:
@@ -493,10 +496,9 @@ def main_gpu(args):
     origin2 = torch.cuda.Event(enable_timing=True)
     barrier()
     origin2.record()
-    if world > 1:
-        gatherer.start(state["obs"])
+    prev_rollout_obs = state["obs"]
     for i in range(e2e_steps):
-        t_e2e += e2e_step(ev2[i])
+        t_e2e += e2e_step(ev2[i], prev_rollout_obs if (i == 0 and world > 1) else None)
     e2e_gather_exposed = 0.0
     if world > 1:
         gatherer.finish()

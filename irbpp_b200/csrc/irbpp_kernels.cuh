@@ -417,6 +417,8 @@ __global__ void __launch_bounds__(CTA_THREADS, IRBPP_SCAN_MIN_CTAS) irbpp_scan_k
     __shared__ double z_sh;
     __shared__ int ok_sh, rot_sh, lx_sh, ly_sh, item_sh, err_sh, any_sh;
     __shared__ __align__(8) mbarrier_t mbar;             // completion of the bulk copies of this bin's inputs
+    __shared__ __align__(16) ShapeRot srot_s[MAX_ROT];   // (56 bytes each) table headers of the item the action places (all rotations), prefetched
+    __shared__ long long a_sh;                           // the bin's action
     __shared__ __align__(16) uint8_t lvmap_s[CTA_WARPS * NPOSE];   // per warp: level code of every pose of its rotation (dense scan)
     const int mode = P.mode;
     // One CTA per bin; get_all_possible_observation (MODE_ALL_OBS) runs one CTA per (bin, buffer slot) in a single
@@ -459,6 +461,7 @@ __global__ void __launch_bounds__(CTA_THREADS, IRBPP_SCAN_MIN_CTAS) irbpp_scan_k
         const uint32_t stw = reinterpret_cast<const uint32_t*>(P.state + env)[lane];
         if (mode == MODE_STEP) a_pf = P.actions[env];
         reinterpret_cast<uint32_t*>(&st_s)[lane] = stw;
+        if (mode == MODE_STEP && lane == 0) a_sh = a_pf;
     }
     if (mode == MODE_RESET) {
         double2* dst = reinterpret_cast<double2*>(hm_s);
@@ -466,7 +469,16 @@ __global__ void __launch_bounds__(CTA_THREADS, IRBPP_SCAN_MIN_CTAS) irbpp_scan_k
     }
     if (tid == 0) { err_sh = 0; any_sh = 0; }
     __syncthreads();                       // mbarrier initialised, state in shared memory
+    if (mode == MODE_STEP) {
+        // while the bulk copies land: the table headers of the item to be placed, all rotations (48 bytes each), so
+        // that decoding the action does not start another round trip to L2
+        static_assert(sizeof(ShapeRot) % 8 == 0, "headers are copied as 8-byte words");
+        constexpr int HW = (int)(sizeof(ShapeRot) / 8);
+        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(P.srot + (int64_t)st_s.cur_item * P.R);
+        for (int i = tid; i < P.R * HW; i += CTA_THREADS) reinterpret_cast<unsigned long long*>(srot_s)[i] = src[i];
+    }
     if (mode != MODE_RESET) mbar_wait(&mbar, 0);
+    if (mode == MODE_STEP) __syncthreads();        // headers visible to every thread
 
     int32_t* queue_g = st_s.queue;
     int next_seq = st_s.next_seq;          // thread 0's register copy; written back with the state
@@ -491,26 +503,35 @@ __global__ void __launch_bounds__(CTA_THREADS, IRBPP_SCAN_MIN_CTAS) irbpp_scan_k
         st_dirty = true;
         __syncthreads();
     } else if (mode == MODE_STEP) {
-        // decode the action (warp 0 computes the drop height of that single pose)
-        if (warp == 0) {
-            const int64_t a = a_pf;
-            const int item = st_s.cur_item;
-            int rot = 0, lx = 0, ly = 0;
-            bool ok = true;
-            if (a < 0 || a >= (P.pose_actions ? P.R * NPOSE : P.sel)) { ok = false; if (lane == 0) err_sh = 2; }
+        // every thread decodes the action: the whole CTA then fetches the placed rotation's top table (what the
+        // heightmap update needs) while warp 0 computes the drop height of that single pose from the bottom table --
+        // the two table reads overlap instead of following each other
+        const int item = st_s.cur_item;
+        int rot = 0, lx = 0, ly = 0;
+        bool ok = true;
+        {
+            const int64_t a = a_sh;
+            if (a < 0 || a >= (P.pose_actions ? P.R * NPOSE : P.sel)) { ok = false; if (tid == 0) err_sh = 2; }
             else {
                 const uint32_t c = P.pose_actions ? (uint32_t)a : (uint32_t)cand_s[a];
                 rot = c >> 8; lx = (c >> 4) & 15; ly = c & 15;
+                if (rot >= P.R) { rot = 0; ok = false; if (tid == 0) err_sh = 2; }
             }
-            const ShapeRot* sr = P.srot + (int64_t)item * P.R + rot;
+        }
+        const ShapeRot& sr = srot_s[rot];
+        const int w = sr.w, h = sr.h;
+        const double* __restrict__ T = P.Ts + sr.off;
+        double tp0 = -INFINITY, tp1 = -INFINITY;               // this thread's first two cells of the top table
+        if (tid < w * h) tp0 = T[tid];
+        if (tid + CTA_THREADS < w * h) tp1 = T[tid + CTA_THREADS];
+        if (warp == 0) {
             // prejudge (binPhy.py:238-245)
-            if (!((sr->okx >> lx) & 1u) || !((sr->oky >> ly) & 1u)) ok = false;
+            if (!((sr.okx >> lx) & 1u) || !((sr.oky >> ly) & 1u)) ok = false;
             if (!st_s.mask_any) ok = false;
             double z = POSZ_INVALID;     // posZmap keeps 1e3 outside the scanned range (space.py:101)
-            if (lx < sr->nX && ly < sr->nY) {
-                const int w = sr->w, h = sr->h;
-                const double* __restrict__ B = P.Bs + sr->off;
-                double acc = sr->any_zero ? 0.0 : -INFINITY;
+            if (lx < sr.nX && ly < sr.nY) {
+                const double* __restrict__ B = P.Bs + sr.off;
+                double acc = sr.any_zero ? 0.0 : -INFINITY;
                 for (int c = lane; c < w * h; c += 32) {
                     const int i = c / h, j = c - i * h;
                     const double v = hm_s[hm_index(STEP * lx + i, STEP * ly + j)] - B[c];
@@ -524,25 +545,21 @@ __global__ void __launch_bounds__(CTA_THREADS, IRBPP_SCAN_MIN_CTAS) irbpp_scan_k
                 z = acc;
             }
             // Interface.simulateHeight (Interface.py:365-369): AABB top above the bin -> failure
-            if (ok && !round6_le0(z + sr->ez - P.binz)) ok = false;
-            if (lane == 0) { z_sh = z; ok_sh = ok; rot_sh = rot; lx_sh = lx; ly_sh = ly; item_sh = item; }
+            if (ok && !round6_le0(z + sr.ez - P.binz)) ok = false;
+            if (lane == 0) { z_sh = z; ok_sh = ok; }
         }
         __syncthreads();
-        const bool ok = ok_sh != 0;
-        const int item = item_sh;
-        __syncthreads();                 // item_sh is rewritten below
+        ok = ok_sh != 0;
         if (ok) {
             // heightmap update: hm[win] = max(hm[win], (T + z) * maskT)   (space.py:213)
-            const ShapeRot* sr = P.srot + (int64_t)item * P.R + rot_sh;
-            const int w = sr->w, h = sr->h;
-            const double* __restrict__ T = P.Ts + sr->off;
             const double z = z_sh;
-            const int x0 = STEP * lx_sh, y0 = STEP * ly_sh;
+            const int x0 = STEP * lx, y0 = STEP * ly;
             // only the cells the item raises are written back (in shared and in global memory): a placement
             // touches at most w x h cells, the other 8 KB of the bin's heightmap stay as they are in HBM
             for (int c = tid; c < w * h; c += CTA_THREADS) {
                 const int i = c / h, j = c - i * h;
-                const double v = T[c] + z;
+                const double t = (c == tid) ? tp0 : ((c == tid + CTA_THREADS) ? tp1 : T[c]);
+                const double v = t + z;
                 const int idx = hm_index(x0 + i, y0 + j);
                 if (v > hm_s[idx]) { hm_s[idx] = v; hm_g[idx] = v; }
             }

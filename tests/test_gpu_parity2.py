@@ -315,3 +315,36 @@ def test_actor_loop_through_learner_glue_at_4096_bins():
         state = next_state
     assert stats.episodes == total_done and total_done > 0 and len(stats.episode_ratio) > 0
     env.close()
+
+
+def test_single_env_evaluation_surface_matches_oracle():
+    """The loop of tools.test (tools.py:303-358): reset / step(int) / get_ratio() before the explicit reset() /
+    .packed / .item_creator.traj_index on a single environment, against the (non-vectorised) oracle env driven the
+    same way -- including that the reset() after a finished episode does not draw a second item."""
+    from irbpp_b200 import shapes
+    from irbpp_b200.single_env import SingleGpuEnv
+    from oracle.oracle_env import OracleConfig, OracleEnv
+    lib = shapes.make_blockout_library(16, seed=7)
+    seq = shapes.make_sequences(1, 200, lib.num_shapes, seed=4)[0]
+    env = SingleGpuEnv(lib, seq, device="cuda:0")
+    ora = OracleEnv(OracleConfig(ZRotNum=4), lib, seq)
+    rng = np.random.default_rng(8)
+    done, episodes = True, 0
+    for _ in range(120):
+        if done:
+            state, o_state = env.reset(), ora.reset()
+            done = False
+        assert np.array_equal(state, o_state.astype(np.float32))
+        valid = np.nonzero(o_state[:2500].reshape(500, 5)[:, 4] == 1)[0]
+        a = int(rng.choice(valid)) if len(valid) and rng.random() > 0.05 else int(rng.integers(0, 500))
+        state, reward, done, info = env.step(a)
+        o_state, o_reward, o_done, o_info = ora.step(a)
+        assert np.float32(o_reward) == np.float32(reward) and done == o_done
+        if done:
+            assert env.get_ratio() == ora.get_ratio() == info["ratio"] and info["counter"] == o_info["counter"] == len(ora.packed_ids)
+            assert [p[0] for p in env.packed] == ora.packed_ids
+            episodes += 1
+        else:
+            assert env.get_ratio() == ora.get_ratio()
+    assert episodes >= 2 and env.item_creator.traj_index == episodes + (0 if done else 1)
+    env.close()
