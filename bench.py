@@ -18,8 +18,8 @@ A "step" is one batched ``step()`` over all bins of a GPU.  For N > 1 the driver
 with torch.distributed.run; bins are sharded by index (weak scaling), there is no collective inside a step,
 and ONE NCCL all-gather of the observations per rollout.  That gather is pipelined: the
 gather of the previous rollout's observations is started with this rollout's first timed step and runs on a side stream beside the steps; the
-timed total counts every part of the gather's duration that did NOT run concurrently with a timed step
-interval (`gather_exposed_ms`), so gather time hidden behind L2 flushes or the stand-in policy is charged.
+timed total counts every part of the gather's duration that did NOT run concurrently with a timed step or
+with the agent stand-in (`gather_exposed_ms`): gather time that fell into an (artificial) L2 flush is charged.
 
 Timing: every timed step is bracketed by CUDA events on the launching stream; between timed steps the L2 is
 flushed by writing a 256 MiB buffer (outside the event pairs).  ``value`` uses actions that are already on the
@@ -422,8 +422,13 @@ def main_gpu(args):
     t_wall0 = time.perf_counter()
     origin.record()
     prev_rollout_obs = state["obs"]
+    ev_pol = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)] if world > 1 else None
     for i in range(args.steps):
+        if world > 1:
+            ev_pol[i][0].record()
         choice = choose()
+        if world > 1:
+            ev_pol[i][1].record()
         flush.fill_(float(i))                       # L2 flush, outside the event pair
         if i == 0 and world > 1:                    # the previous rollout's observations go out while this rollout's
             gatherer.start(prev_rollout_obs)        # first steps run (side stream; starts with the first timed step)
@@ -453,7 +458,9 @@ def main_gpu(args):
     gather_ms = gather_exposed = gather_hidden = 0.0
     if world > 1:
         assert gathered.shape[0] == n_total
-        hidden, gather_ms = overlap_ms(origin, gatherer.events[0], gatherer.events[1], ev)
+        # hidden = the part of the gather that ran beside a timed step or beside the agent stand-in (in training the
+        # agent's forward pass sits there); whatever ran beside the artificial L2 flush or after the last step is exposed
+        hidden, gather_ms = overlap_ms(origin, gatherer.events[0], gatherer.events[1], ev + ev_pol)
         gather_hidden = min(hidden, gather_ms)
         gather_exposed = gather_ms - gather_hidden
     t_dev_ms = float(sum(step_ms)) + gather_exposed
@@ -544,7 +551,7 @@ def main_gpu(args):
                            "parallelism": "env-shard x%d" % world, "kernel_version": irbpp_b200.KERNEL_VERSION,
                            "l2": "flushed between timed steps by a 256 MiB write outside the event pairs",
                            "timing": "sum of per-step CUDA-event intervals on the launching stream"
-                                     + (" + the part of the pipelined rollout all-gather that did not overlap a timed step" if world > 1 else "")
+                                     + (" + the part of the pipelined rollout all-gather that overlapped neither a timed step nor the agent stand-in" if world > 1 else "")
                                      + ", max over ranks"},
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": traffic, "traffic_note": traffic_note, "peak_source": peak_src,

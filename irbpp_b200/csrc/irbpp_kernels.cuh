@@ -448,6 +448,7 @@ __global__ void __launch_bounds__(CTA_THREADS, IRBPP_SCAN_MIN_CTAS) irbpp_scan_k
     uint16_t* cand_s = reinterpret_cast<uint16_t*>(estage + CTA_WARPS * P.maxwh);     // [cand_stride], behind the staging lists
     const bool need_cand = (mode == MODE_STEP) && !P.pose_actions;
     int64_t a_pf = 0;
+    double rew_pf = 0.0, vol_pf = 0.0;      // thread 0: reward and volume of the item being placed (fetched while the copies land)
     if (tid == 0) {
         mbar_init(&mbar, 1);
         if (mode != MODE_RESET) {
@@ -476,6 +477,7 @@ __global__ void __launch_bounds__(CTA_THREADS, IRBPP_SCAN_MIN_CTAS) irbpp_scan_k
         constexpr int HW = (int)(sizeof(ShapeRot) / 8);
         const unsigned long long* src = reinterpret_cast<const unsigned long long*>(P.srot + (int64_t)st_s.cur_item * P.R);
         for (int i = tid; i < P.R * HW; i += CTA_THREADS) reinterpret_cast<unsigned long long*>(srot_s)[i] = src[i];
+        if (tid == 0) { rew_pf = P.reward_tab[st_s.cur_item]; vol_pf = P.vol[st_s.cur_item]; }   // thread 0's bookkeeping inputs
     }
     if (mode != MODE_RESET) mbar_wait(&mbar, 0);
     if (mode == MODE_STEP) __syncthreads();        // headers visible to every thread
@@ -570,7 +572,7 @@ __global__ void __launch_bounds__(CTA_THREADS, IRBPP_SCAN_MIN_CTAS) irbpp_scan_k
         if (tid == 0) {
             const int nfill = P.K > 1 ? P.K : 1;
             if (ok) {
-                const double rew = P.reward_tab[item];
+                const double rew = rew_pf;
                 P.r_reward[env] = (float)rew; P.r_done[env] = 0; P.r_valid[env] = 1;
                 P.r_counter[env] = -1; P.r_eplen[env] = 0; P.r_ratio[env] = -1.0; P.r_eprew[env] = 0.0;
                 if (P.h_reward) {
@@ -578,7 +580,7 @@ __global__ void __launch_bounds__(CTA_THREADS, IRBPP_SCAN_MIN_CTAS) irbpp_scan_k
                     P.h_counter[env] = -1; P.h_eplen[env] = 0; P.h_ratio[env] = -1.0; P.h_eprew[env] = 0.0;
                 }
                 st_s.packed += 1; st_s.ep_len += 1;
-                st_s.vol_sum += P.vol[item];
+                st_s.vol_sum += vol_pf;
                 st_s.ep_rew += rew;
                 // item_creator.update_item_queue(orderAction); generate_item()  (binPhy.py:324-325)
                 const int oa = st_s.order_act;
