@@ -406,13 +406,22 @@ def main_gpu(args):
     state["obs"] = env.reset()
     for _ in range(BURN_IN + args.warmup):          # burn-in: bins spread over all episode phases
         one_step(choose())
-    gatherer = sharding.AsyncRolloutGather(world) if world > 1 else None
+    gatherer = None
+    if world > 1:          # IRBPP_GATHER=nccl selects the NCCL all-gather; default: copy-engine pushes over NVLink peer memory
+        gatherer = sharding.AsyncRolloutGather(world) if os.environ.get("IRBPP_GATHER", "peer") == "nccl" else sharding.PeerCopyGather(world)
     gather_alone_ms = 0.0
     if world > 1:                                   # warm-up of the rollout-end collective (NCCL channel setup) + its stand-alone time
         for _ in range(2):
             gatherer.start(state["obs"]); gatherer.finish()
         torch.cuda.synchronize(dev)
         gather_alone_ms = gatherer.events[0].elapsed_time(gatherer.events[1])
+    # rehearsal: a few untimed iterations shaped exactly like the timed ones (L2 flush, event records), so that nothing
+    # is done for the first time inside the timed region (a first-use stall showed up as one 60 ms step on a fresh box)
+    for i in range(3):
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        choice = choose()
+        flush.fill_(float(i))
+        one_step(choice, (r0, r1))
     torch.cuda.synchronize(dev)
     launches0 = env.launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
@@ -563,12 +572,14 @@ def main_gpu(args):
                         "note": "GpuVecEnv.step(host int64 actions): pinned staging, kernels, reward/done/info arrays back to the "
                                 "host, stream sync; observations stay on the device as in the reference (envs.py:163)"
                                 + ("; includes the exposed part of the rollout all-gather" if world > 1 else "")},
-                "gpu_launches": int(launches_timed), "clocks": clocks, "wall_s_timed_region": t_wall}
+                "gpu_launches": int(launches_timed), "clocks": clocks, "wall_s_timed_region": t_wall,
+                "step_ms": {"median": float(np.median(step_ms)), "min": float(np.min(step_ms)), "max": float(np.max(step_ms))}}
         if world > 1:
             line["gather_ms"] = gather_ms
             line["gather_exposed_ms"] = gather_exposed
             line["gather_hidden_ms"] = gather_ms - gather_exposed
             line["gather_alone_ms"] = gather_alone_ms
+            line["gather_kind"] = getattr(gatherer, "kind", "nccl all-gather")
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
         print(json.dumps(line))

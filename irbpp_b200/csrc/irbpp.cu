@@ -309,7 +309,7 @@ int irbpp_load_shapes(irbpp_handle h, int32_t S, int32_t R, const int32_t* dims,
                             }
                         if (!any_open) continue;                  // fully masked block contributes nothing
                         if (any_masked || !same || i1 - bi * t != t || j1 - bj * t != t) { ok = false; break; }
-                        TileEntry e; e.off = (bi * t / 2) * 16 + (bj * t / 2); e.pad = 0; e.b = b0;
+                        TileEntry e; e.off = 8 * ((bi * t / 2) * 16 + (bj * t / 2)); e.pad = 0; e.b = b0;
                         found[r].push_back(e);
                     }
             }
@@ -332,7 +332,7 @@ int irbpp_load_shapes(irbpp_handle h, int32_t S, int32_t R, const int32_t* dims,
                     for (int j = 0; j < q.h; ++j) {
                         const double b = Bq[(size_t)i * q.h + j];
                         if (std::isinf(b)) continue;
-                        TileEntry e; e.off = ((j & 1) * HX + i) * (HY / 2) + (j >> 1); e.pad = 0; e.b = b;
+                        TileEntry e; e.off = 8 * (((j & 1) * HX + i) * (HY / 2) + (j >> 1)); e.pad = 0; e.b = b;
                         tiles.push_back(e);
                     }
                 q.ntiles = (int32_t)tiles.size() - q.tile_off;

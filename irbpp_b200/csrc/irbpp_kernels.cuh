@@ -98,8 +98,8 @@ struct ShapeRot {          // one (shape, rotation) entry, device resident
 // One entry of a rotation's scan list: either a block of a block-structured table (offset into the
 // block-maxima array M, indexed like the action grid) or one unmasked cell of an arbitrary table (offset
 // into the column-parity heightmap planes).  Masked cells / blocks have no entry.
-struct TileEntry {
-    int32_t off;           // added to the pose's base index: block (du*16 + dv), cell hm_index(i, j)
+struct alignas(16) TileEntry {     // 16 bytes: one LDS.128 per entry
+    int32_t off;           // BYTE offset added to the pose's base address: 8 * (block du*16 + dv), 8 * cell hm_index(i, j)
     int32_t pad;
     double b;              // bottom height of the block / cell
 };
@@ -279,7 +279,8 @@ __device__ __forceinline__ bool scan_rotation(const Params& P, const double* arr
 #pragma unroll 4
             for (int k = 0; k < nt; ++k) {
                 const TileEntry e = es[k];
-                const double u = a0[e.off] - e.b, v = b0[e.off] - e.b;
+                const double u = *reinterpret_cast<const double*>(reinterpret_cast<const char*>(a0) + e.off) - e.b;
+                const double v = *reinterpret_cast<const double*>(reinterpret_cast<const char*>(b0) + e.off) - e.b;
                 accA = (u > accA) ? u : accA;
                 accB = (v > accB) ? v : accB;
             }
@@ -336,7 +337,7 @@ __device__ __forceinline__ bool scan_rotation_dense(const Params& P, const doubl
     auto chunk = [&](int c0, auto ppl_tag) {
         constexpr int PPL = decltype(ppl_tag)::value;
         int cell[PPL];
-        const double* base[PPL];
+        const char* base[PPL];
         bool valid[PPL];
         double acc[PPL];
 #pragma unroll
@@ -346,7 +347,7 @@ __device__ __forceinline__ bool scan_rotation_dense(const Params& P, const doubl
             const int X = valid[k] ? (int)(((uint32_t)v * magic) >> 16) : 0;
             const int Y = valid[k] ? v - X * nY : 0;
             cell[k] = X * 16 + Y;
-            base[k] = arr + X * stride_x + Y;
+            base[k] = reinterpret_cast<const char*>(arr + X * stride_x + Y);
             acc[k] = init;
         }
 #pragma unroll 2
@@ -354,7 +355,7 @@ __device__ __forceinline__ bool scan_rotation_dense(const Params& P, const doubl
             const TileEntry en = es[e];
 #pragma unroll
             for (int k = 0; k < PPL; ++k) {
-                const double u = base[k][en.off] - en.b;
+                const double u = *reinterpret_cast<const double*>(base[k] + en.off) - en.b;      // entry offsets are in bytes
                 acc[k] = (u > acc[k]) ? u : acc[k];
             }
         }

@@ -104,6 +104,91 @@ class AsyncRolloutGather(object):
         return out
 
 
+class PeerCopyGather(object):
+    """The rollout gather as peer-to-peer copies by the COPY ENGINES instead of an NCCL kernel: every rank pushes its
+    shard straight into every peer's gathered buffer over NVLink (the buffers are exchanged once as CUDA IPC handles),
+    then a 4-byte NCCL all-reduce on the same side stream tells each rank that all pushes into ITS buffer are done.
+    An NCCL all-gather occupies SMs on every GPU for its whole duration, and beside the latency-bound step kernels
+    it cost almost as much step time as it took itself (8 GPUs: steps 0.108 -> 0.145 ms while a 0.78 ms gather ran);
+    copy-engine traffic does not compete for SMs, so it really runs beside the next rollout's steps.
+    Same interface as AsyncRolloutGather; a gathered buffer stays valid until the second next ``start``.
+    One node only (CUDA IPC); falls back to AsyncRolloutGather if the handles cannot be exchanged."""
+
+    def __init__(self, world_size=None, group=None):
+        import torch.distributed as dist
+        self.world = dist.get_world_size(group) if world_size is None else world_size
+        self.rank = dist.get_rank(group)
+        self.group = group
+        self._views = None            # [turn][peer rank] -> that peer's gathered buffer (own buffer for peer == rank)
+        self._turn = 0
+        self._side = None
+        self._inflight = None
+        self._fallback = None
+        self.events = None
+        self.kind = "peer-copy (copy engines over NVLink + 4-byte all-reduce)"
+
+    def _setup(self, local):
+        import torch
+        import torch.distributed as dist
+        from torch.multiprocessing.reductions import rebuild_cuda_tensor, reduce_tensor
+        shape = (self.world * local.shape[0],) + tuple(local.shape[1:])
+        own = [torch.empty(shape, dtype=local.dtype, device=local.device) for _ in range(2)]
+        mine = [reduce_tensor(b)[1] for b in own]                  # CUDA IPC handles of both buffers
+        everyone = [None] * self.world
+        dist.all_gather_object(everyone, mine, group=self.group)
+        self._views = [[own[t] if r == self.rank else rebuild_cuda_tensor(*everyone[r][t]) for r in range(self.world)]
+                       for t in range(2)]
+        self._token = torch.zeros(1, dtype=torch.int32, device=local.device)
+        self._side = torch.cuda.Stream(device=local.device)
+        self._n = local.shape[0]
+
+    def start(self, local):
+        import torch
+        import torch.distributed as dist
+        if self._inflight is not None:
+            raise RuntimeError("a gather is already in flight")
+        local = local.contiguous()
+        if self._fallback is None and self._views is None:
+            try:
+                self._setup(local)
+            except Exception as exc:                                # no IPC (other node, containers without it, ...)
+                self._fallback = AsyncRolloutGather(self.world, self.group)
+                self.kind = "nccl all-gather (peer-copy set-up failed: %s)" % type(exc).__name__
+        if self._fallback is not None:
+            self._fallback.start(local)
+            self._inflight = "fallback"
+            return
+        t = self._turn
+        self._turn ^= 1
+        cur = torch.cuda.current_stream(local.device)
+        self._side.wait_stream(cur)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        lo = self.rank * self._n
+        with torch.cuda.stream(self._side):
+            e0.record()
+            for k in range(self.world):                             # start with the next rank: spreads the traffic over the links
+                r = (self.rank + 1 + k) % self.world
+                self._views[t][r][lo:lo + self._n].copy_(local, non_blocking=True)
+            dist.all_reduce(self._token, group=self.group)          # completes when every rank has issued its pushes behind it
+            e1.record()
+        local.record_stream(self._side)
+        self.events = (e0, e1)
+        self._inflight = self._views[t][self.rank]
+
+    def finish(self):
+        import torch
+        if self._inflight is None:
+            raise RuntimeError("no gather in flight")
+        if self._inflight == "fallback":
+            out = self._fallback.finish()
+            self.events = self._fallback.events
+        else:
+            out = self._inflight
+            torch.cuda.current_stream(out.device).wait_stream(self._side)
+        self._inflight = None
+        return out
+
+
 def scatter_actions(global_actions, rank, world_size):
     """Slice of a global action vector (ordered by global env index) that belongs to ``rank``."""
     lo, hi = shard_range(global_actions.shape[0], rank, world_size)
