@@ -109,7 +109,7 @@ class ClockSampler(object):
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "20"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -400,6 +400,9 @@ def main_gpu(args):
             ev[1].record()
 
     # ---- device-resident loop ("value") ----
+    import gc
+    gc.collect()
+    gc.disable()                                    # a generation-2 collection inside a timed step showed up as a 1-30 ms "step"
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()                             # sampled from burn-in through the timed steps (same load)
@@ -407,8 +410,8 @@ def main_gpu(args):
     for _ in range(BURN_IN + args.warmup):          # burn-in: bins spread over all episode phases
         one_step(choose())
     gatherer = None
-    if world > 1:          # IRBPP_GATHER=nccl selects the NCCL all-gather; default: copy-engine pushes over NVLink peer memory
-        gatherer = sharding.AsyncRolloutGather(world) if os.environ.get("IRBPP_GATHER", "peer") == "nccl" else sharding.PeerCopyGather(world)
+    if world > 1:          # NCCL all-gather on a side stream; IRBPP_GATHER=peer: copy-engine pushes into the peers' buffers (CUDA IPC)
+        gatherer = sharding.PeerCopyGather(world) if os.environ.get("IRBPP_GATHER", "nccl") == "peer" else sharding.AsyncRolloutGather(world)
     gather_alone_ms = 0.0
     if world > 1:                                   # warm-up of the rollout-end collective (NCCL channel setup) + its stand-alone time
         for _ in range(2):
@@ -454,8 +457,8 @@ def main_gpu(args):
     # delivered enough clock samples under this load
     extra_steps = 0
     if rank == 0:
-        t_end = time.perf_counter() + 1.5
-        while len(sampler.rows) < 25 and time.perf_counter() < t_end:
+        t_end = time.perf_counter() + 2.5
+        while len(sampler.rows) < 20 and time.perf_counter() < t_end:
             for _ in range(20):
                 one_step(choose())
             torch.cuda.synchronize(dev)
