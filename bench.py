@@ -47,6 +47,7 @@ BURN_IN = 150            # untimed steps before the W warm-up steps so episodes 
 UNIT = "env-steps/s"
 CPU_ENVS_PER_CORE = 2    # bins per worker process of the CPU arm (same in cpu_baseline and --impl reference)
 CPU_SAMPLES = 3          # the CPU arm reports the median of this many timed samples
+DEFAULT_NCCL_CHANNELS = 0   # channels (= SMs) of the rollout all-gather; 0 = NCCL's default (see main_gpu)
 
 CONFIGS = {
     "blockout": dict(bins=4096, k=1, R=4, metric="env steps/sec (4096 bins, BlockOut)",
@@ -361,6 +362,14 @@ def main_gpu(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        # The rollout gather runs beside the next rollout's steps.  NCCL's default all-gather takes up to 32 SMs with
+        # one fat CTA each for its whole duration; the candidates kernel's grid fits the 148 SMs exactly once, so any
+        # SM it loses costs it a second wave (8 GPUs: steps 0.108 -> 0.145 ms while the gather ran).  Fewer channels make
+        # the gather slower but narrower; it has the whole rollout to finish.  IRBPP_NCCL_CHANNELS overrides (0: NCCL's choice).
+        ch = int(os.environ.get("IRBPP_NCCL_CHANNELS", str(DEFAULT_NCCL_CHANNELS)))
+        if ch > 0:
+            os.environ["NCCL_MAX_NCHANNELS"] = str(ch)
+            os.environ["NCCL_MIN_NCHANNELS"] = str(min(ch, 4))
         dist.init_process_group("nccl", device_id=dev)
 
     lib = make_library(args.config)
@@ -583,6 +592,7 @@ def main_gpu(args):
             line["gather_hidden_ms"] = gather_ms - gather_exposed
             line["gather_alone_ms"] = gather_alone_ms
             line["gather_kind"] = getattr(gatherer, "kind", "nccl all-gather")
+            line["nccl_channels"] = os.environ.get("NCCL_MAX_NCHANNELS", "default")
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
         print(json.dumps(line))
