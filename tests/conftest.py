@@ -13,6 +13,26 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    if not config.pluginmanager.hasplugin("timeout"):
+        # pytest-timeout absent: the marker is registered so that it is not an unknown-mark warning, and the emulated
+        # kernel tests (which rely on it against deadlocked barriers) install their own watchdog (see below)
+        config.addinivalue_line("markers", "timeout(seconds): per-test time limit (pytest-timeout)")
+
+
+@pytest.fixture(autouse=True)
+def _watchdog_without_pytest_timeout(request):
+    """Without the pytest-timeout plugin a `timeout` marker would be a silent no-op: arm a faulthandler watchdog that
+    dumps all stacks and exits instead, so a deadlocked emulated barrier cannot hang the suite."""
+    mark = request.node.get_closest_marker("timeout")
+    if mark is None or request.config.pluginmanager.hasplugin("timeout"):
+        yield
+        return
+    import faulthandler
+    faulthandler.dump_traceback_later(float(mark.args[0]) if mark.args else 900.0, exit=True)
+    try:
+        yield
+    finally:
+        faulthandler.cancel_dump_traceback_later()
 
 
 def load_golden(name):
