@@ -100,18 +100,50 @@ def algorithmic_bytes_per_env_step(lib, k=1, sel=SEL):
 
 
 class ClockSampler(object):
-    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    """SM clock and throttle reasons sampled while the benchmark loop runs: NVML queries from a thread of this process
+    (pynvml; a few microseconds each), or an `nvidia-smi -lms` subprocess when pynvml is missing.  (Round 2: the
+    nvidia-smi loop at 20 ms was replaced after single steps of 1-30 ms showed up on multi-GPU boxes.)"""
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index, period_s=0.025):
+        self.index, self.rows, self.proc, self.period = index, [], None, period_s
+        self._stop = threading.Event()
+        self.thread = None
+        self.how = None
+
+    def _nvml_loop(self, nv, handle):
+        masks = [(nv.nvmlClocksEventReasonHwSlowdown, "hw_slowdown"), (nv.nvmlClocksEventReasonHwThermalSlowdown, "hw_thermal_slowdown"),
+                 (nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_thermal_slowdown"), (nv.nvmlClocksEventReasonSwPowerCap, "sw_power_cap")]
+        smax = nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM)
+        while not self._stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)
+                bits = nv.nvmlDeviceGetCurrentClocksEventReasons(handle)
+                self.rows.append((float(sm), float(smax), [nm for m, nm in masks if bits & m]))
+            except Exception:
+                pass
+            self._stop.wait(self.period)
 
     def start(self):
         try:
+            import pynvml as nv
+            nv.nvmlInit()
+            # torch numbers the devices like CUDA does; NVML by PCI order: resolve through the UUID-free common case
+            # (CUDA_VISIBLE_DEVICES unset, CUDA_DEVICE_ORDER default = fastest first == PCI order on a homogeneous box)
+            handle = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.how = "nvml"
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, handle), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.how = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.how = "nvidia-smi"
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -119,31 +151,33 @@ class ClockSampler(object):
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
-
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=3)
-        except Exception:
-            self.proc.kill()
-        sm, smax, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for row in self.rows:
-            parts = [p.strip() for p in row.split(",")]
+            parts = [p.strip() for p in line.strip().split(",")]
             if len(parts) < 6:
                 continue
             try:
-                sm.append(float(parts[0])); smax = float(parts[1])
+                self.rows.append((float(parts[0]), float(parts[1]),
+                                  [nm for nm, v in zip(self.NAMES, parts[2:6]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for nm, v in zip(names, parts[2:6]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "samples": len(sm)}
+
+    def stop(self):
+        if self.how is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML / nvidia-smi"]}
+        self._stop.set()
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=3)
+            except Exception:
+                self.proc.kill()
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+        sm = [r[0] for r in self.rows]
+        reasons = set()
+        for r in self.rows:
+            reasons.update(r[2])
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": self.rows[-1][1] if self.rows else None,
+                "reasons": sorted(reasons), "samples": len(sm), "source": self.how}
 
 
 def device_policy(torch, obs, gen):
@@ -419,8 +453,10 @@ def main_gpu(args):
     for _ in range(BURN_IN + args.warmup):          # burn-in: bins spread over all episode phases
         one_step(choose())
     gatherer = None
-    if world > 1:          # NCCL all-gather on a side stream; IRBPP_GATHER=peer: copy-engine pushes into the peers' buffers (CUDA IPC)
-        gatherer = sharding.PeerCopyGather(world) if os.environ.get("IRBPP_GATHER", "nccl") == "peer" else sharding.AsyncRolloutGather(world)
+    if world > 1:          # IRBPP_GATHER: compact (default: NCCL all-gather of the packed observations, expanded on arrival) | nccl (plain) | peer (copy-engine pushes, CUDA IPC)
+        kind = os.environ.get("IRBPP_GATHER", "compact" if k == 1 else "nccl")
+        gatherer = (sharding.PeerCopyGather(world) if kind == "peer" else
+                    sharding.CompactRolloutGather(SEL, world) if kind == "compact" else sharding.AsyncRolloutGather(world))
     gather_alone_ms = 0.0
     if world > 1:                                   # warm-up of the rollout-end collective (NCCL channel setup) + its stand-alone time
         for _ in range(2):
@@ -441,6 +477,9 @@ def main_gpu(args):
     tail0, tail1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     t_wall0 = time.perf_counter()
+    # runway: the GPU spins for ~30 ms while the host enqueues all K iterations, so the event intervals below are GPU time
+    # only -- a host hiccup between two launches of a step (seen as single "steps" of 1-30 ms) cannot land inside them
+    torch.cuda._sleep(int(0.030 * 1.9e9))
     origin.record()
     prev_rollout_obs = state["obs"]
     ev_pol = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)] if world > 1 else None
@@ -484,6 +523,9 @@ def main_gpu(args):
         hidden, gather_ms = overlap_ms(origin, gatherer.events[0], gatherer.events[1], ev + ev_pol)
         gather_hidden = min(hidden, gather_ms)
         gather_exposed = gather_ms - gather_hidden
+        for evs in (getattr(gatherer, "pack_events", None), getattr(gatherer, "unpack_events", None)):
+            if evs is not None:                     # pack / expansion of the compact form run on the step stream: always exposed
+                gather_exposed += evs[0].elapsed_time(evs[1])
     t_dev_ms = float(sum(step_ms)) + gather_exposed
     t = torch.tensor([t_dev_ms, float(np.mean(step_ms)), gather_ms, gather_exposed, gather_alone_ms], dtype=torch.float64, device=dev)
     if world > 1:
@@ -533,6 +575,9 @@ def main_gpu(args):
         torch.cuda.synchronize(dev)
         hidden, gms = overlap_ms(origin2, gatherer.events[0], gatherer.events[1], ev2)
         e2e_gather_exposed = gms - min(hidden, gms)
+        for evs in (getattr(gatherer, "pack_events", None), getattr(gatherer, "unpack_events", None)):
+            if evs is not None:
+                e2e_gather_exposed += evs[0].elapsed_time(evs[1])
     te = torch.tensor([t_e2e + e2e_gather_exposed * 1e-3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)

@@ -188,6 +188,14 @@ int irbpp_debug_hulls(irbpp_handle h, const double* posZValid, const double* mas
 /* Kernel launches issued by this handle so far (bench.py's gpu_launches). */
 int64_t irbpp_launch_count(irbpp_handle h);
 
+/* ---- compact observations for the rollout gather ----------------------------------------------
+ * The float32 location observation [N, sel*5 + 9 + 1024] (binPhy.py:196-227) re-encoded without loss as u16 poses, f32
+ * heights, one mask bit per row, the item id and the f32 heightmap: irbpp_packed_obs_bytes(sel) bytes per bin (7 184 at
+ * sel = 500, 51 %).  What `sharding.CompactRolloutGather` sends between GPUs; device pointers, handle-free. */
+int irbpp_packed_obs_bytes(int32_t selected_action);
+int irbpp_pack_observations(const float* obs, int64_t obs_stride, int32_t selected_action, int32_t n, void* packed, void* stream);
+int irbpp_unpack_observations(const void* packed, int32_t selected_action, int32_t n, float* obs, int64_t obs_stride, void* stream);
+
 /* ---- point clouds of the next items --------------------------------------------------------
  * Replaces model.py:328-335 / :366-372: `shapeArray[next_item_ID.cpu()]` (a HOST gather of [B, P, 3] float32 rows),
  * `np.random.randint(P, size=samplePointsNum)` (one index set shared by the batch) and the host-to-device copy

@@ -50,6 +50,9 @@ SIGNATURES = {
     "irbpp_debug_scan": (c_i32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "irbpp_debug_hulls": (c_i32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "irbpp_launch_count": (c_i64, [c_void_p]),
+    "irbpp_packed_obs_bytes": (c_i32, [c_i32]),
+    "irbpp_pack_observations": (c_i32, [c_void_p, c_i64, c_i32, c_i32, c_void_p, c_void_p]),
+    "irbpp_unpack_observations": (c_i32, [c_void_p, c_i32, c_i32, c_void_p, c_i64, c_void_p]),
     "irbpp_sample_point_clouds": (c_i32, [c_void_p, c_i32, c_i32, c_void_p, c_i64, c_i32, c_void_p, c_i32, ctypes.c_uint64,
                                           ctypes.c_uint64, c_i32, c_void_p, c_void_p, c_void_p]),
     "irbpp_shape_features": (c_i32, [c_void_p, c_i32, c_i32, c_void_p, c_i64, c_i32, c_void_p, c_i32, ctypes.c_uint64,

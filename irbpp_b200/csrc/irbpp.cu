@@ -18,6 +18,7 @@
 #include "../../include/irbpp.h"
 #include "irbpp_kernels.cuh"
 #include "irbpp_pointnet.cuh"
+#include "irbpp_pack.cuh"
 
 using namespace irbpp;
 
@@ -32,8 +33,13 @@ struct irbpp_env {
     bool scan_current = false;        // the scan scratch holds the drop heights of every bin's cur_item
     int32_t* heur_pose_dev = nullptr; int64_t* heur_index_dev = nullptr;
     bool results_on_host = false;           // the pending step wrote its results straight to the host mirror
-    int host_results_mode = 0;              // IRBPP_HOST_RESULTS: 0 per-bin stores over PCIe (default), 1 copy kernel, 2 cudaMemcpyAsync in step_wait
-    int host_actions_mode = 1;              // IRBPP_HOST_ACTIONS: 1 cudaMemcpyAsync in front of the kernel (default: measured 12 us faster end to end), 0 "mapped": read over PCIe by the kernel
+    // The host step as ONE CUDA graph launch (H2D copy of the actions + scan kernel + candidates kernel with its
+    // programmatic dependency): instantiated per (observation buffer, host result block, action kind) on first use
+    // -- callers cycle through two or three observation buffers -- and replayed afterwards.  IRBPP_GRAPH=0 disables.
+    struct StepGraph { float* obs; int turn; int pose; cudaGraphExec_t exec; };
+    std::vector<StepGraph> step_graphs;
+    cudaStream_t capture_stream = nullptr;
+    bool use_graph = true;
     cudaStream_t pending_stream = nullptr;
     int64_t launches = 0;
     // device allocations
@@ -46,8 +52,7 @@ struct irbpp_env {
     int res_turn = 0;
     size_t results_bytes = 0;
     int64_t* actions_dev = nullptr;
-    int64_t* actions_pinned = nullptr;      // [2][N] mapped pinned: step actions, order actions (read zero-copy)
-    int64_t* actions_mapped = nullptr;      // device view of actions_pinned
+    int64_t* actions_pinned = nullptr;      // [2][N] pinned staging: step actions, order actions
     char* results_mapped = nullptr;         // device view of results_host
     uint8_t* which_dev = nullptr;
     // shape pools
@@ -85,6 +90,13 @@ static cudaError_t dev_alloc(irbpp_env* h, T** p, size_t count, bool zero = true
     return cudaSuccess;
 }
 
+
+static void drop_step_graphs(irbpp_env* h) {        // the instantiated step graphs hold copies of the launch parameters
+#ifndef IRBPP_HOST_EMULATION
+    for (auto& g : h->step_graphs) cudaGraphExecDestroy(g.exec);
+#endif
+    h->step_graphs.clear();
+}
 
 static void free_dev(irbpp_env* h, void* p) {
     if (!p) return;
@@ -152,8 +164,7 @@ int irbpp_create(const irbpp_config* cfg, irbpp_handle* out) {
 
     irbpp_env* h = new irbpp_env();
     h->cfg = *cfg;
-    if (const char* m = getenv("IRBPP_HOST_RESULTS")) h->host_results_mode = !strcmp(m, "kernel") ? 1 : (!strcmp(m, "memcpy") ? 2 : 0);
-    if (const char* m = getenv("IRBPP_HOST_ACTIONS")) h->host_actions_mode = !strcmp(m, "mapped") ? 0 : 1;
+    if (const char* m = getenv("IRBPP_GRAPH")) h->use_graph = strcmp(m, "0") != 0;
     Params& P = h->P;
     memset(&P, 0, sizeof(P));
     const int N = cfg->num_envs;
@@ -195,7 +206,6 @@ int irbpp_create(const irbpp_config* cfg, irbpp_handle* out) {
     }
     h->results_host = h->results_host2[0]; h->results_mapped = h->results_mapped2[0];
     TRY_ALLOC(cudaHostAlloc((void**)&h->actions_pinned, 2 * (size_t)N * sizeof(int64_t), cudaHostAllocMapped));
-    TRY_ALLOC(cudaHostGetDevicePointer((void**)&h->actions_mapped, h->actions_pinned, 0));
     {
         char* b = reinterpret_cast<char*>(h->results_dev);
         P.r_ratio = reinterpret_cast<double*>(b); b += (size_t)N * 8;
@@ -217,6 +227,8 @@ int irbpp_destroy(irbpp_handle h) {
     if (!h) return IRBPP_OK;
     cudaSetDevice(h->cfg.device);
     cudaDeviceSynchronize();
+    drop_step_graphs(h);
+    if (h->capture_stream) cudaStreamDestroy(h->capture_stream);
     for (void* p : h->dev_allocs) cudaFree(p);
     if (h->results_dev) cudaFree(h->results_dev);
     for (int t = 0; t < 2; ++t) if (h->results_host2[t]) cudaFreeHost(h->results_host2[t]);
@@ -342,6 +354,7 @@ int irbpp_load_shapes(irbpp_handle h, int32_t S, int32_t R, const int32_t* dims,
     }
     cudaSetDevice(c.device);
     CUDA_TRY(h, cudaDeviceSynchronize());
+    drop_step_graphs(h);
     for (void* old : {(void*)h->srot_dev, (void*)h->Bs_dev, (void*)h->Ts_dev, (void*)h->vol_dev, (void*)h->rew_dev, (void*)h->tiles_dev})
         free_dev(h, old);                                                 // a reload replaces the previous pools
     CUDA_TRY(h, dev_alloc(h, &h->srot_dev, srot.size(), false));
@@ -370,6 +383,7 @@ int irbpp_load_shapes(irbpp_handle h, int32_t S, int32_t R, const int32_t* dims,
 
 // fresh per-bin state: cursors restart, every bin's first sequence entry is staged for its first draw
 static int restart_items(irbpp_env* h, const int32_t* ids, int32_t length) {
+    drop_step_graphs(h);
     std::vector<EnvState> st((size_t)h->P.N);
     memset(st.data(), 0, st.size() * sizeof(EnvState));
     if (ids) for (int e = 0; e < h->P.N; ++e) st[e].next_seq = ids[(size_t)e * length];
@@ -411,12 +425,6 @@ int irbpp_set_item_rng(irbpp_handle h, uint64_t seed) {
 // candidates kernel when the observation carries candidate rows.  (Running bin ranges on separate
 // streams so that one range's candidates kernel overlaps the next range's scan kernel was measured:
 // no gain -- the scan kernel owns the whole register file, the two cannot co-reside.)
-// Experiment knob (IRBPP_HOST_RESULTS=kernel): the 31 B/bin result block device -> host-mapped memory
-// as one coalesced copy after the step's kernels, instead of eight small stores per bin over PCIe.
-__global__ void irbpp_copy_block_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src, int n16) {
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += gridDim.x * blockDim.x) dst[i] = src[i];
-}
-
 static int launch(irbpp_env* h, Params& P, cudaStream_t s) {
     // the units of a launch: bins, or (bin, buffer slot) pairs for get_all_possible_observation
     const int units = (P.mode == MODE_ALL_OBS) ? P.N * P.K : P.N;
@@ -482,38 +490,64 @@ static int step_async_impl(irbpp_env* h, const int64_t* actions, int32_t on_devi
     cudaStream_t s = (cudaStream_t)stream;
     Params P = h->P;
     P.mode = MODE_STEP; P.obs = obs_out; P.pose_actions = pose_actions;
-    if (on_device) P.actions = actions;
-    else {
-        // host actions: staged in mapped pinned memory and read by the kernel over PCIe (one 8-byte read per
-        // bin) -- no separate copy node in front of the kernel; results go back the same way (posted stores)
+    h->results_on_host = !on_device;
+    if (on_device) {
+        P.actions = actions;
+        rc = launch(h, P, s); if (rc) return rc;
+    } else {
+        // host actions: pinned staging + one H2D copy (measured 12 us faster end to end than letting the kernel read
+        // them over PCIe); results: every bin's thread 0 also stores them into this step's pinned host block
         memcpy(h->actions_pinned, actions, (size_t)P.N * sizeof(int64_t));
-        P.actions = h->actions_mapped;
-        if (h->host_actions_mode == 1) {
-            CUDA_TRY(h, cudaMemcpyAsync(h->actions_dev, h->actions_pinned, (size_t)P.N * sizeof(int64_t), cudaMemcpyHostToDevice, s));
-            P.actions = h->actions_dev;
-        }
+        P.actions = h->actions_dev;
         h->res_turn ^= 1;                                   // this step's host block (the previous step's stays readable)
         h->results_host = h->results_host2[h->res_turn]; h->results_mapped = h->results_mapped2[h->res_turn];
         char* b = h->results_mapped;
         const size_t N = P.N;
-        if (h->host_results_mode == 0) {
-            P.h_ratio = reinterpret_cast<double*>(b); b += N * 8;
-            P.h_eprew = reinterpret_cast<double*>(b); b += N * 8;
-            P.h_reward = reinterpret_cast<float*>(b); b += N * 4;
-            P.h_counter = reinterpret_cast<int32_t*>(b); b += N * 4;
-            P.h_eplen = reinterpret_cast<int32_t*>(b); b += N * 4;
-            P.h_done = reinterpret_cast<uint8_t*>(b); b += N;
-            P.h_valid = reinterpret_cast<uint8_t*>(b); b += N;
-            P.h_error = reinterpret_cast<uint8_t*>(b);
+        P.h_ratio = reinterpret_cast<double*>(b); b += N * 8;
+        P.h_eprew = reinterpret_cast<double*>(b); b += N * 8;
+        P.h_reward = reinterpret_cast<float*>(b); b += N * 4;
+        P.h_counter = reinterpret_cast<int32_t*>(b); b += N * 4;
+        P.h_eplen = reinterpret_cast<int32_t*>(b); b += N * 4;
+        P.h_done = reinterpret_cast<uint8_t*>(b); b += N;
+        P.h_valid = reinterpret_cast<uint8_t*>(b); b += N;
+        P.h_error = reinterpret_cast<uint8_t*>(b);
+        bool launched = false;
+#ifndef IRBPP_HOST_EMULATION
+        if (h->use_graph) {
+            cudaGraphExec_t exec = nullptr;
+            for (auto& g : h->step_graphs)
+                if (g.obs == obs_out && g.turn == h->res_turn && g.pose == pose_actions) { exec = g.exec; break; }
+            if (!exec) {
+                // record the three nodes on the library's own capture stream (the caller's may be the legacy default
+                // stream, which cannot capture); the graph itself is launched on the caller's stream
+                if (!h->capture_stream && cudaStreamCreateWithFlags(&h->capture_stream, cudaStreamNonBlocking) != cudaSuccess) h->use_graph = false;
+                cudaGraph_t graph = nullptr;
+                const int64_t before = h->launches;
+                if (h->use_graph && cudaStreamBeginCapture(h->capture_stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+                    cudaMemcpyAsync(h->actions_dev, h->actions_pinned, (size_t)P.N * sizeof(int64_t), cudaMemcpyHostToDevice, h->capture_stream);
+                    const int lrc = launch(h, P, h->capture_stream);
+                    const cudaError_t ec = cudaStreamEndCapture(h->capture_stream, &graph);
+                    if (lrc == IRBPP_OK && ec == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+                        if (h->step_graphs.size() >= 8) { cudaGraphExecDestroy(h->step_graphs.front().exec); h->step_graphs.erase(h->step_graphs.begin()); }
+                        h->step_graphs.push_back({obs_out, h->res_turn, pose_actions, exec});
+                    } else { exec = nullptr; h->use_graph = false; cudaGetLastError(); }
+                    if (graph) cudaGraphDestroy(graph);
+                } else h->use_graph = false;
+                h->launches = before;                       // counted when the graph is launched
+            }
+            if (exec) {
+                const cudaError_t e = cudaGraphLaunch(exec, s);
+                if (e != cudaSuccess) return fail(h, IRBPP_ECUDA, "cudaGraphLaunch: %s", cudaGetErrorString(e));
+                h->launches += 2;                           // scan + candidates kernel
+                h->scan_current = (P.K == 1);
+                launched = true;
+            }
         }
-    }
-    h->results_on_host = !on_device && h->host_results_mode != 2;
-    rc = launch(h, P, s); if (rc) return rc;
-    if (!on_device && h->host_results_mode == 1) {
-        const int n16 = (int)((h->results_bytes + 15) / 16);           // both blocks are allocated with 64 bytes of slack
-        irbpp_copy_block_kernel<<<8, 256, 0, s>>>(reinterpret_cast<uint4*>(h->results_mapped),
-                                                 reinterpret_cast<const uint4*>(h->results_dev), n16);
-        h->launches += 1;
+#endif
+        if (!launched) {
+            CUDA_TRY(h, cudaMemcpyAsync(h->actions_dev, h->actions_pinned, (size_t)P.N * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+            rc = launch(h, P, s); if (rc) return rc;
+        }
     }
     h->waiting_step = true; h->pending_stream = s;
     return IRBPP_OK;
@@ -544,7 +578,7 @@ int irbpp_step_wait(irbpp_handle h, irbpp_step_result* out) {
     if (!h->waiting_step) return fail(h, IRBPP_ESTATE, "not running an async step");   // vec_env.py:18-26
     cudaStream_t s = h->pending_stream;
     h->waiting_step = false;
-    if (out && !h->results_on_host)
+    if (out && !h->results_on_host)            // a device-resident step waited for with the host call: fetch the block
         CUDA_TRY(h, cudaMemcpyAsync(h->results_host, h->results_dev, h->results_bytes, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(h, cudaStreamSynchronize(s));
     if (out) {
@@ -742,6 +776,27 @@ int irbpp_debug_hulls(irbpp_handle h, const double* posZValid, const double* mas
 }
 
 int64_t irbpp_launch_count(irbpp_handle h) { return h ? h->launches : 0; }
+
+// ---- compact form of the location observation for the rollout gather (csrc/irbpp_pack.cuh) --------------------
+int irbpp_packed_obs_bytes(int32_t selected_action) { return selected_action > 0 ? packed_words(selected_action) * 4 : -1; }
+
+int irbpp_pack_observations(const float* obs, int64_t obs_stride, int32_t selected_action, int32_t n, void* packed, void* stream) {
+    if (!obs || !packed || n <= 0 || selected_action <= 0 || obs_stride < selected_action * 5 + 9 + 1024)
+        return fail(nullptr, IRBPP_EINVAL, "bad pack arguments");
+    irbpp_pack_obs_kernel<<<n, 128, 0, (cudaStream_t)stream>>>(obs, obs_stride, selected_action, reinterpret_cast<uint32_t*>(packed), n);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(nullptr, IRBPP_ECUDA, "kernel launch: %s", cudaGetErrorString(e));
+    return IRBPP_OK;
+}
+
+int irbpp_unpack_observations(const void* packed, int32_t selected_action, int32_t n, float* obs, int64_t obs_stride, void* stream) {
+    if (!obs || !packed || n <= 0 || selected_action <= 0 || obs_stride < selected_action * 5 + 9 + 1024)
+        return fail(nullptr, IRBPP_EINVAL, "bad unpack arguments");
+    irbpp_unpack_obs_kernel<<<n, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint32_t*>(packed), selected_action, obs, obs_stride, n);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(nullptr, IRBPP_ECUDA, "kernel launch: %s", cudaGetErrorString(e));
+    return IRBPP_OK;
+}
 
 // ---- point clouds of the next items (csrc/irbpp_pointnet.cuh) ----------------------------------
 static int pn_common(PointNetParams& Q, const float* shape_array, int32_t S, int32_t P, const float* obs, int64_t obs_stride,

@@ -104,6 +104,66 @@ class AsyncRolloutGather(object):
         return out
 
 
+class CompactRolloutGather(object):
+    """AsyncRolloutGather over the compact form of the location observation (``csrc/irbpp_pack.cuh``: 7 184 instead of
+    14 132 bytes per bin at selectedAction = 500, lossless): pack on the sender, all-gather the packed rows, expand on the
+    receiver.  The gather's duration -- and with it the stretch of steps it disturbs -- halves; the two extra kernels
+    cost ~0.02 ms (pack, 4096 bins) and ~0.1 ms (expanding 8 x 4096 bins).  CUDA tensors only (the kernels are in libirbpp)."""
+
+    def __init__(self, selected_action, world_size=None, group=None):
+        import ctypes
+        from . import _lib
+        self._lib = _lib.load()
+        self._ct = ctypes
+        self.sel = int(selected_action)
+        self.row_bytes = int(self._lib.irbpp_packed_obs_bytes(self.sel))
+        self._inner = AsyncRolloutGather(world_size, group)
+        self.world = self._inner.world
+        self._full = [None, None]
+        self._turn = 0
+        self._pending = None
+        self.kind = "nccl all-gather of packed observations (%d of %d bytes per bin)" % (self.row_bytes, (self.sel * 5 + 9 + 1024) * 4)
+
+    @property
+    def events(self):
+        return self._inner.events
+
+    def start(self, local):
+        import torch
+        n = local.shape[0]
+        packed = torch.empty((n, self.row_bytes), dtype=torch.uint8, device=local.device)
+        st = torch.cuda.current_stream(local.device).cuda_stream
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        rc = self._lib.irbpp_pack_observations(local.data_ptr(), local.stride(0), self.sel, n, packed.data_ptr(), st)
+        p1.record()
+        self.pack_events = (p0, p1)                          # the pack and the expansion run on the caller's stream
+        if rc != 0:
+            raise RuntimeError("irbpp_pack_observations failed: %s" % self._lib.irbpp_last_error(None))
+        self._inner.start(packed)
+        self._pending = (n, local.shape[1], local.device)
+
+    def finish(self):
+        import torch
+        n, width, dev = self._pending
+        gathered = self._inner.finish()                      # [world * n, row_bytes] uint8, current stream waits for it
+        t = self._turn
+        self._turn ^= 1
+        full = self._full[t]
+        if full is None or full.shape != (self.world * n, width):
+            full = self._full[t] = torch.empty((self.world * n, width), dtype=torch.float32, device=dev)
+        st = torch.cuda.current_stream(dev).cuda_stream
+        u0, u1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        u0.record()
+        rc = self._lib.irbpp_unpack_observations(gathered.data_ptr(), self.sel, self.world * n, full.data_ptr(), full.stride(0), st)
+        u1.record()
+        self.unpack_events = (u0, u1)
+        if rc != 0:
+            raise RuntimeError("irbpp_unpack_observations failed: %s" % self._lib.irbpp_last_error(None))
+        self._pending = None
+        return full
+
+
 class PeerCopyGather(object):
     """The rollout gather as peer-to-peer copies by the COPY ENGINES instead of an NCCL kernel: every rank pushes its
     shard straight into every peer's gathered buffer over NVLink (the buffers are exchanged once as CUDA IPC handles),

@@ -244,15 +244,6 @@ def test_emulated_24_rotations(emu):
     _replay(emu, "episode_rot24", 3)
 
 
-@pytest.mark.parametrize("results,actions", [("kernel", "memcpy"), ("memcpy", "mapped")])
-def test_emulated_host_transport_knobs(emu, monkeypatch, results, actions):
-    """IRBPP_HOST_RESULTS / IRBPP_HOST_ACTIONS (experiment knobs of the host path, read at irbpp_create):
-    the alternative transports deliver the same step results."""
-    monkeypatch.setenv("IRBPP_HOST_RESULTS", results)
-    monkeypatch.setenv("IRBPP_HOST_ACTIONS", actions)
-    _replay(emu, "episode_blockout", 6)
-
-
 def _kat_inputs():
     """The SURVEY section 4 known-answer maps (8 x 8) embedded in the 16 x 16 action grid, masked outside."""
     d = load_golden("kats")
@@ -361,3 +352,20 @@ def test_emulated_point_cloud_features_match_torch_fp32(emu):
                                             _P(ids) if use_ids else None, B, U64(seed), U64(counter), n_pts, _P(W1), _P(b1), _P(W2),
                                             _P(b2), ctypes.c_float(0.01), _P(keys), _P(feat), None) == 0
         assert np.all(np.abs(feat - want_feat) <= 1e-5 * (1 + np.abs(want_feat))), np.abs(feat - want_feat).max()
+
+
+def test_emulated_packed_observations_round_trip(emu):
+    """csrc/irbpp_pack.cuh: the compact form the rollout gather sends must expand to the very same float32 observation
+    (every golden BlockOut / irregular / truncation observation; ragged selectedAction)."""
+    for name in ("episode_blockout", "episode_irregular", "episode_truncate"):
+        d = load_golden(name)
+        sel = int(d["selectedAction"])
+        obs = np.ascontiguousarray(d["obs"].reshape(-1, d["obs"].shape[-1]).astype(np.float32))
+        n, width = obs.shape
+        nb = emu.emu_irbpp_packed_obs_bytes(sel)
+        assert nb % 16 == 0 and nb < width * 4
+        packed = np.zeros((n, nb), np.uint8)
+        assert emu.emu_irbpp_pack_observations(_P(obs), ctypes.c_int64(width), sel, n, _P(packed), None) == 0
+        back = np.full((n, width), -7.0, np.float32)
+        assert emu.emu_irbpp_unpack_observations(_P(packed), sel, n, _P(back), ctypes.c_int64(width), None) == 0
+        assert np.array_equal(back, obs), name

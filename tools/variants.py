@@ -5,20 +5,10 @@
         -> irbpp_b200/lib/libirbpp_coop.so, libirbpp_fine.so   (they travel with gpurun like the default .so)
     python tools/variants.py bench coop            # GPU: parity tests of the episode goldens + bench.py per variant
 
-First GPU call of a round (everything below is checked under the CUDA emulator, none of it is timed yet):
-    python tools/variants.py build coop=-DIRBPP_COOP_APPROX split=-DIRBPP_SPLIT_APPLY \\
-        split10=-DIRBPP_SPLIT_APPLY,-DIRBPP_SCAN_MIN_CTAS=10 both=-DIRBPP_COOP_APPROX,-DIRBPP_SPLIT_APPLY \\
-        pf=-DIRBPP_PREFETCH_NEXT=1184
-    python tools/variants.py bench coop split split10 both pf
-
-Known switches (csrc/): IRBPP_COOP_APPROX  contours of >= 17 points by a whole warp (dp_keep_warp)
-                        IRBPP_PROBE_FINE   slots 4-7 of the phase counters time the sub-phases of phase C
-                        IRBPP_SPLIT_APPLY  phase A (apply the action) as its own one-warp-per-bin kernel in front of the scan
-                        IRBPP_PREFETCH_NEXT=1184   scan CTAs prefetch the inputs of the bin a later wave handles into L2
-                        IRBPP_ENVS_PER_CTA / IRBPP_CAND_WARPS / IRBPP_SCAN_MIN_CTAS   CTA shapes
-Run-time knobs of the host path (environment, read at irbpp_create; defaults = what bench.py's e2e measures):
-    IRBPP_HOST_RESULTS=stores|kernel|memcpy   per-bin PCIe stores (default) | one coalesced copy kernel | D2H memcpy in step_wait
-    IRBPP_HOST_ACTIONS=mapped|memcpy          kernel reads the pinned actions over PCIe (default) | H2D memcpy in front of it
+Known build switches (csrc/): IRBPP_PROBE_FINE   slots 4-7 of the phase counters time the sub-phases of phase C
+                              IRBPP_PROBE_TRACE  per-CTA timelines of the candidates kernel (tools/cta_trace.py)
+                              IRBPP_TASKS_PER_LANE / IRBPP_ENVS_PER_CTA / IRBPP_CAND_WARPS / IRBPP_SCAN_MIN_CTAS   CTA shapes
+Run-time knob of the host path (read at irbpp_create): IRBPP_GRAPH=0   separate launches instead of one CUDA graph per step
 """
 import json
 import os
