@@ -33,13 +33,6 @@ struct irbpp_env {
     bool scan_current = false;        // the scan scratch holds the drop heights of every bin's cur_item
     int32_t* heur_pose_dev = nullptr; int64_t* heur_index_dev = nullptr;
     bool results_on_host = false;           // the pending step wrote its results straight to the host mirror
-    // The host step as ONE CUDA graph launch (H2D copy of the actions + scan kernel + candidates kernel with its
-    // programmatic dependency): instantiated per (observation buffer, host result block, action kind) on first use
-    // -- callers cycle through two or three observation buffers -- and replayed afterwards.  IRBPP_GRAPH=0 disables.
-    struct StepGraph { float* obs; int turn; int pose; cudaGraphExec_t exec; };
-    std::vector<StepGraph> step_graphs;
-    cudaStream_t capture_stream = nullptr;
-    bool use_graph = true;
     cudaStream_t pending_stream = nullptr;
     int64_t launches = 0;
     // device allocations
@@ -61,6 +54,30 @@ struct irbpp_env {
     TileEntry* tiles_dev = nullptr;
     unsigned long long* phase_dev = nullptr;
 };
+
+// Every entry point runs on its handle's device and leaves the calling thread's current device as it found it: the
+// host framework (torch) tracks the current device itself, and a library that changes it behind its back makes the
+// caller's next `tensor.cuda()` land on another GPU (seen in a two-device test before this guard existed).
+struct DeviceGuard {
+    int prev = -1, cur = -1;
+    explicit DeviceGuard(int dev) : cur(dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DeviceGuard() { if (prev >= 0 && prev != cur) cudaSetDevice(prev); }
+};
+
+// device that owns a device pointer (the handle-free entry points run where their buffers live)
+static int device_of(const void* p) {
+#ifdef IRBPP_HOST_EMULATION
+    (void)p; return 0;
+#else
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type == cudaMemoryTypeDevice) return at.device;
+    cudaGetLastError();
+    int d = 0; cudaGetDevice(&d); return d;
+#endif
+}
 
 static int fail(irbpp_env* h, int code, const char* fmt, ...) {
     char buf[512];
@@ -90,13 +107,6 @@ static cudaError_t dev_alloc(irbpp_env* h, T** p, size_t count, bool zero = true
     return cudaSuccess;
 }
 
-
-static void drop_step_graphs(irbpp_env* h) {        // the instantiated step graphs hold copies of the launch parameters
-#ifndef IRBPP_HOST_EMULATION
-    for (auto& g : h->step_graphs) cudaGraphExecDestroy(g.exec);
-#endif
-    h->step_graphs.clear();
-}
 
 static void free_dev(irbpp_env* h, void* p) {
     if (!p) return;
@@ -159,12 +169,14 @@ int irbpp_create(const irbpp_config* cfg, irbpp_handle* out) {
         return fail(nullptr, IRBPP_ECUDA, "no CUDA device (%s); this library has no CPU path",
                     e == cudaSuccess ? "count 0" : cudaGetErrorString(e));
     if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, IRBPP_EINVAL, "bad device ordinal %d", cfg->device);
-    e = cudaSetDevice(cfg->device);
-    if (e != cudaSuccess) return fail(nullptr, IRBPP_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+    DeviceGuard guard(cfg->device);
+    {
+        int now = -1;
+        if (cudaGetDevice(&now) != cudaSuccess || now != cfg->device) return fail(nullptr, IRBPP_ECUDA, "cudaSetDevice(%d) failed", cfg->device);
+    }
 
     irbpp_env* h = new irbpp_env();
     h->cfg = *cfg;
-    if (const char* m = getenv("IRBPP_GRAPH")) h->use_graph = strcmp(m, "0") != 0;
     Params& P = h->P;
     memset(&P, 0, sizeof(P));
     const int N = cfg->num_envs;
@@ -225,10 +237,8 @@ int irbpp_create(const irbpp_config* cfg, irbpp_handle* out) {
 
 int irbpp_destroy(irbpp_handle h) {
     if (!h) return IRBPP_OK;
-    cudaSetDevice(h->cfg.device);
+    DeviceGuard guard(h->cfg.device);
     cudaDeviceSynchronize();
-    drop_step_graphs(h);
-    if (h->capture_stream) cudaStreamDestroy(h->capture_stream);
     for (void* p : h->dev_allocs) cudaFree(p);
     if (h->results_dev) cudaFree(h->results_dev);
     for (int t = 0; t < 2; ++t) if (h->results_host2[t]) cudaFreeHost(h->results_host2[t]);
@@ -352,9 +362,8 @@ int irbpp_load_shapes(irbpp_handle h, int32_t S, int32_t R, const int32_t* dims,
         }
         for (int r = 0; r < R; ++r) max_entries = std::max(max_entries, (int)srot[(size_t)s * R + r].ntiles);
     }
-    cudaSetDevice(c.device);
+    DeviceGuard guard(c.device);
     CUDA_TRY(h, cudaDeviceSynchronize());
-    drop_step_graphs(h);
     for (void* old : {(void*)h->srot_dev, (void*)h->Bs_dev, (void*)h->Ts_dev, (void*)h->vol_dev, (void*)h->rew_dev, (void*)h->tiles_dev})
         free_dev(h, old);                                                 // a reload replaces the previous pools
     CUDA_TRY(h, dev_alloc(h, &h->srot_dev, srot.size(), false));
@@ -383,7 +392,6 @@ int irbpp_load_shapes(irbpp_handle h, int32_t S, int32_t R, const int32_t* dims,
 
 // fresh per-bin state: cursors restart, every bin's first sequence entry is staged for its first draw
 static int restart_items(irbpp_env* h, const int32_t* ids, int32_t length) {
-    drop_step_graphs(h);
     std::vector<EnvState> st((size_t)h->P.N);
     memset(st.data(), 0, st.size() * sizeof(EnvState));
     if (ids) for (int e = 0; e < h->P.N; ++e) st[e].next_seq = ids[(size_t)e * length];
@@ -400,7 +408,7 @@ int irbpp_set_sequences(irbpp_handle h, const int32_t* ids, int32_t length) {
     const size_t n = (size_t)h->P.N * length;
     for (size_t i = 0; i < n; ++i)
         if (ids[i] < 0 || ids[i] >= h->P.S) return fail(h, IRBPP_EINVAL, "item id %d out of range at %zu", ids[i], i);
-    cudaSetDevice(h->cfg.device);
+    DeviceGuard guard(h->cfg.device);
     CUDA_TRY(h, cudaDeviceSynchronize());
     free_dev(h, h->seq_dev); h->seq_dev = nullptr;                       // a reload replaces the previous pool
     CUDA_TRY(h, dev_alloc(h, &h->seq_dev, n, false));
@@ -414,7 +422,7 @@ int irbpp_set_sequences(irbpp_handle h, const int32_t* ids, int32_t length) {
 int irbpp_set_item_rng(irbpp_handle h, uint64_t seed) {
     if (!h) return IRBPP_EINVAL;
     if (!h->shapes_loaded) return fail(h, IRBPP_ESTATE, "load shapes before the item generator");
-    cudaSetDevice(h->cfg.device);
+    DeviceGuard guard(h->cfg.device);
     int rc = restart_items(h, nullptr, 0); if (rc) return rc;
     h->P.seq = nullptr; h->P.L = 0; h->P.rng_seed = seed;
     h->sequences_set = true;
@@ -457,13 +465,12 @@ static int launch(irbpp_env* h, Params& P, cudaStream_t s) {
 static int ready(irbpp_env* h) {
     if (!h) return IRBPP_EINVAL;
     if (!h->shapes_loaded || !h->sequences_set) return fail(h, IRBPP_ESTATE, "shapes / sequences not loaded");
-    cudaError_t e = cudaSetDevice(h->cfg.device);
-    if (e != cudaSuccess) return fail(h, IRBPP_ECUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
     return IRBPP_OK;
 }
 
 int irbpp_reset(irbpp_handle h, const uint8_t* which, float* obs_out, void* stream) {
     int rc = ready(h); if (rc) return rc;
+    DeviceGuard guard(h->cfg.device);
     if (!obs_out) return fail(h, IRBPP_EINVAL, "obs_out is null");
     cudaStream_t s = (cudaStream_t)stream;
     if (h->waiting_step) {         // "Called reset() while waiting for the step to complete" (shmem_vec_env.py:61-63)
@@ -484,6 +491,7 @@ int irbpp_reset(irbpp_handle h, const uint8_t* which, float* obs_out, void* stre
 static int step_async_impl(irbpp_env* h, const int64_t* actions, int32_t on_device, float* obs_out, void* stream,
                            int pose_actions) {
     int rc = ready(h); if (rc) return rc;
+    DeviceGuard guard(h->cfg.device);
     if (!actions || !obs_out) return fail(h, IRBPP_EINVAL, "null argument");
     if (!h->was_reset) return fail(h, IRBPP_ESTATE, "step before reset");
     if (h->waiting_step) return fail(h, IRBPP_ESTATE, "already running an async step");   // vec_env.py:7-16
@@ -511,43 +519,10 @@ static int step_async_impl(irbpp_env* h, const int64_t* actions, int32_t on_devi
         P.h_done = reinterpret_cast<uint8_t*>(b); b += N;
         P.h_valid = reinterpret_cast<uint8_t*>(b); b += N;
         P.h_error = reinterpret_cast<uint8_t*>(b);
-        bool launched = false;
-#ifndef IRBPP_HOST_EMULATION
-        if (h->use_graph) {
-            cudaGraphExec_t exec = nullptr;
-            for (auto& g : h->step_graphs)
-                if (g.obs == obs_out && g.turn == h->res_turn && g.pose == pose_actions) { exec = g.exec; break; }
-            if (!exec) {
-                // record the three nodes on the library's own capture stream (the caller's may be the legacy default
-                // stream, which cannot capture); the graph itself is launched on the caller's stream
-                if (!h->capture_stream && cudaStreamCreateWithFlags(&h->capture_stream, cudaStreamNonBlocking) != cudaSuccess) h->use_graph = false;
-                cudaGraph_t graph = nullptr;
-                const int64_t before = h->launches;
-                if (h->use_graph && cudaStreamBeginCapture(h->capture_stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-                    cudaMemcpyAsync(h->actions_dev, h->actions_pinned, (size_t)P.N * sizeof(int64_t), cudaMemcpyHostToDevice, h->capture_stream);
-                    const int lrc = launch(h, P, h->capture_stream);
-                    const cudaError_t ec = cudaStreamEndCapture(h->capture_stream, &graph);
-                    if (lrc == IRBPP_OK && ec == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
-                        if (h->step_graphs.size() >= 8) { cudaGraphExecDestroy(h->step_graphs.front().exec); h->step_graphs.erase(h->step_graphs.begin()); }
-                        h->step_graphs.push_back({obs_out, h->res_turn, pose_actions, exec});
-                    } else { exec = nullptr; h->use_graph = false; cudaGetLastError(); }
-                    if (graph) cudaGraphDestroy(graph);
-                } else h->use_graph = false;
-                h->launches = before;                       // counted when the graph is launched
-            }
-            if (exec) {
-                const cudaError_t e = cudaGraphLaunch(exec, s);
-                if (e != cudaSuccess) return fail(h, IRBPP_ECUDA, "cudaGraphLaunch: %s", cudaGetErrorString(e));
-                h->launches += 2;                           // scan + candidates kernel
-                h->scan_current = (P.K == 1);
-                launched = true;
-            }
-        }
-#endif
-        if (!launched) {
-            CUDA_TRY(h, cudaMemcpyAsync(h->actions_dev, h->actions_pinned, (size_t)P.N * sizeof(int64_t), cudaMemcpyHostToDevice, s));
-            rc = launch(h, P, s); if (rc) return rc;
-        }
+        // (One CUDA graph per step -- H2D copy + both kernels, instantiated per observation buffer -- was measured:
+        // submit 12.8 -> 8.8 us, but the step's wait grew by as much, e2e 0.162 vs 0.155 ms; dropped.)
+        CUDA_TRY(h, cudaMemcpyAsync(h->actions_dev, h->actions_pinned, (size_t)P.N * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+        rc = launch(h, P, s); if (rc) return rc;
     }
     h->waiting_step = true; h->pending_stream = s;
     return IRBPP_OK;
@@ -575,6 +550,7 @@ static void host_views(irbpp_env* h, char* b, irbpp_step_result* out) {
 
 int irbpp_step_wait(irbpp_handle h, irbpp_step_result* out) {
     int rc = ready(h); if (rc) return rc;
+    DeviceGuard guard(h->cfg.device);
     if (!h->waiting_step) return fail(h, IRBPP_ESTATE, "not running an async step");   // vec_env.py:18-26
     cudaStream_t s = h->pending_stream;
     h->waiting_step = false;
@@ -591,6 +567,7 @@ int irbpp_step_wait(irbpp_handle h, irbpp_step_result* out) {
 
 int irbpp_step_wait_device(irbpp_handle h, irbpp_device_result* out) {
     int rc = ready(h); if (rc) return rc;
+    DeviceGuard guard(h->cfg.device);
     if (!h->waiting_step) return fail(h, IRBPP_ESTATE, "not running an async step");
     h->waiting_step = false;
     if (out) {
@@ -612,6 +589,7 @@ int irbpp_device_results(irbpp_handle h, irbpp_device_result* out) {
 int irbpp_get_action_candidates(irbpp_handle h, const int64_t* order_actions, int32_t on_device,
                                 float* loc_obs_out, void* stream) {
     int rc = ready(h); if (rc) return rc;
+    DeviceGuard guard(h->cfg.device);
     if (!order_actions || !loc_obs_out) return fail(h, IRBPP_EINVAL, "null argument");
     if (h->P.K <= 1) return fail(h, IRBPP_ESTATE, "get_action_candidates needs buffer_size > 1");
     if (!h->was_reset) return fail(h, IRBPP_ESTATE, "get_action_candidates before reset");
@@ -630,6 +608,7 @@ int irbpp_get_action_candidates(irbpp_handle h, const int64_t* order_actions, in
 
 int irbpp_get_all_possible_observation(irbpp_handle h, float* out, void* stream) {
     int rc = ready(h); if (rc) return rc;
+    DeviceGuard guard(h->cfg.device);
     if (!out) return fail(h, IRBPP_EINVAL, "null argument");
     if (h->P.K <= 1) return fail(h, IRBPP_ESTATE, "get_all_possible_observation needs buffer_size > 1");
     if (!h->was_reset) return fail(h, IRBPP_ESTATE, "called before reset");
@@ -644,6 +623,7 @@ int irbpp_get_all_possible_observation(irbpp_handle h, float* out, void* stream)
 int irbpp_heuristic_actions(irbpp_handle h, int32_t method, int32_t dir_idx, int32_t* poses_out, int64_t* index_out,
                             int32_t on_device, void* stream) {
     int rc = ready(h); if (rc) return rc;
+    DeviceGuard guard(h->cfg.device);
     if (method < 0 || method >= HEUR_COUNT) return fail(h, IRBPP_EINVAL, "unknown heuristic %d", method);
     if (dir_idx < 0 || dir_idx > 3) return fail(h, IRBPP_EINVAL, "dir_idx %d not in 0..3", dir_idx);   // space.py:167
     if (!h->was_reset || !h->scan_current)
@@ -673,6 +653,7 @@ int irbpp_heuristic_actions(irbpp_handle h, int32_t method, int32_t dir_idx, int
 
 int irbpp_debug_state(irbpp_handle h, double* heightmap, int32_t* queue, int32_t* cursor, int32_t* packed_count) {
     int rc = ready(h); if (rc) return rc;
+    DeviceGuard guard(h->cfg.device);
     CUDA_TRY(h, cudaDeviceSynchronize());
     const int N = h->P.N;
     if (heightmap) {
@@ -699,6 +680,7 @@ int irbpp_debug_state(irbpp_handle h, double* heightmap, int32_t* queue, int32_t
 
 int irbpp_debug_set_heightmap(irbpp_handle h, const double* heightmap) {
     int rc = ready(h); if (rc) return rc;
+    DeviceGuard guard(h->cfg.device);
     if (!heightmap) return fail(h, IRBPP_EINVAL, "null argument");
     const int N = h->P.N;
     std::vector<double> raw((size_t)N * HX * HY);
@@ -748,6 +730,7 @@ static int debug_run(irbpp_env* h, Params& P, double* posZmap, double* posZValid
 int irbpp_debug_scan(irbpp_handle h, const int32_t* item_ids, double* posZmap, double* posZValid,
                      double* naiveMask, double* cand, int32_t* num_hull) {
     int rc = ready(h); if (rc) return rc;
+    DeviceGuard guard(h->cfg.device);
     if (!item_ids) return fail(h, IRBPP_EINVAL, "null argument");
     for (int i = 0; i < h->P.N; ++i)
         if (item_ids[i] < 0 || item_ids[i] >= h->P.S) return fail(h, IRBPP_EINVAL, "item id out of range");
@@ -763,6 +746,7 @@ int irbpp_debug_scan(irbpp_handle h, const int32_t* item_ids, double* posZmap, d
 
 int irbpp_debug_hulls(irbpp_handle h, const double* posZValid, const double* mask, double* cand, int32_t* num_hull) {
     int rc = ready(h); if (rc) return rc;
+    DeviceGuard guard(h->cfg.device);
     if (!posZValid || !mask) return fail(h, IRBPP_EINVAL, "null argument");
     const size_t nm = (size_t)h->P.N * h->P.R * NPOSE;
     std::vector<uint32_t> mb((size_t)h->P.N * h->P.R * 8, 0u);
@@ -783,6 +767,7 @@ int irbpp_packed_obs_bytes(int32_t selected_action) { return selected_action > 0
 int irbpp_pack_observations(const float* obs, int64_t obs_stride, int32_t selected_action, int32_t n, void* packed, void* stream) {
     if (!obs || !packed || n <= 0 || selected_action <= 0 || obs_stride < selected_action * 5 + 9 + 1024)
         return fail(nullptr, IRBPP_EINVAL, "bad pack arguments");
+    DeviceGuard guard(device_of(obs));
     irbpp_pack_obs_kernel<<<n, 128, 0, (cudaStream_t)stream>>>(obs, obs_stride, selected_action, reinterpret_cast<uint32_t*>(packed), n);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(nullptr, IRBPP_ECUDA, "kernel launch: %s", cudaGetErrorString(e));
@@ -792,6 +777,7 @@ int irbpp_pack_observations(const float* obs, int64_t obs_stride, int32_t select
 int irbpp_unpack_observations(const void* packed, int32_t selected_action, int32_t n, float* obs, int64_t obs_stride, void* stream) {
     if (!obs || !packed || n <= 0 || selected_action <= 0 || obs_stride < selected_action * 5 + 9 + 1024)
         return fail(nullptr, IRBPP_EINVAL, "bad unpack arguments");
+    DeviceGuard guard(device_of(obs));
     irbpp_unpack_obs_kernel<<<n, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const uint32_t*>(packed), selected_action, obs, obs_stride, n);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(nullptr, IRBPP_ECUDA, "kernel launch: %s", cudaGetErrorString(e));
@@ -817,6 +803,7 @@ int irbpp_sample_point_clouds(const float* shape_array, int32_t S, int32_t P, co
     int rc = pn_common(Q, shape_array, S, P, obs, obs_stride, item_col, ids, B, seed, counter, n_points); if (rc) return rc;
     if (!out) return fail(nullptr, IRBPP_EINVAL, "null output");
     Q.out = out; Q.indices_out = indices_out;
+    DeviceGuard guard(device_of(shape_array));
     const int64_t n = (int64_t)B * n_points;
     const int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 16);
     irbpp_cloud_gather_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(Q);
@@ -833,9 +820,9 @@ int irbpp_shape_features(const float* shape_array, int32_t S, int32_t P, const f
     int rc = pn_common(Q, shape_array, S, P, obs, obs_stride, item_col, ids, B, seed, counter, n_points); if (rc) return rc;
     if (!W1 || !b1 || !W2 || !b2 || !scratch_keys || !out) return fail(nullptr, IRBPP_EINVAL, "null argument");
     Q.W1 = W1; Q.b1 = b1; Q.W2 = W2; Q.b2 = b2; Q.slope = negative_slope; Q.feat_keys = scratch_keys; Q.out = out;
-    int dev = 0;
-    cudaError_t e = cudaGetDevice(&dev);
-    if (e == cudaSuccess) e = raise_dynamic_smem(dev, 2, PN_SMEM_BYTES);
+    const int dev = device_of(shape_array);
+    DeviceGuard guard(dev);
+    cudaError_t e = raise_dynamic_smem(dev, 2, PN_SMEM_BYTES);
     if (e != cudaSuccess) return fail(nullptr, IRBPP_ECUDA, "shape encoder set-up: %s", cudaGetErrorString(e));
     cudaStream_t s = (cudaStream_t)stream;
     irbpp_pn_init_kernel<<<(S * PN_H + 255) / 256, 256, 0, s>>>(scratch_keys, S * PN_H);
@@ -850,7 +837,7 @@ int irbpp_shape_features(const float* shape_array, int32_t S, int32_t P, const f
 
 int irbpp_debug_phase_cycles(irbpp_handle h, int32_t enable, uint64_t* out8) {
     if (!h) return IRBPP_EINVAL;
-    cudaSetDevice(h->cfg.device);
+    DeviceGuard guard(h->cfg.device);
 #ifdef IRBPP_PROBE_TRACE
     const size_t trace_words = 8 + ((size_t)h->P.N * h->P.K + 1) * 8;     // profiling build: per-CTA timelines behind the counters
 #else

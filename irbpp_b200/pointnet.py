@@ -65,6 +65,8 @@ class DeviceShapeClouds(object):
         t = obs_or_ids
         if not isinstance(t, torch.Tensor) or not t.is_cuda:
             raise ValueError("expected a CUDA tensor: the observations [B, obs_len] or int item ids [B]")
+        if t.device != self.device:
+            raise ValueError("observations live on %s, the point clouds on %s" % (t.device, self.device))
         if t.dtype in (torch.int32, torch.int64):
             ids = t.reshape(-1).to(torch.int32).contiguous()
             return ids, 0, 0, 0, ids.data_ptr(), ids.numel()

@@ -156,8 +156,6 @@ typedef int cudaError_t;
 constexpr cudaError_t cudaSuccess = 0;
 constexpr cudaError_t cudaErrorInvalidDevice = 101;
 typedef void* cudaStream_t;
-typedef void* cudaGraphExec_t;          // never instantiated under the emulation (irbpp.cu guards the graph path)
-static inline int cudaStreamDestroy(cudaStream_t) { return 0; }
 enum cudaMemcpyKind { cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice };
 constexpr unsigned cudaHostAllocMapped = 2;
 enum cudaFuncAttribute { cudaFuncAttributeMaxDynamicSharedMemorySize };

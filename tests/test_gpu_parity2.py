@@ -238,6 +238,7 @@ def test_handles_on_two_devices():
             assert np.array_equal(e.step(acts)[0].cpu().numpy(), want), t
     for e in envs:
         e.close()
+    assert torch.cuda.current_device() == 0          # the library leaves the caller's current device alone
 
 
 def test_point_cloud_sampling_and_shape_features_match_torch_fp32():
@@ -253,7 +254,7 @@ def test_point_cloud_sampling_and_shape_features_match_torch_fp32():
     shape_array = (torch.rand((S, Pn, 3), generator=g) * 0.15).float()
     ids = torch.randint(0, S, (B,), generator=g)
     obs = torch.zeros((B, 3533)); obs[:, 2500] = ids.float()
-    obs = obs.cuda()
+    obs = obs.to("cuda:0")
     enc = torch.nn.Sequential(torch.nn.Linear(3, 128), torch.nn.LeakyReLU(), torch.nn.Linear(128, 128), torch.nn.LeakyReLU()).cuda()
     clouds = DeviceShapeClouds(shape_array, device="cuda:0", n_points=1024, seed=11)
     for counter in (0, 1, 7):

@@ -88,7 +88,6 @@ def run(name, n, steps, burn, e2e):
             torch.cuda.synchronize()
             t += time.perf_counter() - t0
         out["e2e_ms"] = round(1e3 * t / steps, 5)
-        out["graph"] = os.environ.get("IRBPP_GRAPH", "1")
     print(json.dumps(out), flush=True)
     env.close()
 

@@ -8,7 +8,6 @@
 Known build switches (csrc/): IRBPP_PROBE_FINE   slots 4-7 of the phase counters time the sub-phases of phase C
                               IRBPP_PROBE_TRACE  per-CTA timelines of the candidates kernel (tools/cta_trace.py)
                               IRBPP_TASKS_PER_LANE / IRBPP_ENVS_PER_CTA / IRBPP_CAND_WARPS / IRBPP_SCAN_MIN_CTAS   CTA shapes
-Run-time knob of the host path (read at irbpp_create): IRBPP_GRAPH=0   separate launches instead of one CUDA graph per step
 """
 import json
 import os
