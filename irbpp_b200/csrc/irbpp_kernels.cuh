@@ -1013,9 +1013,13 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
         constexpr int TPL = TASKS_PER_LANE;
         constexpr int BATCH = CAND_THREADS * TPL;
         static_assert(FAST_CAP * 32 + (TPL - 1) * 32 * 32 <= WS_MIN_BYTES, "the task slots' point buffers share the warp scratch");
+        // points per contour in task slots 1, 2: what the warp scratch holds beside slot 0's 64-point buffers -- 32 at
+        // R <= 4 (4 KB per warp), 64 from R = 8 on (the scratch grows with R for phase D's lists), where long contours
+        // in the cheaper slots are not rare and every overflow is a serial redo
+        const int cap12 = min(FAST_CAP, (P.ws_bytes - FAST_CAP * 32) / ((TPL > 1 ? TPL - 1 : 1) * 32));
         auto slot_scratch = [&](int owner) {               // point buffer of task slot `owner` (j * CAND_THREADS + thread)
             const int jj = owner / CAND_THREADS, th = owner - jj * CAND_THREADS;
-            return ws_base + (size_t)(th >> 5) * P.ws_bytes + (jj == 0 ? 0 : FAST_CAP * 32 + (jj - 1) * 32 * 32) + (th & 31);
+            return ws_base + (size_t)(th >> 5) * P.ws_bytes + (jj == 0 ? 0 : FAST_CAP * 32 + (jj - 1) * cap12 * 32) + (th & 31);
         };
         for (int mb = 0; mb < ntask; mb += BATCH) {
             int tk[TPL];                                    // slot << 8 | x << 4 | y of my tasks, -1: none
@@ -1049,7 +1053,7 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
                     StridedScratch<32, FAST_CAP> sc;
                     sc.b = slot_scratch(jt * CAND_THREADS + tid);
                     sc.kept = 0;
-                    n = follow_outer_rows(sc, S.slots + slot * ROWS_WORDS, x, y, area2, jt == 0 ? FAST_CAP : 32);
+                    n = follow_outer_rows(sc, S.slots + slot * ROWS_WORDS, x, y, area2, jt == 0 ? FAST_CAP : cap12);
                 }
                 const bool keep = has && n != -2 && area2 <= 0;        // a raster-first start of an outer border
                 if (keep && n < 0) ovf_bits |= 1u << jt;
