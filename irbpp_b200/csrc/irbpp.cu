@@ -207,6 +207,7 @@ int irbpp_create(const irbpp_config* cfg, irbpp_handle* out) {
     TRY_ALLOC(dev_alloc(h, &P.maskbits, units * P.R * 8));
     TRY_ALLOC(dev_alloc(h, &P.bitmaps, units * P.R * MAX_LEVELS * 8));
     TRY_ALLOC(dev_alloc(h, &P.nlevels, units * P.R));
+    if (!lists_in_smem(P.R)) TRY_ALLOC(dev_alloc(h, &P.dlist, units * 2 * P.R * NPOSE));
     // result block (8-byte fields first so every array stays aligned)
     h->results_bytes = (size_t)N * (8 + 8 + 4 + 4 + 4 + 1 + 1 + 1);
     TRY_ALLOC(cudaMalloc(&h->results_dev, h->results_bytes + 64));

@@ -154,6 +154,7 @@ struct Params {
     const uint8_t* which;                // MODE_RESET (NULL = all)
     const int32_t* dbg_items;            // MODE_DEBUG_SCAN
     int32_t ws_bytes;                    // per-warp scratch of the candidates kernel (ws_bytes_for(R))
+    uint16_t* dlist;                     // [units][2][R*256] phase D lists for R > LISTS_SMEM_MAX_R, else NULL
     int32_t pose_actions;                // MODE_STEP: actions are flat poses (rot*256 + lx*16 + ly), not candidate rows
     int32_t heur_method, heur_dir;       // heuristic kernel: Heuristic, dirIdx 0..3 (space.py:162-166)
     int32_t* heur_pose;                  // [N][3] rot, lx, ly
@@ -814,10 +815,14 @@ __global__ void __launch_bounds__(CTA_THREADS) irbpp_heuristic_kernel(const Para
 constexpr int WS_MIN_BYTES = 4096;
 static_assert(WS_MIN_BYTES >= 2 * BIG_CAP && WS_MIN_BYTES >= FAST_CAP * 32, "overflow buffers must fit the lane scratch");
 static_assert(CAND_THREADS * ROWS_WORDS >= ENVS_PER_CTA * 128, "phase D's rank histograms reuse the image slots");
-// (Measured and dropped, profiles/README.md: keeping phase D's lists in a global scratch for R > 4 so that the grid
-// of an R = 8 run fits one wave, and fewer bins per CTA for many rotations -- both slower than this form.)
+// Phase D's candidate list + bucket-sorted index list (2 x uint16 per pose of the bin) live in the warp scratch up to
+// R = 8 (8 KB per warp; measured faster there than a global scratch, profiles/README.md).  Beyond that the scratch
+// would decide the residency -- 24 KB per warp at R = 24 leave 2 CTAs = 8 warps per SM and every phase of the kernel
+// starves for latency hiding -- so the lists move to a global scratch (Params::dlist, L2 resident).
+constexpr int LISTS_SMEM_MAX_R = 8;
+__host__ __device__ inline bool lists_in_smem(int R) { return R <= LISTS_SMEM_MAX_R; }
 __host__ __device__ inline int ws_bytes_for(int R) {
-    const int need = R * NPOSE * 4;                      // uint16 list + uint16 sorted list for every pose
+    const int need = lists_in_smem(R) ? R * NPOSE * 4 : 0;     // uint16 list + uint16 sorted list for every pose
     return ((need > WS_MIN_BYTES ? need : WS_MIN_BYTES) + 15) & ~15;
 }
 
@@ -1213,8 +1218,9 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
         // rows in rotation order, then (col, row) ascending == bit order of the per-rotation sets.
         // Pass 1 compacts the set bits into a list (no memory loads); pass 2 gives every lane one
         // candidate, so the height gathers of 32 candidates are in flight together.
-        uint16_t* list = reinterpret_cast<uint16_t*>(W_pts);          // lane scratch is idle now
-        const int LIST_CAP = P.ws_bytes / 4;                          // list + bucket-sorted index list; >= R * 256 >= Ktot
+        // candidate list + bucket-sorted index list: the (now idle) lane scratch, or the pair's slice of the global scratch
+        const int LIST_CAP = P.dlist ? R * NPOSE : P.ws_bytes / 4;    // >= R * 256 >= Ktot
+        uint16_t* list = P.dlist ? P.dlist + (int64_t)env * 2 * LIST_CAP : reinterpret_cast<uint16_t*>(W_pts);
         auto cell_of = [](int e) { const int b = e & 255; return (e >> 8) * NPOSE + (b & 15) * 16 + (b >> 4); };
         {
             for (int r = 0; r < R; ++r) {

@@ -142,7 +142,7 @@ def _replay(lib, name, steps):
 
 
 @pytest.mark.parametrize("name,steps", [("episode_blockout", 12), ("episode_cube", 14), ("episode_irregular", 5),
-                                        ("episode_truncate", 6), ("episode_buffered", 6), ("episode_buffered10", 5)])
+                                        ("episode_truncate", 6), ("episode_buffered", 6), ("episode_buffered10", 5), ("episode_rot24", 3)])
 def test_emulated_kernels_replay_reference_episodes(emu, name, steps):
     _replay(emu, name, steps)
 
