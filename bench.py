@@ -455,8 +455,9 @@ def main_gpu(args):
     gatherer = None
     if world > 1:          # IRBPP_GATHER: compact (default: NCCL all-gather of the packed observations, expanded on arrival) | nccl (plain) | peer (copy-engine pushes, CUDA IPC)
         kind = os.environ.get("IRBPP_GATHER", "compact" if k == 1 else "nccl")
-        gatherer = (sharding.PeerCopyGather(world) if kind == "peer" else
-                    sharding.CompactRolloutGather(SEL, world) if kind == "compact" else sharding.AsyncRolloutGather(world))
+        gatherer = (sharding.PeerCopyGather(world) if kind == "peer" else sharding.SymmMemGather(world) if kind == "symm" else
+                    sharding.CompactRolloutGather(SEL, world) if kind == "compact" else
+                    sharding.AsyncRolloutGather(world, point_to_point=(kind == "sendrecv")))
     gather_alone_ms = 0.0
     if world > 1:                                   # warm-up of the rollout-end collective (NCCL channel setup) + its stand-alone time
         for _ in range(2):

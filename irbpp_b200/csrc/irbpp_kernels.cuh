@@ -814,7 +814,8 @@ __global__ void __launch_bounds__(CTA_THREADS) irbpp_heuristic_kernel(const Para
 // size grows with the rotation count (a bin can have up to R * 256 candidates).
 constexpr int WS_MIN_BYTES = 4096;
 static_assert(WS_MIN_BYTES >= 2 * BIG_CAP && WS_MIN_BYTES >= FAST_CAP * 32, "overflow buffers must fit the lane scratch");
-static_assert(CAND_THREADS * ROWS_WORDS >= ENVS_PER_CTA * 128, "phase D's rank histograms reuse the image slots");
+constexpr int RANK_BUCKETS = 256;                        // height buckets of the phase-D truncation ranking (per warp: bases + cursors)
+static_assert(RANK_BUCKETS % 32 == 0 && CAND_THREADS * ROWS_WORDS >= ENVS_PER_CTA * 2 * RANK_BUCKETS, "phase D's rank histograms reuse the image slots");
 // Phase D's candidate list + bucket-sorted index list (2 x uint16 per pose of the bin) live in the warp scratch up to
 // R = 8 (8 KB per warp; measured faster there than a global scratch, profiles/README.md).  Beyond that the scratch
 // would decide the residency -- 24 KB per warp at R = 24 leave 2 CTAs = 8 warps per SM and every phase of the kernel
@@ -1244,52 +1245,84 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
                 }
             } else {
                 // More candidates than rows: keep the `sel` lowest heights, ties by original order (stable
-                // argsort; binPhy.py:209-212).  Exact ranks from a monotone bucketing of the heights: a
-                // candidate's rank = (candidates in lower buckets) + (its rank inside its own bucket), so
-                // each candidate is compared only with its bucket instead of with all K.
-                uint16_t* sorted = list + LIST_CAP;                  // second half of the lane scratch
-                int32_t* hist = reinterpret_cast<int32_t*>(S.slots) + warp * 128;   // image slots are idle now; [0,64): counts, [64,128): running offsets
-                auto bucket_of = [&](double H) { const int v = (int)((H + 0.32) * 100.0); return v < 0 ? 0 : (v > 63 ? 63 : v); };
-                hist[lane] = 0; hist[32 + lane] = 0;
-                __syncwarp();
+                // argsort; binPhy.py:209-212).  Exact ranks without a full sort: the feasible candidates are
+                // bucketed by a monotone map of their height (256 buckets over [min, max] of this bin), a
+                // candidate's rank = (candidates in lower buckets) + (its rank inside its own bucket), so it is
+                // compared only with its bucket; the infeasible ones all carry POSZ_INVALID, i.e. they follow the
+                // feasible ones in list order, which a running ballot count gives directly.  List entries grow
+                // with the list index, so "earlier in the list" is a comparison of the entries themselves.
+                uint16_t* sorted = list + LIST_CAP;                  // second half of the scratch: entries grouped by bucket
+                int32_t* hist = reinterpret_cast<int32_t*>(S.slots) + warp * (2 * RANK_BUCKETS);   // image slots are idle now
+                double hmin = POSZ_INVALID, hmax = -POSZ_INVALID;
+                int nvalid = 0;
                 for (int i = lane; i < Ktot; i += 32) {
                     bool m; const double H = height_of(cell_of(list[i]), m);
-                    atomicAdd(&hist[bucket_of(H)], 1);
+                    if (m) { hmin = fmin(hmin, H); hmax = fmax(hmax, H); ++nvalid; }
                 }
-                __syncwarp();
-                {   // exclusive prefix over the 64 buckets
-                    const int h0 = hist[lane], h1 = hist[32 + lane];
-                    int i0 = h0, i1 = h1;
 #pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const int t0 = __shfl_up_sync(0xffffffffu, i0, o), t1 = __shfl_up_sync(0xffffffffu, i1, o);
-                        if (lane >= o) { i0 += t0; i1 += t1; }
-                    }
-                    const int tot0 = __shfl_sync(0xffffffffu, i0, 31);
-                    __syncwarp();
-                    hist[lane] = i0 - h0; hist[32 + lane] = tot0 + i1 - h1;            // bucket bases
-                    hist[64 + lane] = i0 - h0; hist[96 + lane] = tot0 + i1 - h1;      // fill cursors
+                for (int o = 16; o; o >>= 1) {
+                    hmin = fmin(hmin, __shfl_xor_sync(0xffffffffu, hmin, o));
+                    hmax = fmax(hmax, __shfl_xor_sync(0xffffffffu, hmax, o));
+                    nvalid += __shfl_xor_sync(0xffffffffu, nvalid, o);
                 }
+                const double scale = hmax > hmin ? (double)RANK_BUCKETS / (hmax - hmin) : 0.0;
+                auto bucket_of = [&](double H) { const int v = (int)((H - hmin) * scale); return v > RANK_BUCKETS - 1 ? RANK_BUCKETS - 1 : v; };
+                for (int b = lane; b < RANK_BUCKETS; b += 32) hist[b] = 0;
                 __syncwarp();
                 for (int i = lane; i < Ktot; i += 32) {
                     bool m; const double H = height_of(cell_of(list[i]), m);
-                    sorted[atomicAdd(&hist[64 + bucket_of(H)], 1)] = (uint16_t)i;
+                    if (m) atomicAdd(&hist[bucket_of(H)], 1);
+                }
+                __syncwarp();
+                {   // exclusive prefix over the buckets: lane l owns buckets [l * BPL, (l + 1) * BPL)
+                    constexpr int BPL = RANK_BUCKETS / 32;
+                    int c[BPL], tot = 0;
+#pragma unroll
+                    for (int q = 0; q < BPL; ++q) { c[q] = hist[lane * BPL + q]; tot += c[q]; }
+                    int inc = tot;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const int t0 = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t0; }
+                    int base = inc - tot;
+                    __syncwarp();
+#pragma unroll
+                    for (int q = 0; q < BPL; ++q) {
+                        hist[lane * BPL + q] = base;                          // bucket bases
+                        hist[RANK_BUCKETS + lane * BPL + q] = base;           // fill cursors
+                        base += c[q];
+                    }
                 }
                 __syncwarp();
                 for (int i = lane; i < Ktot; i += 32) {
                     const int e = list[i];
-                    const int b = e & 255;
                     bool m; const double H = height_of(cell_of(e), m);
-                    const int bk = bucket_of(H);
-                    const int lo = hist[bk], hi = hist[64 + bk];        // this bucket's segment of `sorted`
-                    if (lo >= sel) continue;                             // everything in it ranks beyond the table
-                    int rank = lo;
-                    for (int t = lo; t < hi; ++t) {
-                        const int j = sorted[t];
-                        bool m2; const double H2 = height_of(cell_of(list[j]), m2);
-                        rank += (H2 < H) || (H2 == H && j < i);
+                    if (m) sorted[atomicAdd(&hist[RANK_BUCKETS + bucket_of(H)], 1)] = (uint16_t)e;
+                }
+                __syncwarp();
+                int inv_before = 0;                                  // infeasible candidates in earlier trips
+                for (int i0 = 0; i0 < Ktot; i0 += 32) {
+                    const int i = i0 + lane;
+                    const int e = i < Ktot ? list[i] : 0;
+                    const int b = e & 255;
+                    bool m = false; double H = 0.0;
+                    if (i < Ktot) H = height_of(cell_of(e), m);
+                    const uint32_t inv = __ballot_sync(0xffffffffu, i < Ktot && !m);
+                    if (i < Ktot && m) {
+                        const int bk = bucket_of(H);
+                        const int lo = hist[bk], hi = hist[RANK_BUCKETS + bk];   // this bucket's segment of `sorted`
+                        if (lo < sel) {                                  // else everything in it ranks beyond the table
+                            int rank = lo;
+                            for (int t = lo; t < hi; ++t) {
+                                const int e2 = sorted[t];
+                                const double H2 = posz_g[cell_of(e2)];
+                                rank += (H2 < H) || (H2 == H && e2 < e);
+                            }
+                            if (rank < sel) put_row(rank, e >> 8, b & 15, b >> 4, H, 1.0);
+                        }
+                    } else if (i < Ktot) {
+                        const int rank = nvalid + inv_before + __popc(inv & ((1u << lane) - 1u));
+                        if (rank < sel) put_row(rank, e >> 8, b & 15, b >> 4, H, 0.0);
                     }
-                    if (rank < sel) put_row(rank, e >> 8, b & 15, b >> 4, H, m ? 1.0 : 0.0);
+                    inv_before += __popc(inv);
                 }
             }
         }

@@ -41,6 +41,15 @@ def gather_rollout(local, world_size=None, group=None):
     return out
 
 
+class _Works(object):
+    def __init__(self, works):
+        self.works = works
+
+    def wait(self):
+        for w in self.works:
+            w.wait()
+
+
 class AsyncRolloutGather(object):
     """The rollout-end gather taken off the critical path ("overlap with the next step's
     scan"): ``start(local)`` enqueues the all-gather of a finished rollout's tensor on a side stream
@@ -49,10 +58,13 @@ class AsyncRolloutGather(object):
     tensor.  Two output buffers alternate, so a gathered tensor stays valid while the next gather is in
     flight.  On CPU tensors (gloo, the tests) the collective simply runs asynchronously."""
 
-    def __init__(self, world_size=None, group=None):
+    def __init__(self, world_size=None, group=None, point_to_point=False):
         import torch.distributed as dist
         self.world = dist.get_world_size(group) if world_size is None else world_size
         self.group = group
+        self.point_to_point = point_to_point    # the gather as world-1 send/recv pairs (NCCL can serve those with the
+        if point_to_point:                      # copy engines, NCCL_P2P_USE_CUDA_MEMCPY=1) instead of the all-gather kernel
+            self.kind = "nccl send/recv pairs"
         self._bufs = [None, None]
         self._turn = 0
         self._work = None
@@ -83,14 +95,31 @@ class AsyncRolloutGather(object):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             with torch.cuda.stream(self._side):
                 e0.record()
-                dist.all_gather_into_tensor(buf, local, group=self.group)
+                if self.point_to_point:
+                    for w in self._pairs(buf, local):
+                        w.wait()                              # stream-ordered for NCCL: the side stream waits, not the host
+                else:
+                    dist.all_gather_into_tensor(buf, local, group=self.group)
                 e1.record()
             local.record_stream(self._side)
             self.events = (e0, e1)
             self._work = True
+        elif self.point_to_point:
+            self._work = _Works(self._pairs(buf, local))
         else:
             self._work = dist.all_gather_into_tensor(buf, local, group=self.group, async_op=True)
         self._out = buf
+
+    def _pairs(self, buf, local):
+        import torch.distributed as dist
+        me, n = dist.get_rank(self.group), local.shape[0]
+        buf[me * n:(me + 1) * n].copy_(local, non_blocking=True)
+        ops = []
+        for d in range(1, self.world):
+            to, frm = (me + d) % self.world, (me - d) % self.world
+            ops.append(dist.P2POp(dist.isend, local, to, self.group))
+            ops.append(dist.P2POp(dist.irecv, buf[frm * n:(frm + 1) * n], frm, self.group))
+        return dist.batch_isend_irecv(ops)
 
     def finish(self):
         import torch
@@ -246,6 +275,94 @@ class PeerCopyGather(object):
             out = self._inflight
             torch.cuda.current_stream(out.device).wait_stream(self._side)
         self._inflight = None
+        return out
+
+
+class SymmMemGather(object):
+    """The rollout gather by the COPY ENGINES over torch's symmetric memory (``torch.distributed._symmetric_memory``:
+    cuMem allocations mapped into every rank of the node): each rank publishes its shard in a symmetric buffer, a
+    barrier, every rank PULLS the other shards straight into its gathered tensor with device-to-device copies over
+    NVLink, a second barrier releases the buffers.  No SM runs the transfer (the barriers are one-CTA kernels), so
+    unlike an NCCL all-gather kernel it does not take SM slots from the latency-bound step kernels beside it.
+    Same interface as AsyncRolloutGather; falls back to it when symmetric memory cannot be set up (other node,
+    no peer access)."""
+
+    def __init__(self, world_size=None, group=None):
+        import torch.distributed as dist
+        self.world = dist.get_world_size(group) if world_size is None else world_size
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self._hdl = None
+        self._src = None
+        self._bufs = [None, None]
+        self._turn = 0
+        self._side = None
+        self._out = None
+        self._fallback = None
+        self.events = None
+        self.kind = "symmetric-memory pull (copy engines over NVLink)"
+
+    def _setup(self, local):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        group = self.group if self.group is not None else dist.group.WORLD
+        self._src = symm_mem.empty(tuple(local.shape), dtype=local.dtype, device=local.device)
+        self._hdl = symm_mem.rendezvous(self._src, group)
+        self._side = torch.cuda.Stream(device=local.device)
+        self._shape, self._dtype = tuple(local.shape), local.dtype
+
+    def start(self, local):
+        import torch
+        if self._out is not None:
+            raise RuntimeError("a gather is already in flight")
+        local = local.contiguous()
+        if self._fallback is None and self._hdl is None:
+            try:
+                self._setup(local)
+            except Exception as exc:
+                self._fallback = AsyncRolloutGather(self.world, self.group)
+                self.kind = "nccl all-gather (symmetric memory set-up failed: %s: %s)" % (type(exc).__name__, str(exc)[:120])
+        if self._fallback is not None:
+            self._fallback.start(local)
+            self._out = "fallback"
+            return
+        if tuple(local.shape) != self._shape or local.dtype != self._dtype:
+            raise ValueError("the gathered tensor must keep its shape and dtype")
+        n = local.shape[0]
+        t = self._turn
+        self._turn ^= 1
+        buf = self._bufs[t]
+        if buf is None:
+            buf = self._bufs[t] = torch.empty((self.world * n,) + self._shape[1:], dtype=self._dtype, device=local.device)
+        cur = torch.cuda.current_stream(local.device)
+        self._side.wait_stream(cur)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(self._side):
+            e0.record()
+            self._src.copy_(local, non_blocking=True)                # publish
+            self._hdl.barrier()                                      # every shard is published
+            buf[self.rank * n:(self.rank + 1) * n].copy_(local, non_blocking=True)
+            for step in range(1, self.world):                        # rank r starts at r - 1: no two ranks pull from one peer at once
+                r = (self.rank - step) % self.world
+                buf[r * n:(r + 1) * n].copy_(self._hdl.get_buffer(r, self._shape, self._dtype), non_blocking=True)
+            self._hdl.barrier()                                      # every rank is done reading: the buffers may be rewritten
+            e1.record()
+        local.record_stream(self._side)
+        self.events = (e0, e1)
+        self._out = buf
+
+    def finish(self):
+        import torch
+        if self._out is None:
+            raise RuntimeError("no gather in flight")
+        if isinstance(self._out, str):
+            out = self._fallback.finish()
+            self.events = self._fallback.events
+        else:
+            out = self._out
+            torch.cuda.current_stream(out.device).wait_stream(self._side)
+        self._out = None
         return out
 
 

@@ -149,6 +149,40 @@ def test_emulated_kernels_replay_reference_episodes(emu, name, steps):
 
 
 
+@pytest.mark.parametrize("sel", [24, 96])
+def test_emulated_truncation_ranking_small_tables(emu, sel):
+    """Tables much smaller than the candidate set (irregular shapes, R = 8): every step truncates, the kept rows
+    mix feasible and infeasible candidates and equal heights -- the bucketed ranking of phase D against the
+    oracle's stable argsort (binPhy.py:209-212), random feasible-first actions, episodes restarting."""
+    from irbpp_b200 import shapes
+    from oracle.oracle_env import OracleConfig, OracleEnv
+    lib = shapes.make_irregular_library(10, seed=5, num_rotations=8)
+    n = 5
+    seqs = shapes.make_sequences(n, 48, lib.num_shapes, seed=3)
+    env = EmuEnv(emu, lib, seqs, selected_action=sel)
+    cfg = OracleConfig(ZRotNum=8, selectedAction=sel)
+    oracles = [OracleEnv(cfg, lib, seqs[i]) for i in range(n)]
+    obs = env.reset()
+    want = np.stack([o.reset() for o in oracles]).astype(np.float32)
+    assert np.array_equal(obs, want)
+    rng = np.random.default_rng(sel)
+    n_trunc = 0
+    for t in range(14):
+        valid = obs[:, :sel * 5].reshape(n, sel, 5)[:, :, 4] == 1
+        n_trunc += int((obs[:, :sel * 5].reshape(n, sel, 5)[:, sel - 1, :3].sum(1) > 0).sum())
+        acts = np.argmax(rng.random((n, sel)) + valid, axis=1)
+        obs, rew, done, counter, ratio = env.step(acts)
+        for i in range(n):
+            o, r, dn, info = oracles[i].step(int(acts[i]))
+            if dn:
+                o = oracles[i].reset()
+            want[i] = o
+            assert np.float32(r) == rew[i] and bool(dn) == bool(done[i])
+        assert np.array_equal(obs, want), (sel, t)
+    assert n_trunc > 0
+    env.close()
+
+
 def test_emulated_fused_all_possible_observation(emu):
     """get_all_possible_observation as ONE scan + ONE candidates launch over (bin, buffer slot) pairs, k = 10, vs
     the oracle's per-item loop (binPhy.py:171-180); then the protocol goes on (candidate state of slot k-1)."""

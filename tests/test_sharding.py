@@ -55,6 +55,11 @@ def _worker(rank, world, port, n_total, width, out_q):
         busy = torch.ones(4).sum()                     # work that overlaps the collective
         got = g.finish()
         ok = ok and got.shape == (n_total, width) and bool((got[:, 0] == torch.arange(n_total, dtype=torch.float32) + rollout).all())
+    g2 = sharding.AsyncRolloutGather(world, point_to_point=True)      # the same gather as send/recv pairs
+    for rollout in range(2):
+        g2.start(local + 7 * rollout)
+        got = g2.finish()
+        ok = ok and got.shape == (n_total, width) and bool((got[:, 0] == torch.arange(n_total, dtype=torch.float32) + 7 * rollout).all())
     try:
         g.finish(); ok = False                         # nothing in flight
     except RuntimeError:

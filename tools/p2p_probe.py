@@ -54,6 +54,20 @@ if world > 1:
         print("rank %d IPC push via cudaMemcpyAsync(D2D): %.3f ms = %.0f GB/s" % (rank, ms, n * 4 / ms / 1e6), flush=True)
     except Exception as exc:
         print("cuda-python path failed:", repr(exc), flush=True)
+    try:
+        import torch.distributed._symmetric_memory as symm_mem
+        sbuf = symm_mem.empty(n, dtype=torch.float32, device=dev)
+        hdl = symm_mem.rendezvous(sbuf, dist.group.WORLD)
+        sbuf.copy_(src); hdl.barrier(); torch.cuda.synchronize()
+        remote = hdl.get_buffer((rank + 1) % world, (n,), torch.float32)
+        dst = torch.empty(n, dtype=torch.float32, device=dev)
+        ms = timed(lambda: dst.copy_(remote, non_blocking=True))
+        print("rank %d symmetric-memory pull via tensor.copy_: %.3f ms = %.0f GB/s (value check %s)" % (rank, ms, n * 4 / ms / 1e6, bool((dst == 1).all())), flush=True)
+        ms = timed(lambda: remote.copy_(src, non_blocking=True))
+        print("rank %d symmetric-memory push via tensor.copy_: %.3f ms = %.0f GB/s" % (rank, ms, n * 4 / ms / 1e6), flush=True)
+        hdl.barrier(); torch.cuda.synchronize()
+    except Exception as exc:
+        print("symmetric memory path failed:", repr(exc), flush=True)
     out = torch.empty(world * n, dtype=torch.float32, device=dev)
     ms = timed(lambda: dist.all_gather_into_tensor(out, src))
     print("rank %d nccl all_gather_into_tensor: %.3f ms" % (rank, ms), flush=True)
