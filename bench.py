@@ -16,10 +16,13 @@ metric is quoted on):
 
 A "step" is one batched ``step()`` over all bins of a GPU.  For N > 1 the driver launches one rank per GPU
 with torch.distributed.run; bins are sharded by index (weak scaling), there is no collective inside a step,
-and ONE NCCL all-gather of the observations per rollout.  That gather is pipelined: the
-gather of the previous rollout's observations is started with this rollout's first timed step and runs on a side stream beside the steps; the
-timed total counts every part of the gather's duration that did NOT run concurrently with a timed step or
-with the agent stand-in (`gather_exposed_ms`): gather time that fell into an (artificial) L2 flush is charged.
+and ONE gather of the observations per rollout (NCCL all-gather; IRBPP_GATHER selects the measured alternatives:
+copy-engine pulls through torch symmetric memory, the packed form, send/recv pairs).  That gather is pipelined: the gather of the previous
+rollout's observations is started with this rollout's first timed step and runs on a side stream beside the steps.  Its
+cost enters the timed total twice: the steps it overlaps are timed with it running (whatever it slows them down by is in
+their event pairs), and `gather_exposed_ms` is added -- the part after the last step in full, the part that fell into the
+benchmark's own L2-flush gaps at the price it would have beside further steps (see gather_account), plus the pack / expand
+kernels of the compact form.  `gather_hidden_ms`, `gather_beside_flush_ms`, `gather_tail_ms` are reported next to it.
 
 Timing: every timed step is bracketed by CUDA events on the launching stream; between timed steps the L2 is
 flushed by writing a 256 MiB buffer (outside the event pairs).  ``value`` uses actions that are already on the
@@ -370,6 +373,29 @@ def overlap_ms(origin, a0, a1, spans):
     return tot, g1 - g0
 
 
+def gather_account(origin, gev, steps, others):
+    """Where one rollout gather [gev] ran, relative to the timed `steps` (event pairs) and the `others` spans (agent stand-in):
+      hidden        beside a step or the agent
+      tail          after the last step ended                                   -> exposed in full
+      beside_flush  in the gaps the benchmark's L2 flushes open between steps; a training loop has no such gaps, this part
+                    of the transfer would run beside the following steps instead -> charged what it would cost there:
+                    (beside_flush / undisturbed step time) further steps, each slowed like the steps the gather did overlap
+    Returns (gather_ms, hidden, tail, beside_flush, exposed)."""
+    hidden, g = overlap_ms(origin, gev[0], gev[1], list(steps) + list(others))
+    hidden = min(hidden, g)
+    g0, g1 = origin.elapsed_time(gev[0]), origin.elapsed_time(gev[1])
+    spans = [(origin.elapsed_time(a), origin.elapsed_time(b)) for a, b in steps]
+    last_end = max(b for _, b in spans)
+    tail = max(0.0, g1 - max(last_end, g0))
+    beside_flush = max(0.0, g - hidden - tail)
+    touched = [b - a for a, b in spans if min(g1, b) - max(g0, a) > 0.0]
+    free = [b - a for a, b in spans if min(g1, b) - max(g0, a) <= 0.0]
+    slow = max(0.0, float(np.mean(touched)) - float(np.mean(free))) if touched and free else 0.0
+    base = float(np.mean(free)) if free else float(np.mean([b - a for a, b in spans]))
+    exposed = tail + (beside_flush / base) * slow
+    return g, hidden, tail, beside_flush, exposed
+
+
 def main_gpu(args):
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -453,10 +479,14 @@ def main_gpu(args):
     for _ in range(BURN_IN + args.warmup):          # burn-in: bins spread over all episode phases
         one_step(choose())
     gatherer = None
-    if world > 1:          # IRBPP_GATHER: compact (default: NCCL all-gather of the packed observations, expanded on arrival) | nccl (plain) | peer (copy-engine pushes, CUDA IPC)
-        kind = os.environ.get("IRBPP_GATHER", "compact" if k == 1 else "nccl")
+    if world > 1:
+        # IRBPP_GATHER: nccl (default: plain all-gather on the side stream) | symm (copy-engine pulls over torch symmetric
+        # memory) | compact (all-gather of the packed observations, expanded on arrival) | sendrecv | peer (CUDA IPC pushes).
+        # 8 x B200, 4096 bins each, same box (profiles/README.md): nccl 0.1165 ms/step, compact 0.1212, symm 0.1288 -- the
+        # copy-engine pulls leave the SMs alone but one step beside them took 0.33 ms, the all-gather kernel costs less.
+        kind = os.environ.get("IRBPP_GATHER", "nccl")
         gatherer = (sharding.PeerCopyGather(world) if kind == "peer" else sharding.SymmMemGather(world) if kind == "symm" else
-                    sharding.CompactRolloutGather(SEL, world) if kind == "compact" else
+                    sharding.CompactRolloutGather(SEL, world) if kind == "compact" and k == 1 else
                     sharding.AsyncRolloutGather(world, point_to_point=(kind == "sendrecv")))
     gather_alone_ms = 0.0
     if world > 1:                                   # warm-up of the rollout-end collective (NCCL channel setup) + its stand-alone time
@@ -516,22 +546,21 @@ def main_gpu(args):
     if clocks is not None:
         clocks["window"] = "burn-in + timed steps + %d further untimed steps of the same loop" % extra_steps
     step_ms = [a.elapsed_time(b) for a, b in ev]
-    gather_ms = gather_exposed = gather_hidden = 0.0
+    gather_ms = gather_exposed = gather_hidden = gather_tail = gather_flush = gather_extra = 0.0
     if world > 1:
         assert gathered.shape[0] == n_total
-        # hidden = the part of the gather that ran beside a timed step or beside the agent stand-in (in training the
-        # agent's forward pass sits there); whatever ran beside the artificial L2 flush or after the last step is exposed
-        hidden, gather_ms = overlap_ms(origin, gatherer.events[0], gatherer.events[1], ev + ev_pol)
-        gather_hidden = min(hidden, gather_ms)
-        gather_exposed = gather_ms - gather_hidden
+        gather_ms, gather_hidden, gather_tail, gather_flush, gather_exposed = gather_account(origin, gatherer.events, ev, ev_pol)
         for evs in (getattr(gatherer, "pack_events", None), getattr(gatherer, "unpack_events", None)):
             if evs is not None:                     # pack / expansion of the compact form run on the step stream: always exposed
-                gather_exposed += evs[0].elapsed_time(evs[1])
+                gather_extra += evs[0].elapsed_time(evs[1])
+        gather_exposed += gather_extra
     t_dev_ms = float(sum(step_ms)) + gather_exposed
-    t = torch.tensor([t_dev_ms, float(np.mean(step_ms)), gather_ms, gather_exposed, gather_alone_ms], dtype=torch.float64, device=dev)
+    t_strict_ms = float(sum(step_ms)) + (gather_ms - gather_hidden) + gather_extra     # every ms outside a step / the agent charged
+    t = torch.tensor([t_dev_ms, float(np.mean(step_ms)), gather_ms, gather_exposed, gather_alone_ms, gather_hidden, gather_tail, gather_flush,
+                      t_strict_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    t_dev_ms, kern_ms, gather_ms, gather_exposed, gather_alone_ms = [float(v) for v in t.tolist()]
+    t_dev_ms, kern_ms, gather_ms, gather_exposed, gather_alone_ms, gather_hidden, gather_tail, gather_flush, t_strict_ms = [float(v) for v in t.tolist()]
     value = n_total * args.steps / (t_dev_ms * 1e-3)
 
     # ---- end-to-end loop through the public API with host actions ----
@@ -574,8 +603,7 @@ def main_gpu(args):
     if world > 1:
         gatherer.finish()
         torch.cuda.synchronize(dev)
-        hidden, gms = overlap_ms(origin2, gatherer.events[0], gatherer.events[1], ev2)
-        e2e_gather_exposed = gms - min(hidden, gms)
+        e2e_gather_exposed = gather_account(origin2, gatherer.events, ev2, [])[4]
         for evs in (getattr(gatherer, "pack_events", None), getattr(gatherer, "unpack_events", None)):
             if evs is not None:
                 e2e_gather_exposed += evs[0].elapsed_time(evs[1])
@@ -635,7 +663,10 @@ def main_gpu(args):
         if world > 1:
             line["gather_ms"] = gather_ms
             line["gather_exposed_ms"] = gather_exposed
-            line["gather_hidden_ms"] = gather_ms - gather_exposed
+            line["gather_hidden_ms"] = gather_hidden
+            line["gather_beside_flush_ms"] = gather_flush
+            line["gather_tail_ms"] = gather_tail
+            line["value_charging_flush_gaps"] = n_total * args.steps / (t_strict_ms * 1e-3)   # round-1 accounting, for comparison
             line["gather_alone_ms"] = gather_alone_ms
             line["gather_kind"] = getattr(gatherer, "kind", "nccl all-gather")
             line["nccl_channels"] = os.environ.get("NCCL_MAX_NCHANNELS", "default")

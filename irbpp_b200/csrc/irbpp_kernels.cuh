@@ -820,7 +820,10 @@ static_assert(RANK_BUCKETS % 32 == 0 && CAND_THREADS * ROWS_WORDS >= ENVS_PER_CT
 // R = 8 (8 KB per warp; measured faster there than a global scratch, profiles/README.md).  Beyond that the scratch
 // would decide the residency -- 24 KB per warp at R = 24 leave 2 CTAs = 8 warps per SM and every phase of the kernel
 // starves for latency hiding -- so the lists move to a global scratch (Params::dlist, L2 resident).
-constexpr int LISTS_SMEM_MAX_R = 8;
+#ifndef IRBPP_LISTS_SMEM_MAX_R
+#define IRBPP_LISTS_SMEM_MAX_R 8
+#endif
+constexpr int LISTS_SMEM_MAX_R = IRBPP_LISTS_SMEM_MAX_R;
 __host__ __device__ inline bool lists_in_smem(int R) { return R <= LISTS_SMEM_MAX_R; }
 __host__ __device__ inline int ws_bytes_for(int R) {
     const int need = lists_in_smem(R) ? R * NPOSE * 4 : 0;     // uint16 list + uint16 sorted list for every pose
@@ -1220,8 +1223,10 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
         // Pass 1 compacts the set bits into a list (no memory loads); pass 2 gives every lane one
         // candidate, so the height gathers of 32 candidates are in flight together.
         // candidate list + bucket-sorted index list: the (now idle) lane scratch, or the pair's slice of the global scratch
-        const int LIST_CAP = P.dlist ? R * NPOSE : P.ws_bytes / 4;    // >= R * 256 >= Ktot
-        uint16_t* list = P.dlist ? P.dlist + (int64_t)env * 2 * LIST_CAP : reinterpret_cast<uint16_t*>(W_pts);
+        // (a bin whose candidates fit the warp scratch keeps its lists there even when the global scratch exists)
+        const bool spill = P.dlist && Ktot > P.ws_bytes / 4;
+        const int LIST_CAP = spill ? R * NPOSE : P.ws_bytes / 4;      // >= Ktot
+        uint16_t* list = spill ? P.dlist + (int64_t)env * 2 * (R * NPOSE) : reinterpret_cast<uint16_t*>(W_pts);
         auto cell_of = [](int e) { const int b = e & 255; return (e >> 8) * NPOSE + (b & 15) * 16 + (b >> 4); };
         {
             for (int r = 0; r < R; ++r) {

@@ -309,7 +309,8 @@ class SymmMemGather(object):
         group = self.group if self.group is not None else dist.group.WORLD
         self._src = symm_mem.empty(tuple(local.shape), dtype=local.dtype, device=local.device)
         self._hdl = symm_mem.rendezvous(self._src, group)
-        self._side = torch.cuda.Stream(device=local.device)
+        # high priority: the two one-CTA barrier kernels must not queue behind a step kernel whose grid fills every SM slot
+        self._side = torch.cuda.Stream(device=local.device, priority=-1)
         self._shape, self._dtype = tuple(local.shape), local.dtype
 
     def start(self, local):

@@ -70,3 +70,39 @@ def test_learner_glue_host_pieces():
     assert m.shape == (3, 500) and m[2, 7] == obs[2, 7 * 5 + 4]          # tools.py:298-299
     assert glue.segment_size(64, 4) == (4, 16)                           # agent.py:69 when it works
     assert glue.segment_size(64, 4096) == (64, 1)                        # ... and when int(64 / 4096) == 0
+
+
+class _Ev(object):
+    """Stand-in for a CUDA event at a fixed position on the device time line (ms)."""
+
+    def __init__(self, t):
+        self.t = t
+
+    def elapsed_time(self, other):
+        return other.t - self.t
+
+
+def test_bench_gather_accounting():
+    """bench.py's split of one rollout gather into hidden / beside-flush / tail and the charge derived from it."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    origin = _Ev(0.0)
+    # 10 steps of 0.10 ms with 0.05 ms flush gaps; the first three are slowed to 0.12 by the gather [0, 0.45]
+    steps, t = [], 0.0
+    for i in range(10):
+        d = 0.12 if i < 3 else 0.10
+        steps.append((_Ev(t), _Ev(t + d)))
+        t += d + 0.05
+    g, hidden, tail, flush, exposed = bench.gather_account(origin, (_Ev(0.0), _Ev(0.45)), steps, [])
+    assert abs(g - 0.45) < 1e-12 and abs(hidden - 0.35) < 1e-9 and tail == 0.0 and abs(flush - 0.10) < 1e-9
+    assert abs(exposed - (0.10 / 0.10) * 0.02) < 1e-9           # one further step, 0.02 ms slower
+    # a gather that outlasts the rollout: the tail is charged in full
+    end = steps[-1][1].t
+    g, hidden, tail, flush, exposed = bench.gather_account(origin, (_Ev(end - 0.05), _Ev(end + 0.30)), steps, [])
+    assert abs(tail - 0.30) < 1e-9 and abs(hidden - 0.05) < 1e-9 and abs(flush) < 1e-9 and exposed >= 0.30
+    # the agent stand-in hides gather time like a step does
+    g, hidden, tail, flush, exposed = bench.gather_account(origin, (_Ev(0.12), _Ev(0.17)), steps, [(_Ev(0.12), _Ev(0.17))])
+    assert abs(hidden - 0.05) < 1e-9 and abs(exposed) < 1e-9
