@@ -28,6 +28,7 @@ struct irbpp_env {
     irbpp_config cfg;
     Params P;                      // device pointers + configuration (mode/inputs filled per launch)
     int cand_smem = 0, scan_smem = 0;
+    int epc = ENVS_PER_CTA_NARROW;       // bins per CTA of the candidates kernel (envs_per_cta_for(R))
     std::string err;
     bool shapes_loaded = false, sequences_set = false, was_reset = false, waiting_step = false;
     bool scan_current = false;        // the scan scratch holds the drop heights of every bin's cur_item
@@ -117,15 +118,17 @@ static void free_dev(irbpp_env* h, void* p) {
 
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-function, PER-DEVICE attribute: the largest value any
 // handle needed is tracked per device ordinal and only ever raised (several handles may coexist on a device,
-// and one process may hold handles on several devices).  which: 0 candidates kernel, 1 scan kernel, 2 shape encoder.
+// and one process may hold handles on several devices).  which: 0 / 3 candidates kernel (narrow / wide CTA), 1 scan kernel, 2 shape encoder.
 static cudaError_t raise_dynamic_smem(int device, int which, int bytes) {
-    static int raised[64][3];
+    static int raised[64][4];
     static std::mutex mu;
     std::lock_guard<std::mutex> lk(mu);
     if (device < 0 || device >= 64) return cudaErrorInvalidDevice;
     if (bytes <= raised[device][which]) return cudaSuccess;
     cudaError_t e = which == 0
-        ? cudaFuncSetAttribute(irbpp_candidates_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)
+        ? cudaFuncSetAttribute(irbpp_candidates_kernel<ENVS_PER_CTA_NARROW>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)
+        : which == 3
+        ? cudaFuncSetAttribute(irbpp_candidates_kernel<ENVS_PER_CTA_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)
         : (which == 1 ? cudaFuncSetAttribute(irbpp_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes)
                       : cudaFuncSetAttribute(irbpp_shape_encode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     if (e == cudaSuccess) raised[device][which] = bytes;
@@ -190,7 +193,11 @@ int irbpp_create(const irbpp_config* cfg, irbpp_handle* out) {
     P.resA = cfg->resolution_act;
     P.binvol = (cfg->bin_dimension[0] * cfg->bin_dimension[1]) * cfg->bin_dimension[2];   // np.prod
     P.ws_bytes = ws_bytes_for(P.R);
-    h->cand_smem = (int)((sizeof(CandSmem) + 15) & ~(size_t)15) + CAND_WARPS * P.ws_bytes + ENVS_PER_CTA * P.R * 8 * 4;
+    h->epc = envs_per_cta_for(P.R);                  // bins (= warps) per CTA of the candidates kernel
+    {
+        const size_t fixed = h->epc == ENVS_PER_CTA_WIDE ? sizeof(CandSmem<ENVS_PER_CTA_WIDE>) : sizeof(CandSmem<ENVS_PER_CTA_NARROW>);
+        h->cand_smem = (int)((fixed + 15) & ~(size_t)15) + h->epc * P.ws_bytes + h->epc * P.R * 8 * 4;
+    }
 
 #define TRY_ALLOC(expr)                                                                          \
     do { cudaError_t e2_ = (expr); if (e2_ != cudaSuccess) {                                      \
@@ -230,7 +237,7 @@ int irbpp_create(const irbpp_config* cfg, irbpp_handle* out) {
         P.r_valid = reinterpret_cast<uint8_t*>(b); b += N;
         P.r_error = reinterpret_cast<uint8_t*>(b);
     }
-    TRY_ALLOC(raise_dynamic_smem(cfg->device, 0, h->cand_smem));
+    TRY_ALLOC(raise_dynamic_smem(cfg->device, h->epc == ENVS_PER_CTA_WIDE ? 3 : 0, h->cand_smem));
 #undef TRY_ALLOC
     *out = h;
     return IRBPP_OK;
@@ -446,13 +453,14 @@ static int launch(irbpp_env* h, Params& P, cudaStream_t s) {
         // programmatic dependent launch: the candidates grid is scheduled while the scan grid's last
         // wave drains and waits at griddepcontrol.wait for the scan's completion
         cudaLaunchConfig_t lc = {};
-        lc.gridDim = dim3((units + ENVS_PER_CTA - 1) / ENVS_PER_CTA); lc.blockDim = dim3(CAND_THREADS);
+        lc.gridDim = dim3((units + h->epc - 1) / h->epc); lc.blockDim = dim3(32 * h->epc);
         lc.dynamicSmemBytes = (size_t)h->cand_smem; lc.stream = s;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[0].val.programmaticStreamSerializationAllowed = (P.mode == MODE_DEBUG_HULLS) ? 0 : 1;
         lc.attrs = at; lc.numAttrs = 1;
-        cudaLaunchKernelEx(&lc, irbpp_candidates_kernel, P);
+        if (h->epc == ENVS_PER_CTA_WIDE) cudaLaunchKernelEx(&lc, irbpp_candidates_kernel<ENVS_PER_CTA_WIDE>, P);
+        else cudaLaunchKernelEx(&lc, irbpp_candidates_kernel<ENVS_PER_CTA_NARROW>, P);
         h->launches += 1;
     }
     cudaError_t e = cudaGetLastError();

@@ -46,16 +46,22 @@ constexpr int STEP = 2;                  // stepSize = resolutionAct / resolutio
 constexpr int NPOSE = AX * AY;           // 256 poses per rotation
 constexpr int CTA_THREADS = 128;
 constexpr int CTA_WARPS = CTA_THREADS / 32;
+// CTA shapes of the candidates kernel (one warp per bin): 4 bins per CTA up to four rotations, 8 from WIDE_MIN_R rotations on.
+// Measured (profiles/README.md, round 2 sweep): BlockOut R = 4  0.109 ms with 4 bins / 0.126 with 8 (512 CTAs of 62 KB no longer
+// fit one wave); irregular R = 8  0.370 / 0.355; R = 24  2.91 / 2.28 -- with many rotations a CTA's fixed phases amortise over
+// more images and the task deal balances over 256 lanes.  Fewer than 4 bins, or more warps than bins, lost everywhere.
 #ifndef IRBPP_ENVS_PER_CTA
 #define IRBPP_ENVS_PER_CTA 4
 #endif
-constexpr int ENVS_PER_CTA = IRBPP_ENVS_PER_CTA;   // bins (= warps) per CTA of the candidates kernel
-#ifndef IRBPP_CAND_WARPS
-#define IRBPP_CAND_WARPS ENVS_PER_CTA
+#ifndef IRBPP_ENVS_PER_CTA_WIDE
+#define IRBPP_ENVS_PER_CTA_WIDE 8
 #endif
-constexpr int CAND_WARPS = IRBPP_CAND_WARPS;          // warps per CTA of the candidates kernel (>= ENVS_PER_CTA)
-constexpr int CAND_THREADS = 32 * CAND_WARPS;
-static_assert(CAND_WARPS >= ENVS_PER_CTA, "phase D needs one warp per bin");
+#ifndef IRBPP_WIDE_MIN_R
+#define IRBPP_WIDE_MIN_R 8
+#endif
+constexpr int ENVS_PER_CTA_NARROW = IRBPP_ENVS_PER_CTA;
+constexpr int ENVS_PER_CTA_WIDE = IRBPP_ENVS_PER_CTA_WIDE;
+__host__ __device__ inline int envs_per_cta_for(int R) { return R >= IRBPP_WIDE_MIN_R ? ENVS_PER_CTA_WIDE : ENVS_PER_CTA_NARROW; }
 constexpr int MAX_LEVELS = 64;           // level-image slots per (bin, rotation) in the scratch
 #ifndef IRBPP_TASKS_PER_LANE
 #define IRBPP_TASKS_PER_LANE 3
@@ -815,13 +821,14 @@ __global__ void __launch_bounds__(CTA_THREADS) irbpp_heuristic_kernel(const Para
 constexpr int WS_MIN_BYTES = 4096;
 static_assert(WS_MIN_BYTES >= 2 * BIG_CAP && WS_MIN_BYTES >= FAST_CAP * 32, "overflow buffers must fit the lane scratch");
 constexpr int RANK_BUCKETS = 256;                        // height buckets of the phase-D truncation ranking (per warp: bases + cursors)
-static_assert(RANK_BUCKETS % 32 == 0 && CAND_THREADS * ROWS_WORDS >= ENVS_PER_CTA * 2 * RANK_BUCKETS, "phase D's rank histograms reuse the image slots");
-// Phase D's candidate list + bucket-sorted index list (2 x uint16 per pose of the bin) live in the warp scratch up to
-// R = 8 (8 KB per warp; measured faster there than a global scratch, profiles/README.md).  Beyond that the scratch
-// would decide the residency -- 24 KB per warp at R = 24 leave 2 CTAs = 8 warps per SM and every phase of the kernel
-// starves for latency hiding -- so the lists move to a global scratch (Params::dlist, L2 resident).
+static_assert(RANK_BUCKETS % 32 == 0 && 32 * ROWS_WORDS >= 2 * RANK_BUCKETS, "phase D's rank histograms reuse the image slots (one warp's share each)");
+// Phase D's candidate list + bucket-sorted entry list (2 x uint16 per candidate): up to R = 4 the warp scratch holds them for
+// every pose of the bin (4 KB).  Beyond that a worst-case sized scratch would decide the residency (8 KB per warp at R = 8:
+// 4 CTAs per SM in two waves, 12.7 warps active; 24 KB at R = 24: 2 CTAs), so the scratch stays at 4 KB, a bin whose
+// candidates fit it (Ktot <= 1024, the usual case at R = 8) keeps its lists there and only a larger one spills to a global
+// scratch (Params::dlist, L2 resident).  Measured: irregular R = 8  0.390 -> 0.370 ms per step, R = 24 unchanged.
 #ifndef IRBPP_LISTS_SMEM_MAX_R
-#define IRBPP_LISTS_SMEM_MAX_R 8
+#define IRBPP_LISTS_SMEM_MAX_R 4
 #endif
 constexpr int LISTS_SMEM_MAX_R = IRBPP_LISTS_SMEM_MAX_R;
 __host__ __device__ inline bool lists_in_smem(int R) { return R <= LISTS_SMEM_MAX_R; }
@@ -830,7 +837,9 @@ __host__ __device__ inline int ws_bytes_for(int R) {
     return ((need > WS_MIN_BYTES ? need : WS_MIN_BYTES) + 15) & ~15;
 }
 
+template <int EPC>
 struct CandSmem {
+    static constexpr int ENVS_PER_CTA = EPC, CAND_WARPS = EPC, CAND_THREADS = 32 * EPC;
     uint32_t slots[CAND_THREADS * ROWS_WORDS];            // level images of this round in padded row form (one per thread)
     uint16_t task_tab[TASK_TAB];                          // micro-task m < TASK_TAB: slot << 8 | x << 4 | y of its start pixel
     int32_t pre[ENVS_PER_CTA * MAX_ROT + 1];              // prefix of level counts over (bin, rotation)
@@ -845,9 +854,11 @@ struct CandSmem {
     int32_t error[ENVS_PER_CTA];
 };
 
-__global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Params P) {
+template <int EPC>
+__global__ void __launch_bounds__(32 * EPC) irbpp_candidates_kernel(const Params P) {
+    constexpr int ENVS_PER_CTA = EPC, CAND_WARPS = EPC, CAND_THREADS = 32 * EPC;     // one warp per bin
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    CandSmem& S = *reinterpret_cast<CandSmem*>(smem_raw);
+    CandSmem<EPC>& S = *reinterpret_cast<CandSmem<EPC>*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int env0 = P.env_lo + blockIdx.x * ENVS_PER_CTA;
     const int nenv = min(ENVS_PER_CTA, P.env_hi - env0);
@@ -897,7 +908,7 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
     };
 
     // dynamic tail: CAND_WARPS blocks of P.ws_bytes, then the 256-bit candidate sets per (bin, rotation)
-    uint32_t* candbits = reinterpret_cast<uint32_t*>(smem_raw + ((sizeof(CandSmem) + 15) & ~(size_t)15) + (size_t)CAND_WARPS * P.ws_bytes);
+    uint32_t* candbits = reinterpret_cast<uint32_t*>(smem_raw + ((sizeof(CandSmem<EPC>) + 15) & ~(size_t)15) + (size_t)CAND_WARPS * P.ws_bytes);
     for (int i = tid; i < ENVS_PER_CTA * R * 8; i += CAND_THREADS) candbits[i] = 0u;
     if (tid < ENVS_PER_CTA) S.error[tid] = 0;
     if (warp == 0) {   // prefix of the level counts over the (bin, rotation) pairs, 32 pairs per step
@@ -917,7 +928,7 @@ __global__ void __launch_bounds__(CAND_THREADS) irbpp_candidates_kernel(const Pa
     __syncthreads();
     const int nimg = S.pre[npairs];
     trace(1);
-    unsigned char* ws_base = smem_raw + ((sizeof(CandSmem) + 15) & ~(size_t)15);     // CAND_WARPS blocks of P.ws_bytes
+    unsigned char* ws_base = smem_raw + ((sizeof(CandSmem<EPC>) + 15) & ~(size_t)15);     // CAND_WARPS blocks of P.ws_bytes
     uint8_t* W_pts = ws_base + (size_t)warp * P.ws_bytes;
 
     // ---- phase C: rounds of CAND_THREADS level images; inside a round one (image, start pixel) per lane ----

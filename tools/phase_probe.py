@@ -37,9 +37,10 @@ for _ in range(n):
     obs, _ = env.step_device(bench.device_policy(torch, obs, gen))
 c = env.debug_phase_cycles(False).astype(np.float64) / n
 scan_ctas = N_ENVS
-cand_ctas = N_ENVS // 4
+bins_per_cta = 8 if lib.num_rotations >= 8 else 4          # envs_per_cta_for(R), csrc/irbpp_kernels.cuh
+cand_ctas = N_ENVS // bins_per_cta
 fine = "fine" in os.path.basename(os.environ.get("IRBPP_LIB", ""))
-out = {"lib": os.environ.get("IRBPP_LIB", "default"), "config": CONFIG,
+out = {"lib": os.environ.get("IRBPP_LIB", "default"), "config": CONFIG, "bins_per_candidates_cta": bins_per_cta,
        "scan_kernel_cycles_per_cta": {"load + apply action (phase A)": round(c[0] / scan_ctas),
                                       "observation, pose scan, level bitmaps": round(c[1] / scan_ctas)},
        "candidates_kernel_cycles_per_cta": {"contour tasks (phase C)": round(c[2] / cand_ctas),
