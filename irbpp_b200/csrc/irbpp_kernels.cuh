@@ -11,7 +11,7 @@
 //        floor_divide semantics (cvTools.py:78-79); one 16x16 bitmap per (rotation, level) by warp
 //        ballots -> global scratch (L2 resident).  Tables that are constant on square blocks of cells
 //        (voxel shapes) are scanned from block maxima of the heightmap (TileEntry lists)
-//   irbpp_candidates_kernel  one CTA (128 threads) per 4 bins
+//   irbpp_candidates_kernel  one CTA per 4 bins (up to four rotations) or 8 bins (from R = 8), one warp per bin
 //     C  candidate extraction (cvTools.py:61-103): the (bin, rotation, level) images of the CTA are
 //        ordered by a cost key; every (image, start pixel) pair is one lane's task, dealt in that order
 //        so that the lanes of a warp carry contours of similar length: border following, then (after
