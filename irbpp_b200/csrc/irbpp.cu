@@ -28,6 +28,8 @@ struct irbpp_env {
     irbpp_config cfg;
     Params P;                      // device pointers + configuration (mode/inputs filled per launch)
     int cand_smem = 0, scan_smem = 0;
+    uint32_t* ready_dev = nullptr;       // scan -> candidates hand-over flags (one per unit)
+    uint32_t epoch = 0;                  // launch counter behind the flags
     int epc = ENVS_PER_CTA_NARROW;       // bins per CTA of the candidates kernel (envs_per_cta_for(R))
     std::string err;
     bool shapes_loaded = false, sequences_set = false, was_reset = false, waiting_step = false;
@@ -215,6 +217,7 @@ int irbpp_create(const irbpp_config* cfg, irbpp_handle* out) {
     TRY_ALLOC(dev_alloc(h, &P.bitmaps, units * P.R * MAX_LEVELS * 8));
     TRY_ALLOC(dev_alloc(h, &P.nlevels, units * P.R));
     if (!lists_in_smem(P.R)) TRY_ALLOC(dev_alloc(h, &P.dlist, units * 2 * P.R * NPOSE));
+    TRY_ALLOC(dev_alloc(h, &h->ready_dev, units));        // zeroed: no launch has epoch 0
     // result block (8-byte fields first so every array stays aligned)
     h->results_bytes = (size_t)N * (8 + 8 + 4 + 4 + 4 + 1 + 1 + 1);
     TRY_ALLOC(cudaMalloc(&h->results_dev, h->results_bytes + 64));
@@ -441,11 +444,23 @@ int irbpp_set_item_rng(irbpp_handle h, uint64_t seed) {
 // candidates kernel when the observation carries candidate rows.  (Running bin ranges on separate
 // streams so that one range's candidates kernel overlaps the next range's scan kernel was measured:
 // no gain -- the scan kernel owns the whole register file, the two cannot co-reside.)
+// IRBPP_HANDOVER=grid restores the grid-wide wait (measurement switch)
+static bool flags_enabled() {
+    static const bool on = [] { const char* e = getenv("IRBPP_HANDOVER"); return !(e && strcmp(e, "grid") == 0); }();
+    return on;
+}
+
 static int launch(irbpp_env* h, Params& P, cudaStream_t s) {
     // the units of a launch: bins, or (bin, buffer slot) pairs for get_all_possible_observation
     const int units = (P.mode == MODE_ALL_OBS) ? P.N * P.K : P.N;
     P.env_lo = 0;
     P.env_hi = units;
+    // per-unit hand-over flags instead of the grid-wide dependency wait.  Not for caller-supplied maps (the levels kernel
+    // sets none) and not for the fused all-slot pass (the k scan CTAs of a bin share its state and candidate table, which
+    // the candidates CTA of the last slot rewrites: that one must wait for all of them)
+    P.ready = (P.mode == MODE_DEBUG_HULLS || P.mode == MODE_ALL_OBS || !flags_enabled()) ? nullptr : h->ready_dev;
+    if (++h->epoch == 0) h->epoch = 1;
+    P.epoch = h->epoch;
     if (P.mode == MODE_DEBUG_HULLS) irbpp_levels_kernel<<<P.N, CTA_THREADS, 0, s>>>(P);
     else irbpp_scan_kernel<<<units, CTA_THREADS, h->scan_smem, s>>>(P);
     h->launches += 1;

@@ -161,6 +161,8 @@ struct Params {
     const int32_t* dbg_items;            // MODE_DEBUG_SCAN
     int32_t ws_bytes;                    // per-warp scratch of the candidates kernel (ws_bytes_for(R))
     uint16_t* dlist;                     // [units][2][R*256] phase D lists for R > LISTS_SMEM_MAX_R, else NULL
+    uint32_t* ready;                     // [units] hand-over flags: the scan CTA of a unit stores `epoch` when its scratch is written (NULL: grid-wide wait)
+    uint32_t epoch;                      // value of this launch (never 0)
     int32_t pose_actions;                // MODE_STEP: actions are flat poses (rot*256 + lx*16 + ly), not candidate rows
     int32_t heur_method, heur_dir;       // heuristic kernel: Heuristic, dirIdx 0..3 (space.py:162-166)
     int32_t* heur_pose;                  // [N][3] rot, lx, ly
@@ -412,6 +414,31 @@ __device__ __forceinline__ bool scan_rotation_dense(const Params& P, const doubl
     return any != 0;
 }
 
+// ---- scan -> candidates hand-over flags -------------------------------------------------------------------
+// The candidates grid is launched programmatically (PDL) and becomes resident while the scan grid's last wave
+// drains (3.46 waves on the bench workload: for ~13 us about half the SM slots have no scan CTA).  Waiting there
+// for the WHOLE scan grid (griddepcontrol.wait) wastes that time for every bin of an earlier wave, so a scan CTA
+// publishes a per-unit flag (release) once its part of the scratch is written and a candidates CTA starts as soon
+// as the flags of ITS bins carry this launch's epoch (acquire).  No deadlock: the scan CTAs trigger the dependent
+// launch at their start, so a candidates CTA exists only when every scan CTA is resident; and a poll that runs out
+// falls back to the grid-wide wait.
+#ifdef IRBPP_HOST_EMULATION
+static inline void ready_publish(uint32_t* f, uint32_t v) { __atomic_store_n(f, v, __ATOMIC_RELEASE); }
+static inline uint32_t ready_peek(const uint32_t* f) { return __atomic_load_n(f, __ATOMIC_ACQUIRE); }
+static inline void grid_dependency_wait() {}
+static inline void backoff() {}
+#else
+__device__ __forceinline__ void ready_publish(uint32_t* f, uint32_t v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(f), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ready_peek(const uint32_t* f) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+    return v;
+}
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void backoff() { __nanosleep(100); }
+#endif
+constexpr int READY_POLLS = 1 << 16;       // ~10 ms of polling before the fallback
+
 // ---- scan kernel ------------------------------------------------------------------------------------------
 #ifndef IRBPP_SCAN_MIN_CTAS
 #define IRBPP_SCAN_MIN_CTAS 8
@@ -436,7 +463,10 @@ __global__ void __launch_bounds__(CTA_THREADS, IRBPP_SCAN_MIN_CTAS) irbpp_scan_k
     const int env = (mode == MODE_ALL_OBS) ? vb / P.K : vb;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     asm volatile("griddepcontrol.launch_dependents;");      // the candidates grid may be scheduled as this one drains (PDL)
-    if (mode == MODE_RESET && P.which && !P.which[env]) return;
+    if (mode == MODE_RESET && P.which && !P.which[env]) {
+        if (P.ready && tid == 0) ready_publish(P.ready + vb, P.epoch);      // nothing to hand over, nobody shall wait
+        return;
+    }
     long long t_prev = P.phase_cycles ? clock64() : 0;
     auto phase_mark = [&](int idx) {
         if (P.phase_cycles && tid == 0) {
@@ -711,6 +741,13 @@ __global__ void __launch_bounds__(CTA_THREADS, IRBPP_SCAN_MIN_CTAS) irbpp_scan_k
             if (warp == 0) reinterpret_cast<uint32_t*>(P.state + env)[lane] = reinterpret_cast<const uint32_t*>(&st_s)[lane];
         }
     }
+    if (P.ready) {
+        // hand-over: all writes of the CTA (scratch, observation, state) happen-before thread 0's release store through
+        // the block barrier -- a release is cumulative over what its thread has synchronised with -- so one fence per
+        // CTA (the MEMBAR.GPU inside st.release) is enough
+        __syncthreads();
+        if (tid == 0) ready_publish(P.ready + vb, P.epoch);
+    }
     phase_mark(1);   // observation heightmap, write-back, scan, level bitmaps
 }
 
@@ -862,7 +899,19 @@ __global__ void __launch_bounds__(32 * EPC) irbpp_candidates_kernel(const Params
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int env0 = P.env_lo + blockIdx.x * ENVS_PER_CTA;
     const int nenv = min(ENVS_PER_CTA, P.env_hi - env0);
-    asm volatile("griddepcontrol.wait;" ::: "memory");      // PDL: scan grid complete, its scratch writes visible
+    if (P.ready) {                                          // start when the scans of THIS CTA's bins are done (see ready_publish)
+        if (tid < nenv) {
+            const uint32_t* f = P.ready + env0 + tid;
+            int polls = 0;
+            while (ready_peek(f) != P.epoch) {
+                if (++polls > READY_POLLS) { grid_dependency_wait(); break; }
+                backoff();
+            }
+        }
+        __syncthreads();
+    } else {
+        grid_dependency_wait();                             // PDL: scan grid complete, its scratch writes visible
+    }
     const int R = P.R;
     const int npairs = nenv * R;
     long long t_prev = P.phase_cycles ? clock64() : 0;
@@ -1164,6 +1213,9 @@ __global__ void __launch_bounds__(32 * EPC) irbpp_candidates_kernel(const Params
     __syncthreads();
     trace(5);
     phase_mark(2);   // contour tasks
+    // the scan grid has long completed; waiting for it formally keeps the stream-order guarantee of a dependent launch
+    // (this grid does not complete before its prerequisite) without delaying the start
+    if (P.ready && tid == 0) grid_dependency_wait();
 
     // ---- phase D: warp w serves bin env0 + w ----
     if (warp >= nenv) return;
