@@ -1,9 +1,11 @@
 #!/usr/bin/env python
 """Build experiment variants of the library next to the default one and (on a GPU box) compare them.
 
-    python tools/variants.py build coop=-DIRBPP_COOP_APPROX fine=-DIRBPP_PROBE_FINE
-        -> irbpp_b200/lib/libirbpp_coop.so, libirbpp_fine.so   (they travel with gpurun like the default .so)
-    python tools/variants.py bench coop            # GPU: parity tests of the episode goldens + bench.py per variant
+    python tools/variants.py build e8=-DIRBPP_ENVS_PER_CTA=8 tpl2=-DIRBPP_TASKS_PER_LANE=2 fine=-DIRBPP_PROBE_FINE
+        -> irbpp_b200/lib/libirbpp_e8.so, libirbpp_tpl2.so, libirbpp_fine.so   (they travel with gpurun like the default .so;
+           several -D flags of one variant are separated by commas)
+    python tools/variants.py bench e8 tpl2         # GPU: parity tests of the episode goldens + bench.py per variant
+    IRBPP_LIB=irbpp_b200/lib/libirbpp_e8.so python tools/kbench.py    # or time one build on several workloads (tools/gpu/call19.sh)
 
 Known build switches (csrc/): IRBPP_PROBE_FINE   slots 4-7 of the phase counters time the sub-phases of phase C
                               IRBPP_PROBE_TRACE  per-CTA timelines of the candidates kernel (tools/cta_trace.py)
